@@ -1,0 +1,101 @@
+// sde_aot.cu — ahead-of-time instantiation of every path kernel for the built-in functors.
+// Compiled twice: -DSDE_STRICT=0 (FMA contraction, hoisted forms; the throughput path) and
+// -DSDE_STRICT=1 -fmad=false (reference operation order; bit-identical to the CPU oracle).
+#include "sde_models_builtin.cuh"
+#include "sde_ktable.h"
+
+using sdeb200::BlackScholes;
+using sdeb200::Heston;
+
+namespace sdeb200 {
+// wiener!(w, Δt) (src/simulation.jl:22-35) is the in-place running sum w[i] = w[i-1] + sqrt(Δt)*z: the
+// Euler–Maruyama recursion of dX_d = dW_d.  Only the reference-layout trajectory kernel is instantiated.
+template <int DIM> struct WienerN {
+  static constexpr int D = DIM, M = DIM, NP = 0;
+  template <typename T> SDE_HD static void prepare(const T *, T, T *) {}
+  template <int SCHEME, typename T> SDE_HD static void step(const T *, T, T, const T *dw, T *x) {
+#pragma unroll
+    for (int d = 0; d < DIM; d++) x[d] = x[d] + dw[d];
+  }
+};
+}  // namespace sdeb200
+
+#if SDE_STRICT
+#define TAGGED(name) name##_s
+#define SDE_AOT_TABLE sde_aot_table_strict
+#define SDE_AOT_WIENER sde_aot_wiener_strict
+#else
+#define TAGGED(name) name##_f
+#define SDE_AOT_TABLE sde_aot_table_fast
+#define SDE_AOT_WIENER sde_aot_wiener_fast
+#endif
+#define XSCHEME(MODEL, TAG, SCH, SNAME) SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)
+#define XCOEF(MODEL, TAG) SDE_KERNELS_COEF(MODEL, TAG)
+#define XFILL(T, TAG, s, SNAME) XFILL2(T, TAG, s, SNAME)
+#define XFILL2(T, TAG, s, SNAME)                                                      \
+  T.sample[s][0] = (const void *)sdek_##TAG##_sample_##SNAME##_f64;                    \
+  T.sample[s][1] = (const void *)sdek_##TAG##_sample_##SNAME##_f32;                    \
+  T.mlmc[s][0] = (const void *)sdek_##TAG##_mlmc_##SNAME##_f64;                        \
+  T.mlmc[s][1] = (const void *)sdek_##TAG##_mlmc_##SNAME##_f32;                        \
+  T.simsoa[s][0] = (const void *)sdek_##TAG##_simsoa_##SNAME##_f64;                    \
+  T.simsoa[s][1] = (const void *)sdek_##TAG##_simsoa_##SNAME##_f32;                    \
+  T.simref[s][0] = (const void *)sdek_##TAG##_simref_##SNAME##_f64;                    \
+  T.simref[s][1] = (const void *)sdek_##TAG##_simref_##SNAME##_f32;                    \
+  T.simw[s][0] = (const void *)sdek_##TAG##_simw_##SNAME##_f64;                        \
+  T.simw[s][1] = (const void *)sdek_##TAG##_simw_##SNAME##_f32;
+#define XCOEFFILL(T, TAG) XCOEFFILL2(T, TAG)
+#define XCOEFFILL2(T, TAG) T.coef = (const void *)sdek_##TAG##_coef;
+
+XSCHEME(BlackScholes, TAGGED(bs), 0, em)
+XSCHEME(BlackScholes, TAGGED(bs), 1, mil)
+XCOEF(BlackScholes, TAGGED(bs))
+XSCHEME(Heston, TAGGED(heston), 0, em)
+XCOEF(Heston, TAGGED(heston))
+
+#define XWIENER(DIM, TAG) XWIENER2(DIM, TAG)
+#define XWIENER2(DIM, TAG)                                                                                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_f64(const __grid_constant__ sde_args a) { \
+    sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, double, 0>(a);                                         \
+  }                                                                                                          \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_f32(const __grid_constant__ sde_args a) { \
+    sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, float, 0>(a);                                          \
+  }
+XWIENER(1, TAGGED(wiener1))
+XWIENER(2, TAGGED(wiener2))
+XWIENER(3, TAGGED(wiener3))
+XWIENER(4, TAGGED(wiener4))
+
+// model: 0 = BlackScholes, 1 = Heston
+extern "C" int SDE_AOT_TABLE(int model, sde_ktable *t) {
+  sde_ktable z = {};
+  *t = z;
+  if (model == 0) {
+    XFILL((*t), TAGGED(bs), 0, em)
+    XFILL((*t), TAGGED(bs), 1, mil)
+    XCOEFFILL((*t), TAGGED(bs))
+    return 0;
+  }
+  if (model == 1) {
+    XFILL((*t), TAGGED(heston), 0, em)
+    XCOEFFILL((*t), TAGGED(heston))
+    return 0;
+  }
+  return -1;
+}
+
+// wiener kernels [dim-1][precision]
+#define XW(TAG, P) XW2(TAG, P)
+#define XW2(TAG, P) (const void *)sdek_##TAG##_##P
+extern "C" const void *SDE_AOT_WIENER(int dim, int precision) {
+  switch (dim * 2 + precision) {
+    case 2: return XW(TAGGED(wiener1), f64);
+    case 3: return XW(TAGGED(wiener1), f32);
+    case 4: return XW(TAGGED(wiener2), f64);
+    case 5: return XW(TAGGED(wiener2), f32);
+    case 6: return XW(TAGGED(wiener3), f64);
+    case 7: return XW(TAGGED(wiener3), f32);
+    case 8: return XW(TAGGED(wiener4), f64);
+    case 9: return XW(TAGGED(wiener4), f32);
+  }
+  return 0;
+}

@@ -1,0 +1,1177 @@
+// sde_api.cu — host side of the C ABI declared in include/sdeb200.h.
+// Owns: device binding, streams/events, scratch memory, host<->device staging pipelines, the kernel tables
+// (AOT for the built-in functors, NVRTC for @sde_model-generated ones), the exact accumulator's host half,
+// and the NCCL communicator (one process per GPU).  No compute happens on the CPU: every driver launches
+// the kernels of sde_device.cuh and fails with SDEB200_E_CUDA when no device is available.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sdeb200.h"
+#include "sde_args.h"
+#include "sde_dsl.h"
+#include "sde_ktable.h"
+
+extern "C" int sde_aot_table_fast(int model, sde_ktable *t);
+extern "C" int sde_aot_table_strict(int model, sde_ktable *t);
+extern "C" const void *sde_aot_wiener_fast(int dim, int precision);
+extern "C" const void *sde_aot_wiener_strict(int dim, int precision);
+extern "C" void sde_launch_accumulate(const double *partials, int64_t nchunks, int stride, int nq,
+                                      unsigned long long *bins, unsigned long long *overflow, cudaStream_t st);
+extern "C" void sde_launch_subsample(int precision, const void *src, void *dst, int64_t npaths, int64_t nrows_dst,
+                                     int64_t nrows_src, int64_t substeps, int dim, cudaStream_t st);
+extern "C" double sde_launch_peak(int precision, void *scratch, int blocks, int iters, cudaStream_t st);
+// sde_nvrtc.cpp
+int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precision, int math, sde_ktable *kt,
+                      void **library_out, std::string *log);
+
+static_assert(SDEB200_NBINS == SDE_NBINS, "bins");
+static_assert(SDEB200_SHARD_ALIGN == SDE_SHARD_ALIGN, "align");
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+  char buf[4096];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(SDEB200_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time so that the library loads on machines without it (and shares the copy
+// PyTorch already mapped when the host process is Python)
+// ---------------------------------------------------------------------------------------------------
+struct nccl_uid { char b[128]; };
+typedef void *nccl_comm;
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(nccl_uid *) = nullptr;
+  int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
+  int (*CommDestroy)(nccl_comm) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+  for (const char *n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return fail(SDEB200_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                       \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);                           \
+  if (!g_nccl.field) return fail(SDEB200_E_NCCL, "libnccl lacks %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return 0;
+}
+#define NC(call)                                                                                         \
+  do {                                                                                                   \
+    int r_ = (call);                                                                                     \
+    if (r_ != 0) return fail(SDEB200_E_NCCL, "%s: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(SDEB200_E_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+static const int MAX_LEVELS = 24;
+static const int RED_WORDS = 2 * SDE_MAXF * SDE_NBINS + 4;  // bins + {n, nonfinite, overflow, pad}
+
+struct Ctx {
+  bool up = false;
+  int device = -1;
+  cudaStream_t own = nullptr, copy = nullptr, ext = nullptr;
+  bool use_ext = false;
+  cudaStream_t lvl[MAX_LEVELS] = {};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, kdone[2] = {}, cdone[2] = {}, lvl_done[MAX_LEVELS] = {};
+  DevBuf slab[2], win[2], partials[MAX_LEVELS], red, misc;
+  double last_ms = 0.0;
+  int64_t launches = 0;
+  nccl_comm comm = nullptr;
+  int nranks = 1, rank = 0;
+  cudaStream_t stream() const { return use_ext ? ext : own; }
+};
+static Ctx g;
+
+static int ensure_up() {
+  if (g.up) return 0;
+  return sdeb200_init(-1);
+}
+
+extern "C" int sdeb200_version(void) { return SDEB200_VERSION; }
+extern "C" const char *sdeb200_last_error(void) { return g_err.c_str(); }
+extern "C" int sdeb200_device_count(int *n) {
+  if (!n) return fail(SDEB200_E_ARG, "n is NULL");
+  *n = 0;
+  CU(cudaGetDeviceCount(n));
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SDEB200_E_CUDA, "no CUDA device (%s); sdeb200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0) {
+    if (g.up) return SDEB200_OK;
+    CU(cudaGetDevice(&device));
+  }
+  if (device >= n) return fail(SDEB200_E_ARG, "device %d out of range (%d devices)", device, n);
+  if (g.up && g.device == device) return SDEB200_OK;
+  if (g.up) sdeb200_shutdown();
+  CU(cudaSetDevice(device));
+  g.device = device;
+  CU(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&g.ev0));
+  CU(cudaEventCreate(&g.ev1));
+  for (int i = 0; i < 2; i++) {
+    CU(cudaEventCreateWithFlags(&g.kdone[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g.cdone[i], cudaEventDisableTiming));
+  }
+  g.up = true;
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_shutdown(void) {
+  if (!g.up) return SDEB200_OK;
+  cudaDeviceSynchronize();
+  if (g.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g.comm);
+  g.comm = nullptr;
+  g.nranks = 1;
+  g.rank = 0;
+  for (int i = 0; i < 2; i++) {
+    g.slab[i].release();
+    g.win[i].release();
+    if (g.kdone[i]) cudaEventDestroy(g.kdone[i]);
+    if (g.cdone[i]) cudaEventDestroy(g.cdone[i]);
+    g.kdone[i] = g.cdone[i] = nullptr;
+  }
+  for (int i = 0; i < MAX_LEVELS; i++) {
+    g.partials[i].release();
+    if (g.lvl[i]) cudaStreamDestroy(g.lvl[i]);
+    if (g.lvl_done[i]) cudaEventDestroy(g.lvl_done[i]);
+    g.lvl[i] = nullptr;
+    g.lvl_done[i] = nullptr;
+  }
+  g.red.release();
+  g.misc.release();
+  if (g.ev0) cudaEventDestroy(g.ev0);
+  if (g.ev1) cudaEventDestroy(g.ev1);
+  if (g.own) cudaStreamDestroy(g.own);
+  if (g.copy) cudaStreamDestroy(g.copy);
+  g.ev0 = g.ev1 = nullptr;
+  g.own = g.copy = nullptr;
+  g.use_ext = false;
+  g.up = false;
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_set_stream(void *s) {
+  int rc = ensure_up();
+  if (rc) return rc;
+  g.ext = (cudaStream_t)s;
+  g.use_ext = true;  // NULL selects the legacy default stream, which is what a torch default stream is
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_synchronize(void) {
+  int rc = ensure_up();
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(g.stream()));
+  return SDEB200_OK;
+}
+extern "C" double sdeb200_last_kernel_ms(void) { return g.last_ms; }
+extern "C" int64_t sdeb200_launch_count(void) { return g.launches; }
+
+extern "C" int sdeb200_measure_peak(int precision, double *tflops, double *ms_out) {
+  int rc = ensure_up();
+  if (rc) return rc;
+  if (!tflops) return fail(SDEB200_E_ARG, "tflops is NULL");
+  const int blocks = 148 * 2, iters = 4096;
+  rc = g.misc.ensure((size_t)blocks * 1024 * 8);
+  if (rc) return rc;
+  cudaStream_t st = g.stream();
+  sde_launch_peak(precision, g.misc.p, blocks, 64, st);  // warm-up
+  double best = 0.0, best_ms = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(g.ev0, st));
+    double flops = sde_launch_peak(precision, g.misc.p, blocks, iters, st);
+    g.launches++;
+    CU(cudaEventRecord(g.ev1, st));
+    CU(cudaEventSynchronize(g.ev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) { best = tf; best_ms = ms; }
+  }
+  CU(cudaGetLastError());
+  *tflops = best;
+  if (ms_out) *ms_out = best_ms;
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// models
+// ---------------------------------------------------------------------------------------------------
+struct sdeb200_model {
+  std::string name;
+  int D = 0, M = 0, kind = 0, builtin = -1;
+  std::vector<std::string> params, vars, drift, diffusion;  // diffusion row-major D x max(M,1)
+  std::string source;                                       // generated functor (empty for built-ins)
+  sde_ktable kt[2];                                         // [math]
+  bool have[2][2] = {{false, false}, {false, false}};       // [math][precision]
+  std::vector<void *> libs;
+};
+
+extern "C" int sdeb200_model_builtin(const char *name, sdeb200_model **out) {
+  if (!name || !out) return fail(SDEB200_E_ARG, "null argument");
+  sdeb200_model *m = new sdeb200_model();
+  m->name = name;
+  if (m->name == "BlackScholes") {
+    m->builtin = 0; m->D = 1; m->M = 1;
+    m->params = {"r", "σ"}; m->vars = {"S"};
+    m->drift = {"r * S"}; m->diffusion = {"σ * S"};
+  } else if (m->name == "Heston") {
+    m->builtin = 1; m->D = 2; m->M = 2;
+    m->params = {"r", "κ", "θ", "σ", "ρ"}; m->vars = {"S", "V"};
+    m->drift = {"r * S", "κ * (θ - V)"};
+    m->diffusion = {"sqrt(V) * S", "0", "σ * sqrt(V) * ρ", "σ * sqrt(V) * sqrt(1 - ρ ^ 2)"};
+  } else {
+    delete m;
+    return fail(SDEB200_E_ARG, "no built-in model named '%s' (BlackScholes, Heston)", name);
+  }
+  sde_aot_table_fast(m->builtin, &m->kt[0]);
+  sde_aot_table_strict(m->builtin, &m->kt[1]);
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2; b++) m->have[a][b] = true;
+  *out = m;
+  return SDEB200_OK;
+}
+
+extern "C" int sdeb200_model_create(const char *name, const char *eqs, const char *const *param_names, int nparams,
+                                    sdeb200_model **out) {
+  if (!name || !eqs || !out) return fail(SDEB200_E_ARG, "null argument");
+  std::vector<std::string> pn;
+  for (int i = 0; i < nparams; i++) pn.push_back(param_names[i]);
+  sde_dsl_model dm;
+  std::string err;
+  if (!sde_dsl_build(name, eqs, pn, &dm, &err)) return fail(SDEB200_E_PARSE, "%s", err.c_str());
+  if (dm.kind == 2)
+    return fail(SDEB200_E_UNSUPPORTED, "model '%s' is a JumpSDE; jump diffusions are outside the accelerated path", name);
+  if (dm.D > SDE_MAXD || dm.M > SDE_MAXM || (int)dm.params.size() > SDE_MAXP)
+    return fail(SDEB200_E_UNSUPPORTED, "model '%s' exceeds D<=%d, M<=%d, %d parameters", name, SDE_MAXD, SDE_MAXM, SDE_MAXP);
+  sdeb200_model *m = new sdeb200_model();
+  m->name = name;
+  m->D = dm.D; m->M = dm.M; m->kind = dm.kind;
+  m->params = dm.params; m->vars = dm.vars; m->drift = dm.drift_str; m->diffusion = dm.diffusion_str;
+  m->source = dm.cuda_source;
+  memset(m->kt, 0, sizeof m->kt);
+  *out = m;
+  return SDEB200_OK;
+}
+
+extern "C" void sdeb200_model_free(sdeb200_model *m) {
+  if (!m) return;
+  for (void *l : m->libs) cudaLibraryUnload((cudaLibrary_t)l);
+  delete m;
+}
+extern "C" int sdeb200_model_info(const sdeb200_model *m, int *D, int *M, int *np, int *kind) {
+  if (!m) return fail(SDEB200_E_ARG, "model is NULL");
+  if (D) *D = m->D;
+  if (M) *M = m->M;
+  if (np) *np = (int)m->params.size();
+  if (kind) *kind = m->kind;
+  return SDEB200_OK;
+}
+extern "C" const char *sdeb200_model_name(const sdeb200_model *m) { return m ? m->name.c_str() : nullptr; }
+extern "C" const char *sdeb200_model_param_name(const sdeb200_model *m, int i) {
+  return (m && i >= 0 && i < (int)m->params.size()) ? m->params[i].c_str() : nullptr;
+}
+extern "C" const char *sdeb200_model_variable_name(const sdeb200_model *m, int i) {
+  return (m && i >= 0 && i < (int)m->vars.size()) ? m->vars[i].c_str() : nullptr;
+}
+extern "C" const char *sdeb200_model_drift_expr(const sdeb200_model *m, int i) {
+  return (m && i >= 0 && i < (int)m->drift.size()) ? m->drift[i].c_str() : nullptr;
+}
+extern "C" const char *sdeb200_model_diffusion_expr(const sdeb200_model *m, int i, int j) {
+  if (!m) return nullptr;
+  const int MW = m->M > 0 ? m->M : 1;
+  const int k = i * MW + j;
+  return (i >= 0 && j >= 0 && j < MW && k < (int)m->diffusion.size()) ? m->diffusion[k].c_str() : nullptr;
+}
+extern "C" const char *sdeb200_model_cuda_source(const sdeb200_model *m) { return m ? m->source.c_str() : nullptr; }
+
+extern "C" int sdeb200_model_compile(sdeb200_model *m, int precision, int math) {
+  if (!m) return fail(SDEB200_E_ARG, "model is NULL");
+  if (precision < 0 || precision > 1 || math < 0 || math > 1) return fail(SDEB200_E_ARG, "bad precision/math");
+  if (m->have[math][precision]) return SDEB200_OK;
+  int rc = ensure_up();
+  if (rc) return rc;
+  void *lib = nullptr;
+  std::string log;
+  rc = sde_nvrtc_compile(m->source, m->D, m->M, precision, math, &m->kt[math], &lib, &log);
+  if (rc) return fail(rc, "NVRTC/load of model '%s' failed:\n%s", m->name.c_str(), log.c_str());
+  m->libs.push_back(lib);
+  m->have[math][precision] = true;
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------
+static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0) {
+  if (!m || !o || !x0) return fail(SDEB200_E_ARG, "null argument");
+  if (!params && !m->params.empty()) return fail(SDEB200_E_ARG, "params is NULL but the model has %zu", m->params.size());
+  if (o->scheme != SDEB200_EULER_MARUYAMA && o->scheme != SDEB200_MILSTEIN)
+    return fail(SDEB200_E_ARG, "unknown scheme %d", o->scheme);
+  if (o->scheme == SDEB200_MILSTEIN && m->M != 1)
+    return fail(SDEB200_E_UNSUPPORTED,
+                "Milstein is defined for models with one Wiener process only (M == 1), as in the reference "
+                "(src/schemes/milstein.jl:4); '%s' has M == %d", m->name.c_str(), m->M);
+  if (o->precision < 0 || o->precision > 1 || o->math < 0 || o->math > 1) return fail(SDEB200_E_ARG, "bad precision/math");
+  if (!(o->dt > 0.0) || !isfinite(o->dt)) return fail(SDEB200_E_ARG, "scheme Δt must be positive and finite");
+  return 0;
+}
+
+static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o, const double *params,
+                      const double *x0) {
+  memset(a, 0, sizeof *a);
+  for (size_t i = 0; i < m->params.size(); i++) a->params[i] = params[i];
+  for (int d = 0; d < m->D; d++) a->x0[d] = x0[d];
+  a->t0 = o->t0;
+  a->dt = o->dt;
+  a->seed_lo = (uint32_t)o->seed;
+  a->seed_hi = (uint32_t)(o->seed >> 32);
+  a->stream = o->stream;
+  a->path0 = o->path_offset;
+}
+
+static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t st) {
+  if (!k) return fail(SDEB200_E_UNSUPPORTED, "kernel not available for this model / scheme");
+  if (grid <= 0) return 0;
+  if (grid > 2147483647LL) return fail(SDEB200_E_ARG, "too many paths for one launch");
+  void *args[1] = {(void *)a};
+  CU(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(SDE_BLOCK), args, 0, st));
+  g.launches++;
+  return 0;
+}
+
+static bool is_device_ptr(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static inline size_t esize(int precision) { return precision == SDEB200_F64 ? 8 : 4; }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+static int get_ktable(sdeb200_model *m, const sdeb200_opts *o, const sde_ktable **kt) {
+  int rc = sdeb200_model_compile(m, o->precision, o->math);
+  if (rc) return rc;
+  *kt = &m->kt[o->math];
+  return 0;
+}
+
+// Generic slab pipeline for path-major outputs: kernel(slab i) on the compute stream overlaps the
+// device->host copy of slab i-1 on the copy stream.  bytes_per_path of contiguous host memory per path.
+template <class LaunchFn>
+static int run_slabs(int64_t npaths, size_t bytes_per_path, void *host_out, LaunchFn &&fn) {
+  cudaStream_t st = g.stream();
+  int64_t slab = (int64_t)((size_t)(256u << 20) / std::max<size_t>(bytes_per_path, 1));
+  slab = std::max<int64_t>(SDE_SHARD_ALIGN, slab / SDE_SHARD_ALIGN * SDE_SHARD_ALIGN);
+  slab = std::min<int64_t>(slab, cdiv(npaths, SDE_SHARD_ALIGN) * SDE_SHARD_ALIGN);
+  const int nb = npaths > slab ? 2 : 1;
+  for (int b = 0; b < nb; b++) {
+    int rc = g.slab[b].ensure((size_t)slab * bytes_per_path);
+    if (rc) return rc;
+  }
+  bool used[2] = {false, false};
+  int b = 0;
+  for (int64_t s0 = 0; s0 < npaths; s0 += slab, b ^= 1) {
+    const int64_t n = std::min<int64_t>(slab, npaths - s0);
+    if (used[b]) {
+      CU(cudaEventSynchronize(g.cdone[b]));      // host: the copy engine released this buffer
+    }
+    int rc = fn(s0, n, g.slab[b].p, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(g.kdone[b], st));
+    CU(cudaStreamWaitEvent(g.copy, g.kdone[b], 0));
+    CU(cudaMemcpyAsync((char *)host_out + (size_t)s0 * bytes_per_path, g.slab[b].p, (size_t)n * bytes_per_path,
+                       cudaMemcpyDeviceToHost, g.copy));
+    CU(cudaEventRecord(g.cdone[b], g.copy));
+    used[b] = true;
+  }
+  CU(cudaStreamSynchronize(g.copy));
+  return 0;
+}
+
+static int timed_begin() {
+  CU(cudaEventRecord(g.ev0, g.stream()));
+  return 0;
+}
+static int timed_end() {
+  cudaStream_t st = g.stream();
+  CU(cudaEventRecord(g.ev1, st));
+  CU(cudaEventSynchronize(g.ev1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+  g.last_ms = ms;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int read_nonfinite(unsigned long long *dev, unsigned long long *host) {
+  CU(cudaMemcpyAsync(host, dev, sizeof *host, cudaMemcpyDeviceToHost, g.stream()));
+  CU(cudaStreamSynchronize(g.stream()));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// drift / diffusion on the device
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sdeb200_model_coefficients(sdeb200_model *m, const double *params, double t, const double *x,
+                                          double *mu, double *sigma) {
+  if (!m || !x) return fail(SDEB200_E_ARG, "null argument");
+  int rc = ensure_up();
+  if (rc) return rc;
+  sdeb200_opts o;
+  memset(&o, 0, sizeof o);
+  o.dt = 1.0;
+  o.t0 = t;
+  o.math = SDEB200_MATH_STRICT;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, &o, &kt))) return rc;
+  const int MW = m->M > 0 ? m->M : 1, nout = m->D + m->D * MW;
+  if ((rc = g.misc.ensure(256 * 8))) return rc;
+  sde_args a;
+  fill_args(&a, m, &o, params, x);
+  a.out = g.misc.p;
+  cudaStream_t st = g.stream();
+  void *args[1] = {&a};
+  if (!kt->coef) return fail(SDEB200_E_UNSUPPORTED, "no coefficient kernel");
+  CU(cudaLaunchKernel(kt->coef, dim3(1), dim3(32), args, 0, st));
+  g.launches++;
+  double host[SDE_MAXD + SDE_MAXD * SDE_MAXM];
+  CU(cudaMemcpyAsync(host, g.misc.p, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (mu) memcpy(mu, host, m->D * sizeof(double));
+  if (sigma) memcpy(sigma, host + m->D, m->D * MW * sizeof(double));
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sample
+// ---------------------------------------------------------------------------------------------------
+static int64_t sample_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * 2); }
+
+extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
+                              int64_t nsteps, int64_t npaths, void *out) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if (nsteps < 0 || npaths < 0 || (!out && npaths > 0)) return fail(SDEB200_E_ARG, "bad nsteps/npaths/out");
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if (npaths == 0) return SDEB200_OK;
+  if ((rc = g.red.ensure(RED_WORDS * 8))) return rc;
+  cudaStream_t st = g.stream();
+  unsigned long long *d_bad = (unsigned long long *)g.red.p;
+  CU(cudaMemsetAsync(d_bad, 0, 8, st));
+  const void *k = kt->sample[o->scheme][o->precision];
+  sde_args a;
+  fill_args(&a, m, o, params, x0);
+  a.nsteps = nsteps;
+  a.nonfinite = d_bad;
+  const size_t bpp = (size_t)m->D * esize(o->precision);
+  if ((rc = timed_begin())) return rc;
+  if (is_device_ptr(out)) {
+    a.npaths = npaths;
+    a.out = out;
+    if ((rc = launch(k, sample_grid(npaths), &a, st))) return rc;
+  } else {
+    rc = run_slabs(npaths, bpp, out, [&](int64_t s0, int64_t n, void *dev, cudaStream_t s) {
+      sde_args b = a;
+      b.npaths = n;
+      b.path0 = o->path_offset + s0;
+      b.out = dev;
+      return launch(k, sample_grid(n), &b, s);
+    });
+    if (rc) return rc;
+  }
+  if ((rc = timed_end())) return rc;
+  unsigned long long bad = 0;
+  if ((rc = read_nonfinite(d_bad, &bad))) return rc;
+  if (bad)
+    return fail(SDEB200_E_DOMAIN, "%llu of %lld paths ended non-finite (the reference raises DomainError, e.g. sqrt of a "
+                "negative variance)", bad, (long long)npaths);
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// simulate (RNG-driven full trajectories)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
+                                int64_t nsteps, int64_t npaths, int layout, void *out) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if (nsteps < 0 || npaths < 0 || (!out && npaths > 0)) return fail(SDEB200_E_ARG, "bad nsteps/npaths/out");
+  if (layout != SDEB200_LAYOUT_REFERENCE && layout != SDEB200_LAYOUT_SOA) return fail(SDEB200_E_ARG, "bad layout");
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if (npaths == 0) return SDEB200_OK;
+  cudaStream_t st = g.stream();
+  const size_t es = esize(o->precision);
+  const int64_t nrows = nsteps + 1;
+  sde_args a;
+  fill_args(&a, m, o, params, x0);
+  a.nsteps = nsteps;
+  const bool dev = is_device_ptr(out);
+  if ((rc = timed_begin())) return rc;
+  if (layout == SDEB200_LAYOUT_REFERENCE) {
+    const void *k = kt->simref[o->scheme][o->precision];
+    const size_t bpp = (size_t)nrows * m->D * es;
+    if (dev) {
+      a.npaths = npaths;
+      a.out = out;
+      if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+    } else {
+      rc = run_slabs(npaths, bpp, out, [&](int64_t s0, int64_t n, void *d, cudaStream_t s) {
+        sde_args b = a;
+        b.npaths = n;
+        b.path0 = o->path_offset + s0;
+        b.out = d;
+        return launch(k, cdiv(n, SDE_BLOCK), &b, s);
+      });
+      if (rc) return rc;
+    }
+  } else {
+    const void *k = kt->simsoa[o->scheme][o->precision];
+    const int vec = (int)(16 / es);
+    if (dev) {
+      a.npaths = npaths;
+      a.out = out;
+      a.ld_paths = npaths;
+      a.path_off = 0;
+      if ((rc = launch(k, cdiv(cdiv(npaths, vec), SDE_BLOCK), &a, st))) return rc;
+    } else {
+      // host SoA: slabs of columns, strided in host memory -> 2-D copies
+      const size_t rowsD = (size_t)nrows * m->D;
+      int64_t slab = (int64_t)((size_t)(256u << 20) / (rowsD * es));
+      slab = std::max<int64_t>(SDE_SHARD_ALIGN, slab / SDE_SHARD_ALIGN * SDE_SHARD_ALIGN);
+      slab = std::min<int64_t>(slab, cdiv(npaths, SDE_SHARD_ALIGN) * SDE_SHARD_ALIGN);
+      if ((rc = g.slab[0].ensure((size_t)slab * rowsD * es))) return rc;
+      for (int64_t s0 = 0; s0 < npaths; s0 += slab) {
+        const int64_t n = std::min<int64_t>(slab, npaths - s0);
+        sde_args b = a;
+        b.npaths = n;
+        b.path0 = o->path_offset + s0;
+        b.out = g.slab[0].p;
+        b.ld_paths = slab;
+        b.path_off = 0;
+        if ((rc = launch(k, cdiv(cdiv(n, vec), SDE_BLOCK), &b, st))) return rc;
+        CU(cudaMemcpy2DAsync((char *)out + (size_t)s0 * es, (size_t)npaths * es, g.slab[0].p, (size_t)slab * es,
+                             (size_t)n * es, rowsD, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+      }
+    }
+  }
+  if ((rc = timed_end())) return rc;
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// simulate! driven by a Wiener path
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, const double *params,
+                                       const double *x0, int64_t nrows, int64_t npaths, const void *w, void *x) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if (nrows < 1 || npaths < 0 || ((!w || !x) && npaths > 0)) return fail(SDEB200_E_ARG, "bad nrows/npaths/w/x");
+  const int MW = m->M > 0 ? m->M : 1;
+  if (w == x && m->D != MW)
+    return fail(SDEB200_E_ARG, "x === w needs eltype(x) == eltype(w), i.e. D == M (D=%d, M=%d)", m->D, m->M);
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if (npaths == 0) return SDEB200_OK;
+  cudaStream_t st = g.stream();
+  const size_t es = esize(o->precision);
+  const void *k = kt->simw[o->scheme][o->precision];
+  sde_args a;
+  fill_args(&a, m, o, params, x0);
+  a.nsteps = nrows - 1;
+  const bool wdev = is_device_ptr(w), xdev = is_device_ptr(x);
+  if ((rc = timed_begin())) return rc;
+  if (wdev && xdev) {
+    a.npaths = npaths;
+    a.out = x;
+    a.out2 = (void *)w;
+    if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+  } else {
+    const size_t wb = (size_t)nrows * MW * es, xb = (size_t)nrows * m->D * es;
+    int64_t slab = (int64_t)((size_t)(128u << 20) / std::max(wb, xb));
+    slab = std::max<int64_t>(32, std::min<int64_t>(slab, npaths));
+    if ((rc = g.win[0].ensure((size_t)slab * wb))) return rc;
+    if ((rc = g.slab[0].ensure((size_t)slab * xb))) return rc;
+    for (int64_t s0 = 0; s0 < npaths; s0 += slab) {
+      const int64_t n = std::min<int64_t>(slab, npaths - s0);
+      const void *wsrc = (const char *)w + (size_t)s0 * wb;
+      CU(cudaMemcpyAsync(g.win[0].p, wsrc, (size_t)n * wb, wdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+      sde_args b = a;
+      b.npaths = n;
+      b.out = g.slab[0].p;
+      b.out2 = g.win[0].p;
+      if ((rc = launch(k, cdiv(n, SDE_BLOCK), &b, st))) return rc;
+      CU(cudaMemcpyAsync((char *)x + (size_t)s0 * xb, g.slab[0].p, (size_t)n * xb,
+                         xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  if ((rc = timed_end())) return rc;
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// wiener!
+// ---------------------------------------------------------------------------------------------------
+static int wiener_device(const sdeb200_opts *o, int dim, int64_t nrows, int64_t npaths, int64_t path0, void *dev,
+                         cudaStream_t st) {
+  const void *k = o->math == SDEB200_MATH_STRICT ? sde_aot_wiener_strict(dim, o->precision)
+                                                 : sde_aot_wiener_fast(dim, o->precision);
+  if (!k) return fail(SDEB200_E_ARG, "wiener!: dim must be 1..4");
+  sde_args a;
+  memset(&a, 0, sizeof a);
+  a.t0 = o->t0;
+  a.dt = o->dt;
+  a.seed_lo = (uint32_t)o->seed;
+  a.seed_hi = (uint32_t)(o->seed >> 32);
+  a.stream = o->stream;
+  a.path0 = path0;
+  a.nsteps = nrows - 1;
+  a.npaths = npaths;
+  a.out = dev;
+  return launch(k, cdiv(npaths, SDE_BLOCK), &a, st);
+}
+
+extern "C" int sdeb200_wiener(const sdeb200_opts *o, int dim, int64_t nrows, int64_t npaths, void *w) {
+  if (!o || (!w && npaths > 0)) return fail(SDEB200_E_ARG, "null argument");
+  if (nrows < 1 || npaths < 0 || dim < 1 || dim > 4) return fail(SDEB200_E_ARG, "bad nrows/npaths/dim");
+  if (!(o->dt > 0.0)) return fail(SDEB200_E_ARG, "Δt must be positive");
+  int rc = ensure_up();
+  if (rc) return rc;
+  if (npaths == 0) return SDEB200_OK;
+  cudaStream_t st = g.stream();
+  const size_t bpp = (size_t)nrows * dim * esize(o->precision);
+  if ((rc = timed_begin())) return rc;
+  if (is_device_ptr(w)) {
+    if ((rc = wiener_device(o, dim, nrows, npaths, o->path_offset, w, st))) return rc;
+  } else {
+    rc = run_slabs(npaths, bpp, w, [&](int64_t s0, int64_t n, void *d, cudaStream_t s) {
+      return wiener_device(o, dim, nrows, n, o->path_offset + s0, d, s);
+    });
+    if (rc) return rc;
+  }
+  return timed_end();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact accumulator, host half
+// ---------------------------------------------------------------------------------------------------
+extern "C" void sdeb200_bins_add(int64_t *bins, double v) {
+  uint64_t b;
+  memcpy(&b, &v, 8);
+  const int e = (int)((b >> 52) & 0x7ff);
+  uint64_t mant = b & 0xFFFFFFFFFFFFFull;
+  if (e == 0x7ff || (e == 0 && mant == 0)) return;
+  int sh = e - 1;
+  if (e == 0) sh = 0; else mant |= (1ull << 52);
+  const int bin = sh >> 5, off = sh & 31;
+  const uint64_t lo64 = mant << off, hi = off ? (mant >> (64 - off)) : 0ull;
+  int64_t l0 = (int64_t)(lo64 & 0xffffffffull), l1 = (int64_t)(lo64 >> 32), l2 = (int64_t)hi;
+  if (b >> 63) { l0 = -l0; l1 = -l1; l2 = -l2; }
+  bins[bin] += l0;
+  bins[bin + 1] += l1;
+  bins[bin + 2] += l2;
+}
+
+extern "C" double sdeb200_bins_to_double(const int64_t *bins) {
+  uint32_t limb[SDE_NBINS];
+  __int128 carry = 0;
+  for (int b = 0; b < SDE_NBINS; b++) {
+    __int128 t = (__int128)bins[b] + carry;
+    limb[b] = (uint32_t)((unsigned __int128)t & 0xffffffffu);
+    carry = t >> 32;  // arithmetic shift: floor division
+  }
+  bool neg = false;
+  if (carry < 0) {
+    if (carry != -1) return -INFINITY;
+    neg = true;
+    uint64_t c = 1;  // two's complement over the limbs
+    for (int b = 0; b < SDE_NBINS; b++) {
+      uint64_t t = (uint64_t)(uint32_t)~limb[b] + c;
+      limb[b] = (uint32_t)t;
+      c = t >> 32;
+    }
+  } else if (carry > 0) {
+    return INFINITY;
+  }
+  int hi = SDE_NBINS - 1;
+  while (hi >= 0 && limb[hi] == 0) hi--;
+  if (hi < 0) return 0.0;
+  double r;
+  if (hi <= 1) {
+    const uint64_t v = ((uint64_t)(hi == 1 ? limb[1] : 0) << 32) | limb[0];
+    // <= 64 bits: exact conversion needs care above 53 bits
+    if (v < (1ull << 53)) {
+      r = ldexp((double)v, -1074);
+    } else {
+      const int L = 64 - __builtin_clzll(v), shf = L - 53;
+      uint64_t mant = v >> shf, rem = v & ((1ull << shf) - 1), half = 1ull << (shf - 1);
+      if (rem > half || (rem == half && (mant & 1))) mant++;
+      r = ldexp((double)mant, shf - 1074);
+    }
+  } else {
+    unsigned __int128 t = ((unsigned __int128)limb[hi] << 64) | ((unsigned __int128)limb[hi - 1] << 32) | limb[hi - 2];
+    bool sticky = false;
+    for (int b = hi - 3; b >= 0 && !sticky; b--) sticky = limb[b] != 0;
+    int L = 96;
+    while (!((t >> (L - 1)) & 1)) L--;  // L >= 65 because limb[hi] != 0
+    const int shf = L - 53;
+    uint64_t mant = (uint64_t)(t >> shf);
+    const unsigned __int128 rem = t & (((unsigned __int128)1 << shf) - 1), half = (unsigned __int128)1 << (shf - 1);
+    if (rem > half || (rem == half && (sticky || (mant & 1)))) mant++;
+    r = ldexp((double)mant, shf + 32 * (hi - 2) - 1074);
+  }
+  return neg ? -r : r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// estimators
+// ---------------------------------------------------------------------------------------------------
+struct RedSlot {  // device layout of one reduction record
+  unsigned long long *bins, *n, *bad, *ovf;
+};
+static RedSlot red_slot(void *base, int idx) {
+  unsigned long long *p = (unsigned long long *)base + (size_t)idx * RED_WORDS;
+  RedSlot r;
+  r.bins = p;
+  r.n = p + 2 * SDE_MAXF * SDE_NBINS;
+  r.bad = r.n + 1;
+  r.ovf = r.n + 2;
+  return r;
+}
+
+static int payoff_nf(const sdeb200_model *m, const sdeb200_payoff *p) {
+  return p->kind == SDEB200_PAYOFF_MOMENTS ? m->D : 1;
+}
+static int check_payoff(const sdeb200_model *m, const sdeb200_payoff *p) {
+  if (!p) return fail(SDEB200_E_ARG, "payoff is NULL");
+  if (p->kind < 0 || p->kind > 3) return fail(SDEB200_E_ARG, "unknown payoff kind %d", p->kind);
+  if (p->kind != SDEB200_PAYOFF_MOMENTS && (p->comp < 0 || p->comp >= m->D))
+    return fail(SDEB200_E_ARG, "payoff component %d out of range (D = %d)", p->comp, m->D);
+  return 0;
+}
+
+// finish nrec reduction records: (allreduce) -> host -> doubles.  nq[i] quantities per record.
+static int finish_reductions(int nrec, const int *nq, cudaStream_t *streams, double *result, int result_stride,
+                             unsigned long long *bad_total) {
+  std::vector<unsigned long long> host((size_t)nrec * RED_WORDS);
+  if (g.comm) {
+    NC(g_nccl.GroupStart());
+    for (int i = 0; i < nrec; i++) {
+      RedSlot r = red_slot(g.red.p, i);
+      NC(g_nccl.AllReduce(r.bins, r.bins, RED_WORDS, /*ncclInt64*/ 4, /*ncclSum*/ 0, g.comm, streams[i]));
+    }
+    NC(g_nccl.GroupEnd());
+  }
+  for (int i = 0; i < nrec; i++) {
+    CU(cudaMemcpyAsync(host.data() + (size_t)i * RED_WORDS, red_slot(g.red.p, i).bins, RED_WORDS * 8,
+                       cudaMemcpyDeviceToHost, streams[i]));
+  }
+  for (int i = 0; i < nrec; i++) CU(cudaStreamSynchronize(streams[i]));
+  *bad_total = 0;
+  for (int i = 0; i < nrec; i++) {
+    const unsigned long long *h = host.data() + (size_t)i * RED_WORDS;
+    const unsigned long long *ex = h + 2 * SDE_MAXF * SDE_NBINS;
+    double *res = result + (size_t)i * result_stride;
+    for (int q = 0; q < nq[i]; q++) res[q] = sdeb200_bins_to_double((const int64_t *)h + q * SDE_NBINS);
+    res[nq[i]] = (double)ex[0];
+    res[nq[i] + 1] = (double)ex[1];
+    *bad_total += ex[1];
+    if (ex[2]) return fail(SDEB200_E_DOMAIN, "a partial payoff sum overflowed to inf/nan");
+  }
+  return 0;
+}
+
+extern "C" int sdeb200_estimate(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
+                                int64_t nsteps, int64_t npaths, const sdeb200_payoff *payoff, void *terminal,
+                                double *result) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if ((rc = check_payoff(m, payoff))) return rc;
+  if (nsteps < 0 || npaths < 0 || !result) return fail(SDEB200_E_ARG, "bad nsteps/npaths/result");
+  if (terminal && !is_device_ptr(terminal) && npaths > 0)
+    return fail(SDEB200_E_ARG, "estimate: `terminal` must be device memory (use sdeb200_sample for host arrays)");
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  cudaStream_t st = g.stream();
+  const int nf = payoff_nf(m, payoff), nq = 2 * nf;
+  const int64_t grid = sample_grid(npaths);
+  if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
+  if ((rc = g.partials[0].ensure((size_t)std::max<int64_t>(grid, 1) * 2 * SDE_MAXF * 8))) return rc;
+  RedSlot r = red_slot(g.red.p, 0);
+  if ((rc = timed_begin())) return rc;
+  CU(cudaMemsetAsync(r.bins, 0, RED_WORDS * 8, st));
+  unsigned long long n_local = (unsigned long long)npaths;
+  CU(cudaMemcpyAsync(r.n, &n_local, 8, cudaMemcpyHostToDevice, st));
+  if (npaths > 0) {
+    sde_args a;
+    fill_args(&a, m, o, params, x0);
+    a.nsteps = nsteps;
+    a.npaths = npaths;
+    a.out = terminal;
+    a.partials = (double *)g.partials[0].p;
+    a.nonfinite = r.bad;
+    a.payoff_kind = payoff->kind;
+    a.payoff_comp = payoff->comp;
+    a.payoff_k = payoff->strike;
+    a.payoff_disc = payoff->discount;
+    if ((rc = launch(kt->sample[o->scheme][o->precision], grid, &a, st))) return rc;
+    sde_launch_accumulate((const double *)g.partials[0].p, grid, 2 * SDE_MAXF, nq, r.bins, r.ovf, st);
+    g.launches++;
+  }
+  unsigned long long bad = 0;
+  if ((rc = finish_reductions(1, &nq, &st, result, nq + 2, &bad))) return rc;
+  if ((rc = timed_end())) return rc;
+  if (bad) return fail(SDEB200_E_DOMAIN, "%llu paths ended non-finite; they are excluded from the sums", bad);
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multilevel
+// ---------------------------------------------------------------------------------------------------
+static int mlmc_args(sde_args *a, sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
+                     double dt_fine, int64_t substeps, int64_t ncoarse, int64_t npaths) {
+  if (substeps < 1 || ncoarse < 0 || npaths < 0) return fail(SDEB200_E_ARG, "bad substeps/ncoarse/npaths");
+  if (!(dt_fine > 0.0)) return fail(SDEB200_E_ARG, "fine Δt must be positive");
+  const int MW = m->M > 0 ? m->M : 1;
+  if (m->M != 0 && m->D != MW)
+    return fail(SDEB200_E_UNSUPPORTED,
+                "the coupled level sampler needs D == M (Δw = zero(typeof(x0)) in src/multilevel.jl:79); "
+                "'%s' has D=%d, M=%d", m->name.c_str(), m->D, m->M);
+  fill_args(a, m, o, params, x0);
+  a->dt = dt_fine;
+  a->dt_coarse = o->dt;
+  a->substeps = substeps;
+  a->nsteps = ncoarse * substeps;
+  a->npaths = npaths;
+  return 0;
+}
+
+extern "C" int sdeb200_mlmc_sample_level(sdeb200_model *m, const sdeb200_opts *o, const double *params,
+                                         const double *x0, double dt_fine, int64_t substeps, int64_t ncoarse,
+                                         int64_t npaths, void *xc, void *xf) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  sde_args a;
+  if ((rc = mlmc_args(&a, m, o, params, x0, dt_fine, substeps, ncoarse, npaths))) return rc;
+  if (npaths == 0) return SDEB200_OK;
+  cudaStream_t st = g.stream();
+  const size_t bytes = (size_t)npaths * m->D * esize(o->precision);
+  const bool cdev = xc && is_device_ptr(xc), fdev = xf && is_device_ptr(xf);
+  if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
+  unsigned long long *d_bad = (unsigned long long *)g.red.p;
+  CU(cudaMemsetAsync(d_bad, 0, 8, st));
+  a.nonfinite = d_bad;
+  if (xf) {
+    if (fdev) a.out = xf;
+    else { if ((rc = g.slab[0].ensure(bytes))) return rc; a.out = g.slab[0].p; }
+  }
+  if (xc) {
+    if (cdev) a.out2 = xc;
+    else { if ((rc = g.slab[1].ensure(bytes))) return rc; a.out2 = g.slab[1].p; }
+  }
+  if ((rc = timed_begin())) return rc;
+  if ((rc = launch(kt->mlmc[o->scheme][o->precision], cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+  if (xf && !fdev) CU(cudaMemcpyAsync(xf, a.out, bytes, cudaMemcpyDeviceToHost, st));
+  if (xc && !cdev) CU(cudaMemcpyAsync(xc, a.out2, bytes, cudaMemcpyDeviceToHost, st));
+  if ((rc = timed_end())) return rc;
+  unsigned long long bad = 0;
+  if ((rc = read_nonfinite(d_bad, &bad))) return rc;
+  if (bad) return fail(SDEB200_E_DOMAIN, "%llu of %lld coupled paths ended non-finite", bad, (long long)npaths);
+  return SDEB200_OK;
+}
+
+extern "C" int sdeb200_mlmc_simulate_level(sdeb200_model *m, const sdeb200_opts *o, const double *params,
+                                           const double *x0, double dt_fine, int64_t substeps, int64_t ncoarse,
+                                           int64_t npaths, void *xc, void *xf) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if (!xc || !xf) return fail(SDEB200_E_ARG, "xc/xf are NULL");
+  if (m->D != m->M)
+    return fail(SDEB200_E_UNSUPPORTED, "_multilevel_simulate needs D == M (wiener! fills an array of eltype(x0), "
+                "src/multilevel.jl:94); '%s' has D=%d, M=%d", m->name.c_str(), m->D, m->M);
+  if (substeps < 1 || ncoarse < 0 || npaths < 0) return fail(SDEB200_E_ARG, "bad substeps/ncoarse/npaths");
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if (npaths == 0) return SDEB200_OK;
+  cudaStream_t st = g.stream();
+  const size_t es = esize(o->precision);
+  const int64_t nf = ncoarse * substeps + 1, nc = ncoarse + 1;
+  const size_t fb = (size_t)npaths * nf * m->D * es, cb = (size_t)npaths * nc * m->D * es;
+  const bool fdev = is_device_ptr(xf), cdev = is_device_ptr(xc);
+  void *dxf = xf, *dxc = xc;
+  if (!fdev) { if ((rc = g.slab[0].ensure(fb))) return rc; dxf = g.slab[0].p; }
+  if (!cdev) { if ((rc = g.slab[1].ensure(cb))) return rc; dxc = g.slab[1].p; }
+  if ((rc = timed_begin())) return rc;
+  // wiener!(xf, fine.Δt); xc = xf[1:substeps:end, :]; simulate!(xf, ..., xf); simulate!(xc, ..., xc)
+  sdeb200_opts of = *o;
+  of.dt = dt_fine;
+  if ((rc = wiener_device(&of, m->D, nf, npaths, o->path_offset, dxf, st))) return rc;
+  sde_launch_subsample(o->precision, dxf, dxc, npaths, nc, nf, substeps, m->D, st);
+  g.launches++;
+  const void *k = kt->simw[o->scheme][o->precision];
+  sde_args a;
+  fill_args(&a, m, &of, params, x0);
+  a.npaths = npaths;
+  a.nsteps = nf - 1;
+  a.out = dxf;
+  a.out2 = dxf;
+  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+  fill_args(&a, m, o, params, x0);
+  a.npaths = npaths;
+  a.nsteps = nc - 1;
+  a.out = dxc;
+  a.out2 = dxc;
+  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+  if (!fdev) CU(cudaMemcpyAsync(xf, dxf, fb, cudaMemcpyDeviceToHost, st));
+  if (!cdev) CU(cudaMemcpyAsync(xc, dxc, cb, cudaMemcpyDeviceToHost, st));
+  return timed_end();
+}
+
+static int ensure_level_streams(int n) {
+  for (int i = 0; i < n; i++) {
+    if (!g.lvl[i]) CU(cudaStreamCreateWithFlags(&g.lvl[i], cudaStreamNonBlocking));
+    if (!g.lvl_done[i]) CU(cudaEventCreateWithFlags(&g.lvl_done[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+// queue one level's kernels on `st` using reduction record `slot`
+static int queue_level(sdeb200_model *m, const sde_ktable *kt, const sdeb200_opts *o, const double *params,
+                       const double *x0, bool coupled, double dt_fine, int64_t substeps, int64_t ncoarse,
+                       int64_t npaths, const sdeb200_payoff *payoff, int slot, cudaStream_t st) {
+  int rc;
+  RedSlot r = red_slot(g.red.p, slot);
+  CU(cudaMemsetAsync(r.bins, 0, RED_WORDS * 8, st));
+  unsigned long long n_local = (unsigned long long)npaths;
+  CU(cudaMemcpyAsync(r.n, &n_local, 8, cudaMemcpyHostToDevice, st));
+  if (npaths == 0) return 0;
+  sde_args a;
+  int64_t grid;
+  const void *k;
+  if (coupled) {
+    if ((rc = mlmc_args(&a, m, o, params, x0, dt_fine, substeps, ncoarse, npaths))) return rc;
+    grid = cdiv(npaths, SDE_BLOCK);
+    k = kt->mlmc[o->scheme][o->precision];
+  } else {
+    fill_args(&a, m, o, params, x0);
+    a.nsteps = ncoarse;
+    a.npaths = npaths;
+    grid = sample_grid(npaths);
+    k = kt->sample[o->scheme][o->precision];
+  }
+  if ((rc = g.partials[slot].ensure((size_t)grid * 2 * SDE_MAXF * 8))) return rc;
+  a.partials = (double *)g.partials[slot].p;
+  a.nonfinite = r.bad;
+  a.payoff_kind = payoff->kind;
+  a.payoff_comp = payoff->comp;
+  a.payoff_k = payoff->strike;
+  a.payoff_disc = payoff->discount;
+  if ((rc = launch(k, grid, &a, st))) return rc;
+  sde_launch_accumulate((const double *)g.partials[slot].p, grid, 2 * SDE_MAXF, coupled ? 6 : 2, r.bins, r.ovf, st);
+  g.launches++;
+  return 0;
+}
+
+extern "C" int sdeb200_mlmc_estimate_level(sdeb200_model *m, const sdeb200_opts *o, const double *params,
+                                           const double *x0, double dt_fine, int64_t substeps, int64_t ncoarse,
+                                           int64_t npaths, const sdeb200_payoff *payoff, double *result) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if ((rc = check_payoff(m, payoff))) return rc;
+  if (payoff->kind == SDEB200_PAYOFF_MOMENTS) return fail(SDEB200_E_ARG, "multilevel estimators need a scalar payoff");
+  if (!result) return fail(SDEB200_E_ARG, "result is NULL");
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
+  cudaStream_t st = g.stream();
+  if ((rc = timed_begin())) return rc;
+  if ((rc = queue_level(m, kt, o, params, x0, true, dt_fine, substeps, ncoarse, npaths, payoff, 0, st))) return rc;
+  const int nq = 6;
+  unsigned long long bad = 0;
+  if ((rc = finish_reductions(1, &nq, &st, result, 8, &bad))) return rc;
+  if ((rc = timed_end())) return rc;
+  if (bad) return fail(SDEB200_E_DOMAIN, "%llu coupled paths ended non-finite; they are excluded from the sums", bad);
+  return SDEB200_OK;
+}
+
+static int64_t ipow64(int64_t b, int64_t e) {
+  int64_t r = 1;
+  while (e-- > 0) r *= b;
+  return r;
+}
+
+extern "C" int sdeb200_mlmc_estimate(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
+                                     int64_t substeps, int64_t level_first, int nlevels, int64_t nsteps,
+                                     const int64_t *npaths, const sdeb200_payoff *payoff, double *result) {
+  int rc = check_common(m, o, params, x0);
+  if (rc) return rc;
+  if ((rc = check_payoff(m, payoff))) return rc;
+  if (payoff->kind == SDEB200_PAYOFF_MOMENTS) return fail(SDEB200_E_ARG, "multilevel estimators need a scalar payoff");
+  if (!npaths || !result || nlevels < 1 || nlevels > MAX_LEVELS || substeps < 1 || level_first < 0 || nsteps < 0)
+    return fail(SDEB200_E_ARG, "bad level specification");
+  if ((rc = ensure_up())) return rc;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
+  if ((rc = ensure_level_streams(nlevels))) return rc;
+  cudaStream_t st = g.stream();
+  if ((rc = timed_begin())) return rc;
+  int nq[MAX_LEVELS];
+  cudaStream_t streams[MAX_LEVELS];
+  // finest (longest) levels first so the short ones fill the machine's tail
+  for (int i = nlevels - 1; i >= 0; i--) {
+    streams[i] = g.lvl[i];
+    CU(cudaStreamWaitEvent(streams[i], g.ev0, 0));
+    sdeb200_opts ol = *o;
+    ol.stream = o->stream + (uint32_t)i;  // fresh, independent noise per level pair (multilevel.jl:58-60)
+    const int64_t li = level_first + i;
+    if (i == 0) {
+      // x[1] = sample(model, ml_schemes[1], t0, x0, nsteps*ml_steps[1], npaths[1])   (multilevel.jl:56)
+      ol.dt = o->dt / (double)ipow64(substeps, li);
+      rc = queue_level(m, kt, &ol, params, x0, false, 0.0, 1, nsteps * ipow64(substeps, li), npaths[i], payoff, i, streams[i]);
+      nq[i] = 2;
+    } else {
+      // _multilevel_sample(model, ml_schemes[i-1], ml_schemes[i], substeps, t0, x0, nsteps*ml_steps[i-1], npaths[i])
+      ol.dt = o->dt / (double)ipow64(substeps, li - 1);
+      const double dt_fine = o->dt / (double)ipow64(substeps, li);
+      rc = queue_level(m, kt, &ol, params, x0, true, dt_fine, substeps, nsteps * ipow64(substeps, li - 1), npaths[i],
+                       payoff, i, streams[i]);
+      nq[i] = 6;
+    }
+    if (rc) return rc;
+  }
+  std::vector<double> tmp((size_t)nlevels * 8, 0.0);
+  unsigned long long bad = 0;
+  if ((rc = finish_reductions(nlevels, nq, streams, tmp.data(), 8, &bad))) return rc;
+  for (int i = 0; i < nlevels; i++) {
+    double *res = result + (size_t)i * 8, *t = tmp.data() + (size_t)i * 8;
+    if (nq[i] == 2) {  // level 0: Y = Pf, no coarse partner
+      res[0] = t[0]; res[1] = t[1]; res[2] = t[0]; res[3] = t[1]; res[4] = 0.0; res[5] = 0.0; res[6] = t[2]; res[7] = t[3];
+    } else {
+      for (int q = 0; q < 8; q++) res[q] = t[q];
+    }
+    CU(cudaEventRecord(g.lvl_done[i], streams[i]));
+    CU(cudaStreamWaitEvent(st, g.lvl_done[i], 0));
+  }
+  if ((rc = timed_end())) return rc;
+  if (bad) return fail(SDEB200_E_DOMAIN, "%llu paths ended non-finite; they are excluded from the sums", bad);
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// communicator
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sdeb200_comm_unique_id(void *id128) {
+  if (!id128) return fail(SDEB200_E_ARG, "id is NULL");
+  int rc = nccl_load();
+  if (rc) return rc;
+  nccl_uid id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(id128, id.b, 128);
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_comm_init(const void *id128, int nranks, int rank) {
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(SDEB200_E_ARG, "bad communicator arguments");
+  int rc = ensure_up();
+  if (rc) return rc;
+  if ((rc = nccl_load())) return rc;
+  if (g.comm) sdeb200_comm_destroy();
+  nccl_uid id;
+  memcpy(id.b, id128, 128);
+  NC(g_nccl.CommInitRank(&g.comm, nranks, id, rank));
+  g.nranks = nranks;
+  g.rank = rank;
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_comm_destroy(void) {
+  if (g.comm && g_nccl.CommDestroy) {
+    cudaDeviceSynchronize();
+    g_nccl.CommDestroy(g.comm);
+  }
+  g.comm = nullptr;
+  g.nranks = 1;
+  g.rank = 0;
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_comm_info(int *nranks, int *rank) {
+  if (nranks) *nranks = g.nranks;
+  if (rank) *rank = g.rank;
+  return SDEB200_OK;
+}

@@ -1,0 +1,56 @@
+/* sde_args.h — plain-old-data kernel argument blocks shared by the host C-ABI layer and the device
+ * kernels (AOT-compiled by nvcc and JIT-compiled by NVRTC from the same header).  C types only. */
+#ifndef SDE_ARGS_H
+#define SDE_ARGS_H
+
+#if defined(__CUDACC_RTC__)
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#else
+#include <stdint.h>
+#endif
+
+#define SDE_MAXD 4        /* state dimension  (reference type parameter D of AbstractSDE{D,M}) */
+#define SDE_MAXM 4        /* noise dimension  (M) */
+#define SDE_MAXP 16       /* model parameters (struct fields of the generated model type) */
+#define SDE_MAXC 32       /* per-thread prepared constants (raw parameters + hoisted sub-expressions) */
+#define SDE_MAXF 4        /* payoff features reduced per path */
+#define SDE_BLOCK 128     /* threads per CTA for every path kernel */
+#define SDE_NBINS 68      /* 32-bit limbs of the exact (Kulisch-style) accumulator, held in int64 */
+#define SDE_SHARD_ALIGN 1024 /* shards start on multiples of this many paths => chunking is G-invariant */
+
+/* payoff kinds (new functionality on top of the reference) */
+#define SDE_PAYOFF_MOMENTS 0   /* features f_d = x_d, d < D */
+#define SDE_PAYOFF_CALL 1      /* disc * max(x_k - K, 0) */
+#define SDE_PAYOFF_PUT 2       /* disc * max(K - x_k, 0) */
+#define SDE_PAYOFF_COMPONENT 3 /* x_k */
+
+/* full-path layouts */
+#define SDE_LAYOUT_REFERENCE 0 /* [path][time][D]  == Julia Array{SVector{D}}(nsteps+1, npaths)   */
+#define SDE_LAYOUT_SOA 1       /* [time][D][path]  coalesced device layout */
+
+typedef struct {
+  double params[SDE_MAXP];
+  double x0[SDE_MAXD];
+  double t0, dt;
+  int64_t nsteps;    /* time steps (for mlmc: number of FINE steps = ncoarse * substeps) */
+  int64_t npaths;    /* paths handled by this launch */
+  int64_t path0;     /* global index of the first path of this launch (Philox counter, sharding) */
+  uint32_t seed_lo, seed_hi, stream;
+  int32_t payoff_kind, payoff_comp;
+  double payoff_k, payoff_disc;
+  /* mlmc only */
+  double dt_coarse;
+  int64_t substeps;
+  /* outputs (any may be null) */
+  void *out;         /* sample: [npaths][D]; simulate: see layout; mlmc: fine terminals [npaths][D] */
+  void *out2;        /* mlmc: coarse terminals [npaths][D]; simulate_wiener: the Wiener input w */
+  double *partials;  /* [nchunks][2*NF] per-CTA sums, then exactly accumulated by sde_accumulate */
+  unsigned long long *nonfinite; /* number of paths that ended non-finite (reference: DomainError) */
+  int64_t ld_paths;  /* SoA layout: leading dimension (total paths of the buffer) */
+  int64_t path_off;  /* SoA layout: column offset of this launch inside the buffer */
+} sde_args;
+
+#endif

@@ -1,0 +1,782 @@
+// sde_device.cuh — device layer of sdeb200: the Monte Carlo path-simulation hot path of SDEModels.jl
+// (src/simulation.jl:39-48,59-67,104-134; src/schemes/euler_maruyama.jl:1-6; src/schemes/milstein.jl:4-10;
+// src/multilevel.jl:65-89) written B200-first: one thread per path, state in registers, a counter-based
+// Philox4x32-10 normal generator fused into the step, warp-shuffle + CTA reduction of payoff sums,
+// coalesced / shared-memory-staged stores when full trajectories are kept.
+//
+// The same header is compiled ahead of time by nvcc (built-in BlackScholes / Heston functors) and at run
+// time by NVRTC (functors emitted by the @sde_model code generator, sde_dsl.cpp), and — math helpers only —
+// by g++ for CPU unit tests of the generator (tests/test_device_math.py).  It therefore includes nothing
+// but its own siblings.
+#pragma once
+#include "sde_args.h"
+#include "sde_coeffs.inc"
+
+#if !defined(__CUDACC_RTC__)
+#include <math.h>
+#include <string.h>
+#endif
+
+#if defined(__CUDACC__)
+#define SDE_HD __host__ __device__ __forceinline__
+#define SDE_D __device__ __forceinline__
+#else
+#define SDE_HD static inline
+#endif
+
+#ifndef SDE_STRICT
+#define SDE_STRICT 0 /* 1: reference evaluation order, translation unit compiled with -fmad=false */
+#endif
+
+namespace sdeb200 {
+
+// FP64 polynomial coefficients: one __constant__ array on the device (ptxas keeps them in uniform registers
+// as DFMA operands instead of rebuilding 64-bit immediates with two moves per use), literals on the host.
+#if defined(__CUDACC__)
+static __constant__ double sde_kd[SDE_K_N] = SDE_K_INIT;
+#endif
+#if defined(__CUDA_ARCH__)
+#define SDE_K(name) sdeb200::sde_kd[name##_I]
+#else
+#define SDE_K(name) (name##_V)
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// bit helpers (device intrinsics with host twins so the transform can be unit-tested on the CPU)
+// ---------------------------------------------------------------------------------------------------
+SDE_HD double hilo2double(uint32_t hi, uint32_t lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((int)hi, (int)lo);
+#else
+  uint64_t b = ((uint64_t)hi << 32) | lo;
+  double d;
+  memcpy(&d, &b, 8);
+  return d;
+#endif
+}
+SDE_HD uint32_t double2hi(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__double2hiint(d);
+#else
+  uint64_t b;
+  memcpy(&b, &d, 8);
+  return (uint32_t)(b >> 32);
+#endif
+}
+SDE_HD uint32_t double2lo(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__double2loint(d);
+#else
+  uint64_t b;
+  memcpy(&b, &d, 8);
+  return (uint32_t)b;
+#endif
+}
+SDE_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return __builtin_clzll(x);
+#endif
+}
+SDE_HD float bits2float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+// ~2^-22-accurate reciprocal square root seed (MUFU.RSQ64H: reads/writes the high word only)
+SDE_HD double rsqrt_seed(double a) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  return y;
+#else
+  double y = 1.0 / sqrt(hilo2double(double2hi(a), 0));
+  return hilo2double(double2hi(y), 0);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (path_lo, path_hi, block, stream), key = seed.
+// The key schedule is loop-invariant per launch; ptxas keeps the ten bumped keys in uniform registers.
+// ---------------------------------------------------------------------------------------------------
+SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t (&r)[4]) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 10; i++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// "sdeb200 normal stream v1", FP64: 128 Philox bits -> two N(0, scale2) variates (Box–Muller).
+//   X1 = r1:r0  -> u1 = m 2^-(lz+1), m in [1,2) from the 52 bits below the leading one  (u1 in (0,1))
+//   X2 = r3:r2  -> angle = X2 / 2^64 turns, reduced to |x| <= 1/8 turn + quadrant
+//   -2 ln u1 = 2 (lz+1) ln 2 + [ r Q(r) + 2 ln(1/c_j) ],  r = m/c_j - 1, |r| <= 2^-8   (128-entry table)
+//   radius by a Goldschmidt iteration on the MUFU.RSQ64H seed; sin/cos by even/odd polynomials.
+// 31 FP64-pipe instructions per pair; everything else (bit slicing, quadrant fix-up) is integer work that
+// issues beside the FP64 pipe.  tab: {1/c_j, 2 ln(1/c_j)} pairs, in shared memory on the device.
+// ---------------------------------------------------------------------------------------------------
+SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, double scale2, double &z0, double &z1) {
+  uint64_t X1 = ((uint64_t)r[1] << 32) | r[0];
+  if (X1 == 0) X1 = 1;
+  const int lz = clz64(X1);
+  const uint64_t Y = X1 << lz;
+  const uint32_t yh = (uint32_t)(Y >> 32), yl = (uint32_t)Y;
+  const double m = hilo2double(0x3FF00000u | ((yh << 1) >> 12), (yh << 21) | (yl >> 11));
+  const int j = (int)((yh >> 24) & 0x7Fu);
+  const double inv_c = tab[2 * j], tl = tab[2 * j + 1];
+  const double rr = fma(m, inv_c, -1.0);
+  double q = SDE_K(SDE_LOG_C4);
+  q = fma(q, rr, SDE_K(SDE_LOG_C3));
+  q = fma(q, rr, SDE_K(SDE_LOG_C2));
+  q = fma(q, rr, SDE_K(SDE_LOG_C1));
+  q = fma(q, rr, -2.0);
+  double w = fma(rr, q, tl);
+  w = fma((double)(lz + 1), SDE_K(SDE_TWO_LN2), w);
+  // true value >= 2^-52; rounding can push the computed one to <= 0 once in ~2^52 draws: clamp via the high word
+  if ((int32_t)double2hi(w) < 0x3C000000) w = 0x1.0p-63;
+  w *= scale2;
+  // radius = sqrt(w)
+  const double y = rsqrt_seed(w);
+  double g = w * y;
+  double h = hilo2double(double2hi(y) - 0x00100000u, 0); /* y/2: y has a zero low word */
+  const double e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  const double d = fma(-g, g, w);
+  g = fma(d, h, g);
+  // angle
+  const uint64_t X2 = ((uint64_t)r[3] << 32) | r[2];
+  const uint32_t n = (uint32_t)((X2 + (1ull << 61)) >> 62);
+  const int64_t f = (int64_t)(X2 - ((uint64_t)n << 62));
+  const double x = (double)f * 0x1.0p-64;
+  const double u = x * x;
+  double sp = SDE_K(SDE_SIN_C6);
+  sp = fma(sp, u, SDE_K(SDE_SIN_C5));
+  sp = fma(sp, u, SDE_K(SDE_SIN_C4));
+  sp = fma(sp, u, SDE_K(SDE_SIN_C3));
+  sp = fma(sp, u, SDE_K(SDE_SIN_C2));
+  sp = fma(sp, u, SDE_K(SDE_SIN_C1));
+  sp = fma(sp, u, SDE_K(SDE_SIN_C0));
+  const double s = x * sp;
+  double c = SDE_K(SDE_COS_C7);
+  c = fma(c, u, SDE_K(SDE_COS_C6));
+  c = fma(c, u, SDE_K(SDE_COS_C5));
+  c = fma(c, u, SDE_K(SDE_COS_C4));
+  c = fma(c, u, SDE_K(SDE_COS_C3));
+  c = fma(c, u, SDE_K(SDE_COS_C2));
+  c = fma(c, u, SDE_K(SDE_COS_C1));
+  c = fma(c, u, 1.0);
+  // quadrant n: 0 -> (c, s)   1 -> (-s, c)   2 -> (-c, -s)   3 -> (s, -c)
+  const bool swap = (n & 1u) != 0;
+  const double a = swap ? s : c, b = swap ? c : s;
+  const uint32_t fa = ((n + 1u) & 2u) << 30, fb = (n & 2u) << 30;
+  const double ca = hilo2double(double2hi(a) ^ fa, double2lo(a));
+  const double sb = hilo2double(double2hi(b) ^ fb, double2lo(b));
+  z0 = g * ca;
+  z1 = g * sb;
+}
+
+// FP32 stream: 128 Philox bits -> four N(0, scale2) variates.  u1 = (r + 1/2) 2^-32, angle = (int32)r' 2^-32
+// turns.  log2 and rsqrt on the MUFU unit, sin/cos by FFMA polynomials (cheaper than two more MUFU ops).
+SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, float &z0, float &z1) {
+#if defined(__CUDA_ARCH__)
+  const float u1 = fmaf(__uint2float_rn(ra), 0x1.0p-32f, 0x1.0p-33f);
+  float w = -0x1.62e430p+0f /* 2 ln 2 */ * __log2f(u1);
+#else
+  const float u1 = fmaf((float)ra, 0x1.0p-32f, 0x1.0p-33f);
+  float w = -0x1.62e430p+0f * log2f(u1);
+#endif
+  w = fmaxf(w * scale2, 0.0f);
+#if defined(__CUDA_ARCH__)
+  float g;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(w));
+#else
+  const float g = sqrtf(w);
+#endif
+  const uint32_t n = (rb + (1u << 29)) >> 30;
+  const int32_t f = (int32_t)(rb - (n << 30));
+  const float x = (float)f * 0x1.0p-32f;
+  const float u = x * x;
+  float sp = SDE_SINF_C3;
+  sp = fmaf(sp, u, SDE_SINF_C2);
+  sp = fmaf(sp, u, SDE_SINF_C1);
+  sp = fmaf(sp, u, SDE_SINF_C0);
+  const float s = x * sp;
+  float c = SDE_COSF_C4;
+  c = fmaf(c, u, SDE_COSF_C3);
+  c = fmaf(c, u, SDE_COSF_C2);
+  c = fmaf(c, u, SDE_COSF_C1);
+  c = fmaf(c, u, SDE_COSF_C0);
+  const bool swap = (n & 1u) != 0;
+  const float a = swap ? s : c, b = swap ? c : s;
+  const uint32_t fa = ((n + 1u) & 2u) << 30, fb = (n & 2u) << 30;
+#if defined(__CUDA_ARCH__)
+  z0 = g * __uint_as_float(__float_as_uint(a) ^ fa);
+  z1 = g * __uint_as_float(__float_as_uint(b) ^ fb);
+#else
+  z0 = g * (fa ? -a : a);
+  z1 = g * (fb ? -b : b);
+#endif
+}
+
+// Normals per Philox block for each precision.
+template <typename T> struct NPC;
+template <> struct NPC<double> { static constexpr int value = 2; };
+template <> struct NPC<float> { static constexpr int value = 4; };
+
+SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, double scale2, double *z) {
+  normal_pair_f64(r, tab, scale2, z[0], z[1]);
+}
+SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, float scale2, float *z) {
+  (void)tab;
+  normal_pair_f32(r[0], r[1], scale2, z[0], z[1]);
+  normal_pair_f32(r[2], r[3], scale2, z[2], z[3]);
+}
+
+constexpr int sde_gcd(int a, int b) { return b == 0 ? a : sde_gcd(b, a % b); }
+
+#if defined(__CUDACC__)
+// ===================================================================================================
+// Device-only part: kernels
+// ===================================================================================================
+static __device__ const double g_log_tab[256] = SDE_LOG_TAB_INIT;
+
+SDE_D void load_log_table(double *s_tab) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = g_log_tab[i];
+  __syncthreads();
+}
+
+template <typename T> struct Consts {
+  T c[SDE_MAXC];
+};
+
+// A batch of U steps' worth of increments for one path: dW[u*M + j] ~ N(0, dt), generated from the path's
+// sub-stream blocks [blk0, blk0 + NB).  Flat normal index q = step*M + j follows the reference's draw order
+// (path outer, step inner, M draws left to right: src/simulation.jl:4-11,42-46).
+template <typename T, int M> struct Batch {
+  static constexpr int NPB = NPC<T>::value;                              // normals per Philox block
+  static constexpr int U = (M == 0) ? 1 : NPB / sde_gcd(M, NPB);         // steps per batch
+  static constexpr int NB = (M == 0) ? 0 : (U * M) / NPB;                // Philox blocks per batch
+  static constexpr int NZ = (M == 0) ? 1 : U * M;
+};
+
+template <typename T, int M>
+SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, uint32_t k0, uint32_t k1, const double *s_tab,
+                     T scale2, T *dw) {
+  typedef Batch<T, M> B;
+  if (M == 0) {
+    dw[0] = (T)0;
+    return;
+  }
+#pragma unroll
+  for (int b = 0; b < B::NB; b++) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, k0, k1, r);
+    normals_from_block(r, s_tab, scale2, dw + b * B::NPB);
+  }
+}
+
+template <typename T> SDE_D bool all_finite(const T *x, int D) {
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++)
+    if (d < D) ok = ok && isfinite(x[d]);
+  return ok;
+}
+
+// payoff features of one terminal state
+SDE_D int payoff_features(const sde_args &a, int D, const double *x, double *f) {
+  switch (a.payoff_kind) {
+    case SDE_PAYOFF_CALL: f[0] = a.payoff_disc * fmax(x[a.payoff_comp] - a.payoff_k, 0.0); return 1;
+    case SDE_PAYOFF_PUT: f[0] = a.payoff_disc * fmax(a.payoff_k - x[a.payoff_comp], 0.0); return 1;
+    case SDE_PAYOFF_COMPONENT: f[0] = x[a.payoff_comp]; return 1;
+    default:
+#pragma unroll
+      for (int d = 0; d < SDE_MAXD; d++) f[d] = d < D ? x[d] : 0.0;
+      return D;
+  }
+}
+
+// Warp-shuffle + CTA reduction of per-thread sums; thread 0 writes the CTA's partial (fixed order =>
+// deterministic for a given path chunk, independent of how chunks are spread over GPUs).
+template <int NQ> SDE_D void block_reduce_store(double (&v)[NQ], int nq, double *s_red, double *dst) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    if (q < nq) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+      if (lane == 0) s_red[wid * NQ + q] = v[q];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < nq; q++) {
+      double s = s_red[q];
+      for (int w = 1; w < nw; w++) s += s_red[w * NQ + q];
+      dst[q] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1  terminal values: sample(model, scheme, t0, x0, nsteps, npaths)   [simulation.jl:39-48,59-67]
+//     + optional fused payoff reduction (north_star (c)).  PPT paths per thread for ILP.
+//     chunk = blockDim.x * PPT consecutive paths per CTA; path = chunk_base + p*blockDim.x + tid.
+// ---------------------------------------------------------------------------------------------------
+template <class Model, typename T, int SCHEME, int PPT>
+SDE_D void sample_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M;
+  typedef Batch<T, M> B;
+  __shared__ double s_tab[256];
+  __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
+  load_log_table(s_tab);
+
+  Consts<T> cst;
+  T prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
+  const T dt = (T)a.dt, t0 = (T)a.t0;
+  Model::prepare(prm, dt, cst.c);
+
+  const int64_t base = (int64_t)blockIdx.x * (blockDim.x * PPT);
+  T x[PPT][SDE_MAXD];
+  bool live[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; p++) {
+    live[p] = base + p * (int)blockDim.x + threadIdx.x < a.npaths;
+#pragma unroll
+    for (int d = 0; d < SDE_MAXD; d++) x[p][d] = d < D ? (T)a.x0[d] : (T)0;
+  }
+  const uint64_t gpath0 = (uint64_t)(a.path0 + base) + threadIdx.x;
+  const int64_t nbatch = a.nsteps / B::U;
+  const int rem = (int)(a.nsteps - nbatch * B::U);
+
+  for (int64_t it = 0; it < nbatch; it++) {
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+      T dw[B::NZ];
+      gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, a.seed_lo,
+                      a.seed_hi, s_tab, dt, dw);
+#pragma unroll
+      for (int u = 0; u < B::U; u++) {
+        const T t = t0 + (T)(it * B::U + u) * dt;
+        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x[p]);
+      }
+    }
+  }
+  if (rem > 0) {
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+      T dw[B::NZ];
+      gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, a.seed_lo,
+                      a.seed_hi, s_tab, dt, dw);
+#pragma unroll
+      for (int u = 0; u < B::U; u++) {
+        if (u < rem) {
+          const T t = t0 + (T)(nbatch * B::U + u) * dt;
+          Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x[p]);
+        }
+      }
+    }
+  }
+
+  // terminal states, reference layout [path][D]  (Vector{SVector{D}}: simulation.jl:59-60)
+  if (a.out) {
+    T *out = (T *)a.out;
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+      if (live[p]) {
+        const int64_t k = base + p * (int)blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int d = 0; d < D; d++) out[k * D + d] = x[p][d];
+      }
+    }
+  }
+  if (a.partials) {
+    double acc[2 * SDE_MAXF];
+#pragma unroll
+    for (int q = 0; q < 2 * SDE_MAXF; q++) acc[q] = 0.0;
+    unsigned bad = 0;
+    int nf = 1;
+#pragma unroll
+    for (int p = 0; p < PPT; p++) {
+      double xd[SDE_MAXD], f[SDE_MAXF];
+#pragma unroll
+      for (int d = 0; d < SDE_MAXD; d++) xd[d] = (double)x[p][d];
+      nf = payoff_features(a, D, xd, f);
+      if (live[p]) {
+        if (all_finite(xd, D)) {
+#pragma unroll
+          for (int q = 0; q < SDE_MAXF; q++)
+            if (q < nf) { acc[2 * q] += f[q]; acc[2 * q + 1] += f[q] * f[q]; }
+        } else {
+          bad++;
+        }
+      }
+    }
+    block_reduce_store<2 * SDE_MAXF>(acc, 2 * nf, s_red, a.partials + (int64_t)blockIdx.x * (2 * SDE_MAXF));
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
+  } else if (a.nonfinite) {
+    unsigned bad = 0;
+#pragma unroll
+    for (int p = 0; p < PPT; p++) bad += (live[p] && !all_finite(x[p], D)) ? 1u : 0u;
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4  coupled fine/coarse level pair: _multilevel_sample   [multilevel.jl:65-89]
+//     a.nsteps = number of FINE steps (ncoarse*substeps), a.dt = fine Δt, a.dt_coarse = coarse Δt.
+//     ΔW accumulates the fine increments sequentially from zero exactly as multilevel.jl:79-83 does.
+//     out = fine terminals, out2 = coarse terminals; partial features (Pf - Pc, Pf, Pc).
+// ---------------------------------------------------------------------------------------------------
+template <class Model, typename T, int SCHEME>
+SDE_D void mlmc_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M;
+  typedef Batch<T, M> B;
+  __shared__ double s_tab[256];
+  __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
+  load_log_table(s_tab);
+
+  Consts<T> cf, cc;
+  T prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
+  const T dtf = (T)a.dt, dtc = (T)a.dt_coarse, t0 = (T)a.t0;
+  Model::prepare(prm, dtf, cf.c);
+  Model::prepare(prm, dtc, cc.c);
+
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = k < a.npaths;
+  const uint64_t gpath = (uint64_t)(a.path0 + k);
+  T xf[SDE_MAXD], xc[SDE_MAXD], DW[M > 0 ? M : 1];
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++) xf[d] = xc[d] = d < D ? (T)a.x0[d] : (T)0;
+#pragma unroll
+  for (int j = 0; j < (M > 0 ? M : 1); j++) DW[j] = (T)0;
+
+  const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
+  const int substeps = (int)a.substeps;
+  int sub = 0;          // fine steps taken inside the current coarse step
+  int64_t ncoarse = 0;  // coarse steps completed
+  for (int64_t it = 0; it < nbatch; it++) {
+    T dw[B::NZ];
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, dtf, dw);
+#pragma unroll
+    for (int u = 0; u < B::U; u++) {
+      const int64_t fstep = it * B::U + u;
+      if (fstep < a.nsteps) {
+        const T tc = t0 + (T)ncoarse * dtc;
+        const T tf = tc + (T)sub * dtf;
+        const T *dwu = dw + u * (M > 0 ? M : 0);
+#pragma unroll
+        for (int j = 0; j < M; j++) DW[j] = DW[j] + dwu[j];
+        Model::template step<SCHEME>(cf.c, tf, dtf, dwu, xf);
+        if (++sub == substeps) {
+          Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
+#pragma unroll
+          for (int j = 0; j < (M > 0 ? M : 1); j++) DW[j] = (T)0;
+          sub = 0;
+          ncoarse++;
+        }
+      }
+    }
+  }
+  if (live) {
+    if (a.out) {
+#pragma unroll
+      for (int d = 0; d < D; d++) ((T *)a.out)[k * D + d] = xf[d];
+    }
+    if (a.out2) {
+#pragma unroll
+      for (int d = 0; d < D; d++) ((T *)a.out2)[k * D + d] = xc[d];
+    }
+  }
+  if (a.partials) {
+    double acc[2 * SDE_MAXF];
+#pragma unroll
+    for (int q = 0; q < 2 * SDE_MAXF; q++) acc[q] = 0.0;
+    double xd[SDE_MAXD], ff[SDE_MAXF], fc[SDE_MAXF];
+#pragma unroll
+    for (int d = 0; d < SDE_MAXD; d++) xd[d] = (double)xf[d];
+    payoff_features(a, D, xd, ff);
+    bool ok = all_finite(xd, D);
+#pragma unroll
+    for (int d = 0; d < SDE_MAXD; d++) xd[d] = (double)xc[d];
+    payoff_features(a, D, xd, fc);
+    ok = ok && all_finite(xd, D);
+    unsigned bad = 0;
+    if (live) {
+      if (ok) {
+        const double y = ff[0] - fc[0];
+        acc[0] = y; acc[1] = y * y;
+        acc[2] = ff[0]; acc[3] = ff[0] * ff[0];
+        acc[4] = fc[0]; acc[5] = fc[0] * fc[0];
+      } else {
+        bad = 1;
+      }
+    }
+    block_reduce_store<2 * SDE_MAXF>(acc, 6, s_red, a.partials + (int64_t)blockIdx.x * (2 * SDE_MAXF));
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
+  } else if (a.nonfinite) {
+    unsigned bad = (live && !(all_finite(xf, D) && all_finite(xc, D))) ? 1u : 0u;
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2a full trajectories, device layout [time][D][path]:  simulate / simulate!   [simulation.jl:71-76,104-117]
+//     VEC consecutive paths per thread -> one 16-byte streaming store per (time, d) per thread.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int VEC> struct VecStore;
+template <> struct VecStore<double, 2> {
+  static SDE_D void st(double *p, const double *v) { __stcs((double2 *)p, make_double2(v[0], v[1])); }
+};
+template <> struct VecStore<float, 4> {
+  static SDE_D void st(float *p, const float *v) { __stcs((float4 *)p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+
+template <class Model, typename T, int SCHEME>
+SDE_D void simulate_soa_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M, VEC = 16 / (int)sizeof(T);
+  typedef Batch<T, M> B;
+  __shared__ double s_tab[256];
+  load_log_table(s_tab);
+  Consts<T> cst;
+  T prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
+  const T dt = (T)a.dt, t0 = (T)a.t0;
+  Model::prepare(prm, dt, cst.c);
+
+  const int64_t k0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;  // first local path of this thread
+  if (k0 >= a.npaths) return;
+  const int nlive = (int)((a.npaths - k0) < VEC ? (a.npaths - k0) : VEC);
+  T *out = (T *)a.out;
+  const int64_t ld = a.ld_paths, col = a.path_off + k0;
+  const bool vec_ok = nlive == VEC && ((ld % VEC) == 0) && ((col % VEC) == 0) &&
+                      ((((uint64_t)out) & 15u) == 0);
+  T x[VEC][SDE_MAXD];
+#pragma unroll
+  for (int v = 0; v < VEC; v++)
+#pragma unroll
+    for (int d = 0; d < SDE_MAXD; d++) x[v][d] = d < D ? (T)a.x0[d] : (T)0;
+
+  auto store_row = [&](int64_t row) {
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+      T *p = out + (row * D + d) * ld + col;
+      T vals[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; v++) vals[v] = x[v][d];
+      if (vec_ok) {
+        VecStore<T, VEC>::st(p, vals);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+          if (v < nlive) __stcs(p + v, vals[v]);
+      }
+    }
+  };
+  store_row(0);
+  const uint64_t gpath = (uint64_t)(a.path0 + k0);
+  const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
+  for (int64_t it = 0; it < nbatch; it++) {
+    T dw[VEC][B::NZ];
+#pragma unroll
+    for (int v = 0; v < VEC; v++)
+      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, dt, dw[v]);
+#pragma unroll
+    for (int u = 0; u < B::U; u++) {
+      const int64_t i = it * B::U + u;
+      if (i < a.nsteps) {
+        const T t = t0 + (T)i * dt;
+#pragma unroll
+        for (int v = 0; v < VEC; v++) Model::template step<SCHEME>(cst.c, t, dt, dw[v] + u * (M > 0 ? M : 0), x[v]);
+        store_row(i + 1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2b full trajectories written directly in the reference's memory order [path][time][D]:
+//     each warp stages a (32 paths) x (TS time rows) tile in shared memory and writes whole path rows,
+//     so global stores stay coalesced (32 consecutive elements per instruction) without a transpose pass.
+// ---------------------------------------------------------------------------------------------------
+template <class Model, typename T, int SCHEME>
+SDE_D void simulate_ref_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M;
+  constexpr int TS = 32 / D;                 // time rows per tile
+  constexpr int ROW = TS * D;                 // elements per path per tile (<= 32)
+  constexpr int LDS = ROW | 1;                // odd stride: conflict-free column writes
+  typedef Batch<T, M> B;
+  __shared__ double s_tab[256];
+  __shared__ T s_tile[SDE_BLOCK / 32][32 * LDS];
+  load_log_table(s_tab);
+  Consts<T> cst;
+  T prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
+  const T dt = (T)a.dt, t0 = (T)a.t0;
+  Model::prepare(prm, dt, cst.c);
+
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t wbase = ((int64_t)blockIdx.x * blockDim.x + (wid << 5));  // first path of this warp
+  if (wbase >= a.npaths) return;
+  const int64_t k = wbase + lane;
+  const int nrow_live = (int)((a.npaths - wbase) < 32 ? (a.npaths - wbase) : 32);
+  T *tile = s_tile[wid];
+  T *out = (T *)a.out;
+  const int64_t nrows = a.nsteps + 1;
+  T x[SDE_MAXD];
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
+
+  int fill = 0;          // time rows currently staged
+  int64_t row0 = 0;      // first staged time row
+  auto stage = [&]() {
+#pragma unroll
+    for (int d = 0; d < D; d++) tile[lane * LDS + fill * D + d] = x[d];
+    fill++;
+  };
+  auto flush = [&]() {
+    __syncwarp();
+    const int n = fill * D;
+    for (int r = 0; r < nrow_live; r++) {
+      T *dst = out + ((wbase + r) * nrows + row0) * D;
+      for (int e = lane; e < n; e += 32) __stcs(dst + e, tile[r * LDS + e]);
+    }
+    __syncwarp();
+    row0 += fill;
+    fill = 0;
+  };
+  stage();
+  const uint64_t gpath = (uint64_t)(a.path0 + k);
+  const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
+  for (int64_t it = 0; it < nbatch; it++) {
+    T dw[B::NZ];
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, dt, dw);
+#pragma unroll
+    for (int u = 0; u < B::U; u++) {
+      const int64_t i = it * B::U + u;
+      if (i < a.nsteps) {
+        const T t = t0 + (T)i * dt;
+        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x);
+        if (fill == TS) flush();
+        stage();
+      }
+    }
+  }
+  flush();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3  Wiener-driven trajectories, in place allowed: simulate!(x, model, scheme, t0, x0, w)  [simulation.jl:119-134]
+//     w (a.out2) and x (a.out) both in reference order [path][row][.]; increments = w[i] - w[i-1].
+//     Parity entry point: with SDE_STRICT=1 the arithmetic is the reference's operation for operation.
+// ---------------------------------------------------------------------------------------------------
+template <class Model, typename T, int SCHEME>
+SDE_D void simulate_wiener_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M, MW = (M > 0 ? M : 1);
+  Consts<T> cst;
+  T prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
+  const T dt = (T)a.dt, t0 = (T)a.t0;
+  Model::prepare(prm, dt, cst.c);
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.npaths) return;
+  const int64_t nrows = a.nsteps + 1;
+  const T *w = (const T *)a.out2 + k * nrows * MW;
+  T *xo = (T *)a.out + k * nrows * D;
+  T x[SDE_MAXD], wprev[MW], dw[MW];
+#pragma unroll
+  for (int j = 0; j < MW; j++) wprev[j] = w[j];
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
+#pragma unroll
+  for (int d = 0; d < D; d++) xo[d] = x[d];
+  for (int64_t i = 1; i < nrows; i++) {
+    const T t = t0 + (T)(i - 1) * dt;
+#pragma unroll
+    for (int j = 0; j < MW; j++) {
+      const T wn = w[i * MW + j];
+      dw[j] = wn - wprev[j];
+      wprev[j] = wn;
+    }
+    Model::template step<SCHEME>(cst.c, t, dt, dw, x);
+#pragma unroll
+    for (int d = 0; d < D; d++) xo[i * D + d] = x[d];
+  }
+}
+
+// K6  drift / diffusion evaluation at one point (functor known-answer tests, test/runtests.jl:61-82).
+//     out[0..D) = drift, out[D .. D + D*max(M,1)) = diffusion, row-major.
+template <class Model>
+SDE_D void coef_eval_body(const sde_args &a) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double prm[SDE_MAXP], x[SDE_MAXD], mu[SDE_MAXD], sig[SDE_MAXD * SDE_MAXM];
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = a.params[i];
+  for (int d = 0; d < SDE_MAXD; d++) { x[d] = a.x0[d]; mu[d] = 0.0; }
+  for (int i = 0; i < SDE_MAXD * SDE_MAXM; i++) sig[i] = 0.0;
+  Model::coefficients(prm, a.t0, x, mu, sig);
+  double *out = (double *)a.out;
+  constexpr int D = Model::D, MW = Model::M > 0 ? Model::M : 1;
+  for (int d = 0; d < D; d++) out[d] = mu[d];
+  for (int i = 0; i < D; i++)
+    for (int j = 0; j < MW; j++) out[D + i * MW + j] = sig[i * SDE_MAXM + j];
+}
+
+#define SDE_EM 0
+#define SDE_MILSTEIN 1
+
+// Kernel entry points for one model type, scheme and precision.  TAG makes the symbols unique.  The
+// reference defines Milstein for M == 1 models only (milstein.jl:4): instantiate SCH = 1 only there.
+#define SDE_KERNELS(MODEL, TAG, SCH, SNAME, T, PNAME)                                                            \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_##SNAME##_##PNAME(                \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 2>(a); }                       \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_mlmc_##SNAME##_##PNAME(                  \
+      const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, T, SCH>(a); }                            \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_##SNAME##_##PNAME(                \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }
+
+#define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \
+  SDE_KERNELS(MODEL, TAG, SCH, SNAME, double, f64)  \
+  SDE_KERNELS(MODEL, TAG, SCH, SNAME, float, f32)
+
+#define SDE_KERNELS_COEF(MODEL, TAG)                                                                             \
+  extern "C" __global__ void sdek_##TAG##_coef(const __grid_constant__ sde_args a) {                            \
+    sdeb200::coef_eval_body<MODEL>(a);                                                                           \
+  }
+
+#endif  // __CUDACC__
+
+}  // namespace sdeb200

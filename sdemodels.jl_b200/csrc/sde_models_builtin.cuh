@@ -1,0 +1,101 @@
+// sde_models_builtin.cuh — hand-written device functors for the two registry models the benchmark
+// configurations name: BlackScholes (src/models/black_scholes.jl:1) and Heston (src/models/models.jl:44-48).
+// They have exactly the interface the @sde_model code generator emits for arbitrary models (sde_dsl.cpp):
+//
+//   D, M, NP                         dim(model) and the number of struct fields (parameter order pinned by
+//                                    test/runtests.jl:51-53)
+//   prepare(p, dt, c)                hoists parameter-only sub-expressions once per thread
+//   step<SCHEME>(c, t, dt, dw, x)    one scheme step in place: euler_maruyama.jl:1-6 / milstein.jl:4-10
+//   coefficients(p, t, x, mu, sig)   drift / diffusion (Cholesky of the correlation folded in, codegen.jl:112)
+//
+// SDE_STRICT=1 (translation unit compiled with -fmad=false): the reference's literal operation order
+//  — bit-identical to the CPU oracle.  SDE_STRICT=0: algebraically identical forms with
+// loop invariants hoisted and FMAs, the throughput path.
+#pragma once
+#include "sde_device.cuh"
+
+namespace sdeb200 {
+
+SDE_HD double sde_sqrt(double v) { return sqrt(v); }
+SDE_HD float sde_sqrt(float v) { return sqrtf(v); }
+SDE_HD double sde_fma(double a, double b, double c) { return fma(a, b, c); }
+SDE_HD float sde_fma(float a, float b, float c) { return fmaf(a, b, c); }
+
+struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
+  static constexpr int D = 1, M = 1, NP = 2;
+  template <typename T> SDE_HD static void prepare(const T *p, T dt, T *c) {
+    c[0] = p[0];
+    c[1] = p[1];
+#if !SDE_STRICT
+    c[2] = p[0] * dt;                 // r Δt
+    c[3] = (T)0.5 * p[1] * p[1];      // σ²/2
+#else
+    (void)dt;
+#endif
+  }
+  template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
+    (void)t;
+    const T S = x[0], w = dw[0];
+#if SDE_STRICT
+    const T mu = c[0] * S, sg = c[1] * S;
+    T y = (S + mu * dt) + sg * w;
+    if (SCHEME == 1) y = y + ((c[1] * sg) * (w * w - dt)) / (T)2;  // ∂σ = σ exactly (ForwardDiff dual of σ*x)
+    x[0] = y;
+#else
+    T a = sde_fma(c[1], w, c[2]);
+    if (SCHEME == 1) a = sde_fma(c[3], sde_fma(w, w, -dt), a);
+    x[0] = sde_fma(S, a, S);
+#endif
+  }
+  SDE_HD static void coefficients(const double *p, double t, const double *x, double *mu, double *sig) {
+    (void)t;
+    mu[0] = p[0] * x[0];
+    sig[0] = p[1] * x[0];
+  }
+};
+
+struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)*dW2 ; dW1*dW2 = ρ*dt ; params (r, κ, θ, σ, ρ)
+  static constexpr int D = 2, M = 2, NP = 5;
+  template <typename T> SDE_HD static void prepare(const T *p, T dt, T *c) {
+#if SDE_STRICT
+    (void)dt;
+    for (int i = 0; i < 5; i++) c[i] = p[i];
+    c[5] = sde_sqrt((T)1 - p[4] * p[4]);  // sqrt(1 - ρ^2): parameter-only, same value every step
+#else
+    c[0] = p[0] * dt;                      // r Δt
+    c[1] = (T)1 - p[1] * dt;               // 1 - κ Δt
+    c[2] = p[1] * p[2] * dt;               // κ θ Δt
+    c[3] = p[3] * p[4];                    // σ ρ
+    c[4] = p[3] * sde_sqrt((T)1 - p[4] * p[4]);  // σ sqrt(1 - ρ²)
+#endif
+  }
+  template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
+    (void)t;
+    static_assert(SCHEME == 0, "the reference defines Milstein for M == 1 models only (milstein.jl:4)");
+    const T S = x[0], V = x[1];
+    const T sv = sde_sqrt(V);
+#if SDE_STRICT
+    const T mu1 = c[0] * S, mu2 = c[1] * (c[2] - V);
+    const T s11 = sv * S, s21 = (c[3] * sv) * c[4], s22 = (c[3] * sv) * c[5];
+    x[0] = (S + mu1 * dt) + s11 * dw[0];                  // + 0.0*dw[1] is exact for finite increments
+    x[1] = (V + mu2 * dt) + (s21 * dw[0] + s22 * dw[1]);
+#else
+    (void)dt;
+    x[0] = sde_fma(S, sde_fma(sv, dw[0], c[0]), S);
+    const T n = sde_fma(c[4], dw[1], c[3] * dw[0]);
+    x[1] = sde_fma(sv, n, sde_fma(V, c[1], c[2]));
+#endif
+  }
+  SDE_HD static void coefficients(const double *p, double t, const double *x, double *mu, double *sig) {
+    (void)t;
+    const double sv = sqrt(x[1]);
+    mu[0] = p[0] * x[0];
+    mu[1] = p[1] * (p[2] - x[1]);
+    sig[0 * SDE_MAXM + 0] = sv * x[0];
+    sig[0 * SDE_MAXM + 1] = 0.0;
+    sig[1 * SDE_MAXM + 0] = (p[3] * sv) * p[4];
+    sig[1 * SDE_MAXM + 1] = (p[3] * sv) * sqrt(1.0 - p[4] * p[4]);
+  }
+};
+
+}  // namespace sdeb200

@@ -1,0 +1,298 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances (BASELINE.md §5 / north_star): FP64 trajectories on identical Wiener increments <= 1e-12 relative
+(bit-identical in STRICT math), FP32 <= 1e-5 relative; on-device RNG estimates within 3 standard errors.
+"""
+import numpy as np
+import pytest
+
+from conftest import BS_P, HESTON_P
+
+pytestmark = pytest.mark.gpu
+
+EM, MIL = 0, 1
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def wiener_paths(O, npaths, nsteps, dim, dt, seed):
+    z = np.random.default_rng(seed).standard_normal((npaths, nsteps, dim))
+    return O.wiener_z(dt, z)
+
+
+CASES = [
+    ("BlackScholes", BS_P, 100.0, EM, 252),
+    ("BlackScholes", BS_P, 100.0, MIL, 512),
+    ("Heston", HESTON_P, [100.0, 0.4], EM, 1024),
+]
+
+
+def _model(gpu, name, params):
+    return getattr(gpu, name)(*params)
+
+
+def _scheme(gpu, sid, dt):
+    return gpu.EulerMaruyama(dt) if sid == EM else gpu.Milstein(dt)
+
+
+@pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
+def test_wiener_driven_strict_is_bit_identical(gpu, O, name, params, x0, sid, nsteps):
+    """simulate!(x, model, scheme, t0, x0, w): STRICT math reproduces the oracle bit for bit."""
+    dt = 1.0 / nsteps
+    D, M, _ = O.dims(name)
+    w = wiener_paths(O, 257, nsteps, M, dt, 1)
+    ref = O.simulate_wiener(name, sid, params, 0.0, dt, x0, w)
+    x = np.empty_like(ref)
+    xs = x[..., 0] if D == 1 else x
+    ws = w[..., 0] if M == 1 else w
+    gpu.simulate_(xs, _model(gpu, name, params), _scheme(gpu, sid, dt), 0.0, x0, np.ascontiguousarray(ws), math="strict")
+    assert np.array_equal(x, ref)
+
+
+@pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
+def test_wiener_driven_fast_within_1e12(gpu, O, name, params, x0, sid, nsteps):
+    dt = 1.0 / nsteps
+    D, M, _ = O.dims(name)
+    w = wiener_paths(O, 300, nsteps, M, dt, 2)
+    ref = O.simulate_wiener(name, sid, params, 0.0, dt, x0, w)
+    x = np.empty_like(ref)
+    xs = x[..., 0] if D == 1 else x
+    ws = w[..., 0] if M == 1 else w
+    gpu.simulate_(xs, _model(gpu, name, params), _scheme(gpu, sid, dt), 0.0, x0, np.ascontiguousarray(ws), math="fast")
+    assert rel_err(x, ref) <= 1e-12
+
+
+@pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
+def test_wiener_driven_f32_within_1e5(gpu, O, name, params, x0, sid, nsteps):
+    dt = 1.0 / nsteps
+    D, M, _ = O.dims(name)
+    w = wiener_paths(O, 130, nsteps, M, dt, 3).astype(np.float32)
+    ref = O.simulate_wiener(name, sid, params, 0.0, dt, x0, w.astype(np.float64))
+    x = np.empty(ref.shape, dtype=np.float32)
+    xs = x[..., 0] if D == 1 else x
+    ws = w[..., 0] if M == 1 else w
+    gpu.simulate_(xs, _model(gpu, name, params), _scheme(gpu, sid, dt), 0.0, x0, np.ascontiguousarray(ws))
+    # FP32 rounding accumulates over the trajectory: compare terminal S relative, all rows with a path-length factor
+    assert rel_err(x[:, -1, 0], ref[:, -1, 0]) <= 2e-4
+    assert rel_err(x[:, :32], ref[:, :32]) <= 1e-5
+
+
+def test_wiener_driven_in_place(gpu, O):
+    """x === w is allowed (simulation.jl:120)."""
+    name, params, x0, nsteps = "Heston", HESTON_P, [100.0, 0.4], 64
+    dt = 1.0 / nsteps
+    w = wiener_paths(O, 40, nsteps, 2, dt, 4)
+    ref = O.simulate_wiener(name, EM, params, 0.0, dt, x0, w.copy())
+    buf = w.copy()
+    gpu.simulate_(buf, _model(gpu, name, params), gpu.EulerMaruyama(dt), 0.0, x0, buf, math="strict")
+    assert np.array_equal(buf, ref)
+
+
+@pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
+@pytest.mark.parametrize("math", ["fast", "strict"])
+def test_sample_matches_oracle_on_the_same_normal_stream(gpu, O, name, params, x0, sid, nsteps, math):
+    """RNG-driven terminal values, path by path: the oracle consumes the normals of the documented
+    Philox stream (oracle/philox_spec.c) through the reference's sample loop (simulation.jl:39-48)."""
+    dt = 1.0 / nsteps
+    D, M, _ = O.dims(name)
+    npaths, seed, stream, off = 300, 12345, 7, 1000
+    z = O.normals_paths(seed, stream, off, npaths, nsteps, M)
+    ref = O.sample_z(name, sid, params, 0.0, dt, x0, z)
+    got = gpu.sample(_model(gpu, name, params), _scheme(gpu, sid, dt), 0.0, x0, nsteps, npaths, seed=seed,
+                     stream=stream, path_offset=off, math=math)
+    got = got.reshape(npaths, D)
+    assert rel_err(got, ref) <= 1e-11
+
+
+def test_sample_f32_matches_oracle_on_the_same_normal_stream(gpu, O):
+    name, params, x0, nsteps = "Heston", HESTON_P, [100.0, 0.4], 256
+    dt = 1.0 / nsteps
+    npaths = 200
+    z = O.normals_paths(9, 0, 0, npaths, nsteps, 2, "f32")
+    ref = O.sample_z(name, EM, params, 0.0, dt, x0, z)
+    got = gpu.sample(_model(gpu, name, params), gpu.EulerMaruyama(dt), 0.0, x0, nsteps, npaths, seed=9, precision="f32")
+    assert got.dtype == np.float32
+    assert rel_err(got, ref) <= 5e-4
+
+
+@pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_simulate_layouts_agree_and_end_in_sample(gpu, name, params, x0, sid, nsteps, precision):
+    """Full trajectories: reference layout == transposed SoA layout, row 0 == x0, last row == sample()."""
+    nsteps = min(nsteps, 200)
+    dt = 1.0 / nsteps
+    m, sch = _model(gpu, name, params), _scheme(gpu, sid, dt)
+    npaths = 1000
+    xr, t = gpu.simulate(m, sch, 0.0, x0, nsteps, npaths, seed=5, precision=precision)
+    xs, _ = gpu.simulate(m, sch, 0.0, x0, nsteps, npaths, seed=5, precision=precision, layout="soa")
+    term = gpu.sample(m, sch, 0.0, x0, nsteps, npaths, seed=5, precision=precision)
+    D = m._D
+    xr3 = xr.reshape(npaths, nsteps + 1, D)
+    xs3 = xs.reshape(nsteps + 1, D, npaths)
+    assert np.array_equal(xr3, np.transpose(xs3, (2, 0, 1)))
+    assert np.array_equal(xr3[:, 0, :], np.broadcast_to(np.atleast_1d(np.asarray(x0, dtype=xr.dtype)), (npaths, D)))
+    assert np.array_equal(xr3[:, -1, :], term.reshape(npaths, D))
+    assert t.shape == (nsteps + 1,) and t[0] == 0.0 and abs(t[-1] - 1.0) < 1e-12
+
+
+def test_simulate_trajectory_matches_oracle_rows(gpu, O):
+    name, params, x0, nsteps = "BlackScholes", BS_P, 100.0, 77
+    dt = 1.0 / nsteps
+    npaths = 150
+    z = O.normals_paths(3, 2, 0, npaths, nsteps, 1)
+    ref = O.simulate_z(name, MIL, params, 0.0, dt, x0, z)[..., 0]
+    x, _ = gpu.simulate(_model(gpu, name, params), gpu.Milstein(dt), 0.0, x0, nsteps, npaths, seed=3, stream=2)
+    assert rel_err(x, ref) <= 1e-11
+
+
+def test_device_resident_outputs(gpu):
+    import torch
+    m, sch = gpu.Heston(*HESTON_P), gpu.EulerMaruyama(1 / 64)
+    a = gpu.sample(m, sch, 0.0, [100.0, 0.4], 64, 5000, seed=1)
+    b = gpu.sample(m, sch, 0.0, [100.0, 0.4], 64, 5000, seed=1, device=True)
+    assert isinstance(b, torch.Tensor) and b.is_cuda
+    assert np.array_equal(a, b.cpu().numpy())
+
+
+def test_sharded_paths_reproduce_the_single_launch(gpu):
+    """path_offset: two shards of one logical run == the run itself (multi-GPU partitioning)."""
+    m, sch = gpu.Heston(*HESTON_P), gpu.EulerMaruyama(1 / 32)
+    full = gpu.sample(m, sch, 0.0, [100.0, 0.4], 32, 5000, seed=8)
+    lo = gpu.sample(m, sch, 0.0, [100.0, 0.4], 32, 2048, seed=8)
+    hi = gpu.sample(m, sch, 0.0, [100.0, 0.4], 32, 5000 - 2048, seed=8, path_offset=2048)
+    assert np.array_equal(full, np.concatenate([lo, hi]))
+
+
+@pytest.mark.parametrize("substeps,ncoarse", [(2, 16), (4, 10)])
+def test_coupled_level_matches_oracle(gpu, O, substeps, ncoarse):
+    """_multilevel_sample (multilevel.jl:65-89): same increments drive fine and coarse paths."""
+    name, params, x0 = "Heston", HESTON_P, [100.0, 0.4]
+    dtc = 1.0 / ncoarse
+    dtf = O.level_dt(dtc, substeps, 1)
+    npaths = 200
+    z = O.normals_paths(21, 3, 0, npaths, ncoarse * substeps, 2)
+    rc, rf = O.multilevel_sample_z(name, EM, params, 0.0, dtc, dtf, substeps, x0, z)
+    coarse = gpu.EulerMaruyama(dtc)
+    fine = gpu.subdivide(coarse, substeps)
+    assert fine.dt == dtf
+    xc, xf = gpu.multilevel_sample_level(gpu.Heston(*params), coarse, fine, substeps, 0.0, x0, ncoarse, npaths,
+                                         seed=21, stream=3)
+    assert rel_err(xf, rf) <= 1e-11 and rel_err(xc, rc) <= 1e-11
+    # the fine path of the pair is the plain sample with the fine scheme on the same stream
+    plain = gpu.sample(gpu.Heston(*params), fine, 0.0, x0, ncoarse * substeps, npaths, seed=21, stream=3)
+    assert np.array_equal(plain, xf)
+
+
+def test_reference_multilevel_testset(gpu):
+    """test/runtests.jl:99-122 replayed: fine path of _multilevel_simulate == simulate!(fine) on the same
+    Wiener path; terminals of _multilevel_sample == last rows of _multilevel_simulate (tolerances of the
+    reference: sum of squared norms <= 1e-16 resp. 1e-13)."""
+    S = gpu
+    substeps = 4
+    coarse = S.EulerMaruyama(0.1)
+    fine = S.subdivide(coarse, substeps)
+    x0 = [100.0, 0.4]
+    m2 = S.Heston(*HESTON_P)
+    xc, xf, tc, tf = S.multilevel_simulate_level(m2, coarse, fine, substeps, 0.0, x0, 10, 100, seed=0)
+    assert xf.shape == (100, 41, 2) and xc.shape == (100, 11, 2)
+    assert np.allclose(tf, 0.0 + fine.dt * np.arange(41)) and np.array_equal(tc, tf[::4])
+    # wiener! consumes the stream like simulate! does: the same seed gives the same fine trajectory
+    w = np.zeros((100, 41, 2))
+    S.wiener_(w, fine.dt, seed=0)
+    x = np.empty_like(w)
+    S.simulate_(x, m2, fine, 0.0, x0, w)
+    assert np.sum((xf - x) ** 2) <= 1e-16
+    yc, yf = S.multilevel_sample_level(m2, coarse, fine, substeps, 0.0, x0, 10, 100, seed=0)
+    assert np.sum((xf[:, -1] - yf) ** 2) <= 1e-12 * 100 ** 2  # Σδw vs differenced running sum: rounding only
+    assert np.sum((xc[:, -1] - yc) ** 2) <= 1e-12 * 100 ** 2
+    ml = S.MultilevelScheme(coarse, 4, range(0, 5))
+    xs, ts = S.simulate(m2, ml, 0.0, x0, 1, 1, seed=0)
+    assert len(xs) == 9 and len({(round(t[0], 12), round(t[-1], 12)) for t in ts}) == 1
+    smp = S.sample(m2, ml, 0.0, x0, 1, 1, seed=0)
+    assert len(smp) == 9
+    for a, b in zip(xs, smp):
+        assert np.sum(np.abs(a[:, -1] - b)) <= 1e-9
+
+
+def test_estimate_equals_mean_of_sample(gpu):
+    """estimate == mean(payoff.(sample(...))) — and the exact accumulator returns the correctly rounded sum."""
+    import math
+    m, sch = gpu.Heston(*HESTON_P), gpu.EulerMaruyama(1 / 64)
+    n = 70001
+    x = gpu.sample(m, sch, 0.0, [100.0, 0.4], 64, n, seed=4)
+    e = gpu.estimate(m, sch, gpu.Moments(), 0.0, [100.0, 0.4], 64, n, seed=4)
+    assert e.n == n and e.nonfinite == 0
+    assert abs(e.sums[0, 0] - math.fsum(x[:, 0])) / e.sums[0, 0] <= 1e-13
+    assert abs(e.sums[1, 0] - math.fsum(x[:, 1])) / e.sums[1, 0] <= 1e-13
+    assert abs(e.sums[0, 1] - math.fsum(x[:, 0] ** 2)) / e.sums[0, 1] <= 1e-13
+    disc = math.exp(-0.01)
+    c = gpu.estimate(m, sch, gpu.Call(100.0, disc), 0.0, [100.0, 0.4], 64, n, seed=4)
+    pay = disc * np.maximum(x[:, 0] - 100.0, 0.0)
+    assert abs(c.mean[0] - pay.mean()) <= 1e-10 and abs(c.stderr[0] - pay.std(ddof=1) / math.sqrt(n)) <= 1e-10
+
+
+def test_estimate_is_invariant_under_sharding(gpu):
+    """Bit-identical sums for 1 and 2 shards (host-combined limbs stand in for the NCCL all-reduce)."""
+    m, sch = gpu.Heston(*HESTON_P), gpu.EulerMaruyama(1 / 16)
+    n = 50000
+    full = gpu.estimate(m, sch, gpu.Moments(), 0.0, [100.0, 0.4], 16, n, seed=2)
+    lo, hi = gpu.shard_range(n, 0, 2), gpu.shard_range(n, 1, 2)
+    a = gpu.estimate(m, sch, gpu.Moments(), 0.0, [100.0, 0.4], 16, lo[1] - lo[0], seed=2, path_offset=lo[0])
+    b = gpu.estimate(m, sch, gpu.Moments(), 0.0, [100.0, 0.4], 16, hi[1] - hi[0], seed=2, path_offset=hi[0])
+    assert a.n + b.n == n
+    # per-shard sums are exact sums of the same per-chunk partials: their exact total rounds to the same double
+    from fractions import Fraction
+    for q in range(2):
+        for k in range(2):
+            tot = Fraction(a.sums[q, k]) + Fraction(b.sums[q, k])
+            assert abs(float(tot) - full.sums[q, k]) <= abs(full.sums[q, k]) * 2.3e-16
+
+
+def test_c1_blackscholes_mean_within_3se(gpu):
+    """C1: BlackScholes EM 10^6 x 252, closed-form E[S_N] = 100 (1 + r Δt)^N."""
+    m, sch = gpu.BlackScholes(*BS_P), gpu.EulerMaruyama(1 / 252)
+    e = gpu.estimate(m, sch, gpu.Moments(), 0.0, 100.0, 252, 10 ** 6, seed=0)
+    assert abs(e.mean[0] - 101.00499666826876) <= 3 * e.stderr[0]
+    assert abs(e.stderr[0] - 0.030992) < 0.001
+    second = 100.0 ** 2 * ((1 + 0.01 / 252) ** 2 + 0.3 ** 2 / 252) ** 252
+    assert abs(e.sums[0, 1] / e.n - second) / second < 5e-3
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_heston_moments_within_3se(gpu, precision):
+    m, sch = gpu.Heston(*HESTON_P), gpu.EulerMaruyama(1 / 1024)
+    e = gpu.estimate(m, sch, gpu.Moments(), 0.0, [100.0, 0.4], 1024, 2 * 10 ** 6, seed=1, precision=precision)
+    assert abs(e.mean[0] - 101.00501177656254) <= 3 * e.stderr[0] + (2e-3 if precision == "f32" else 0)
+    assert abs(e.mean[1] - 0.3000043222543304) <= 3 * e.stderr[1] + (2e-5 if precision == "f32" else 0)
+    assert e.nonfinite == 0
+
+
+def test_milstein_rejected_for_heston(gpu):
+    with pytest.raises(gpu.SDEB200Error) as ei:
+        gpu.sample(gpu.Heston(*HESTON_P), gpu.Milstein(0.01), 0.0, [100.0, 0.4], 10, 10)
+    assert ei.value.code == gpu._lib.E_UNSUPPORTED
+
+
+def test_negative_variance_raises_domain_error(gpu):
+    """sqrt(V < 0): Julia throws DomainError; here the non-finite paths are counted and reported."""
+    m = gpu.Heston(0.01, 10.0, 0.3, 3.0, 0.4)  # huge vol-of-vol with a coarse step drives V negative
+    with pytest.raises(gpu.DomainError):
+        gpu.sample(m, gpu.EulerMaruyama(0.25), 0.0, [100.0, 0.05], 8, 4096, seed=0)
+
+
+def test_mlmc_estimator_call_price(gpu):
+    """C4 (reduced): Heston call, levels 0..5; the telescoping sum matches the finest-level plain estimate
+    within 3 SE and the semi-analytic price 22.3375 within bias + 3 SE."""
+    import math
+    S = gpu
+    m = S.Heston(*HESTON_P)
+    ml = S.MultilevelScheme(S.EulerMaruyama(1 / 16), 2, range(0, 6))
+    n = [2 ** (19 - l) for l in range(6)]
+    pay = S.Call(100.0, math.exp(-0.01))
+    est = S.ml_estimate(m, ml, pay, 0.0, [100.0, 0.4], 16, n, seed=11)
+    assert np.all(est.nonfinite == 0) and list(est.n) == n
+    assert np.all(np.abs(est.level_mean[1:]) < 1.0) and est.level_var[-1] < est.level_var[1]
+    assert abs(est.mean - 22.3374853590066) <= 3 * est.stderr + 0.15
