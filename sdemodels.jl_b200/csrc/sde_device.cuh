@@ -251,7 +251,15 @@ SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, float 
   normal_pair_f32(r[2], r[3], scale2, z[2], z[3]);
 }
 
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 constexpr int sde_gcd(int a, int b) { return b == 0 ? a : sde_gcd(b, a % b); }
+
+#if !defined(__CUDACC__)
+// host twin of the log table, for the CPU unit tests of the transform (tests/host_math_harness.cpp)
+static const double h_log_tab[256] = SDE_LOG_TAB_INIT;
+#endif
 
 #if defined(__CUDACC__)
 // ===================================================================================================

@@ -1,0 +1,39 @@
+// Compiles the math helpers of sde_device.cuh with g++ (no CUDA) so the Philox block function and the
+// fused normal transforms can be checked on the CPU against oracle/philox_spec.c.
+#include "../sdemodels.jl_b200/csrc/sde_device.cuh"
+using namespace sdeb200;
+
+extern "C" void h_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+  uint32_t r[4];
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], r);
+  for (int i = 0; i < 4; i++) out[i] = r[i];
+}
+extern "C" void h_normals_f64(uint64_t seed, uint32_t stream, uint64_t path, uint64_t q0, int64_t n, double scale2,
+                              double *out) {
+  for (int64_t i = 0; i < n; i++) {
+    const uint64_t q = q0 + (uint64_t)i;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(q >> 1), stream, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    double z[2];
+    normal_pair_f64(r, h_log_tab, scale2, z[0], z[1]);
+    out[i] = z[q & 1];
+  }
+}
+extern "C" void h_normals_f32(uint64_t seed, uint32_t stream, uint64_t path, uint64_t q0, int64_t n, float scale2,
+                              float *out) {
+  for (int64_t i = 0; i < n; i++) {
+    const uint64_t q = q0 + (uint64_t)i;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(q >> 2), stream, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    float z[4];
+    normals_from_block(r, nullptr, scale2, z);
+    out[i] = z[q & 3];
+  }
+}
+// raw transform on chosen bits (edge cases: tails, u1 -> 1, quadrant boundaries)
+extern "C" void h_pair_from_bits(const uint32_t *r4, double scale2, double *z) {
+  uint32_t r[4] = {r4[0], r4[1], r4[2], r4[3]};
+  normal_pair_f64(r, h_log_tab, scale2, z[0], z[1]);
+}

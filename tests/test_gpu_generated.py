@@ -1,0 +1,159 @@
+"""GPU tests of the @sde_model -> NVRTC path: functors generated from equation text, compiled at run time,
+driven through the same kernels as the built-ins.  The reference's own model / drift / diffusion / simulation
+testsets (test/runtests.jl:50-97) are replayed against the device."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import BS_P, HESTON_P
+from test_dsl import CASES, MODELS
+
+pytestmark = pytest.mark.gpu
+EM, MIL = 0, 1
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+_cache = {}
+
+
+def gen(gpu, name):
+    if name not in _cache:
+        _cache[name] = gpu.sde_model(name + "_g", MODELS.get(name) or gpu.REGISTRY[name])
+    return _cache[name]
+
+
+def test_reference_drift_testset_on_device(gpu):
+    # runtests.jl:61-72 (corrected_drift is outside the hot path)
+    S = gpu
+    m1, m2 = gen(S, "BlackScholes")(*BS_P), gen(S, "Heston")(*HESTON_P)
+    m3 = gen(S, "TestModel")(1, 2, 3, 4, 5, 6)
+    assert np.isclose(S.drift(m1, 0.0, 100.0), 100.0 * 0.01)
+    assert np.allclose(S.drift(m2, 0.0, [100.0, 0.4]), [0.01 * 100.0, 10.0 * (0.3 - 0.4)])
+    assert np.allclose(S.drift(m3, 0.0, [0.1, 0.2, 0.3]), [0.2 * 1, 0.3 * 2, 0.1 * 3])
+    assert S.drift(gen(S, "Wiener")(), 0.0, 100.0) == 0.0
+    assert S.drift(gen(S, "Deterministic")(), 0.0, 100.0) == 100.0
+    td = gen(S, "TimeDependent")(1, 2)
+    assert S.drift(td, 0.0, 3.0) != S.drift(td, 1.0, 3.0)
+    assert np.isclose(S.drift(td, 4.0, 3.0), 12)
+    # the built-in functors answer the same
+    assert S.drift(S.BlackScholes(*BS_P), 0.0, 100.0) == S.drift(m1, 0.0, 100.0)
+    assert np.array_equal(S.drift(S.Heston(*HESTON_P), 0.0, [100.0, 0.4]), S.drift(m2, 0.0, [100.0, 0.4]))
+
+
+def test_reference_diffusion_testset_on_device(gpu):
+    # runtests.jl:75-82
+    S = gpu
+    assert np.isclose(S.diffusion(gen(S, "BlackScholes")(*BS_P), 0.0, 100.0), 100.0 * 0.3)
+    want = [[100.0 * math.sqrt(0.4), 0.0], [0.4 * 0.1 * math.sqrt(0.4), math.sqrt(1 - 0.4 ** 2) * 0.1 * math.sqrt(0.4)]]
+    assert np.allclose(S.diffusion(gen(S, "Heston")(*HESTON_P), 0.0, [100.0, 0.4]), want)
+    assert np.array_equal(S.diffusion(S.Heston(*HESTON_P), 0.0, [100.0, 0.4]),
+                          S.diffusion(gen(S, "Heston")(*HESTON_P), 0.0, [100.0, 0.4]))
+    assert np.allclose(S.diffusion(gen(S, "TestModel")(1, 2, 3, 4, 5, 6), 0.0, [0.1, 0.2, 0.3]),
+                       [[4, 5, 0, 0], [0, 1, 1, 0], [0, 0, 6, -1]])
+    assert S.diffusion(gen(S, "Wiener")(), 0.0, 100.0) == 1.0
+    assert S.diffusion(gen(S, "Deterministic")(), 0.0, 100.0) == 0.0
+
+
+def test_reference_simulation_testset(gpu):
+    # runtests.jl:84-97 (numpy order: Julia (2, 501) == numpy (501, 2))
+    S = gpu
+    m1, m2 = gen(S, "BlackScholes")(*BS_P), gen(S, "Heston")(*HESTON_P)
+    assert S.simulate(m1, S.EulerMaruyama(0.01), 0.0, 100.0, 1000)[0].shape == (1001,)
+    assert S.simulate(m1, S.Milstein(0.01), 0.0, 100.0, 1000)[0].shape == (1001,)
+    assert S.simulate(m2, S.EulerMaruyama(0.01), 0.0, [100.0, 0.4], 500)[0].shape == (501, 2)
+    det = gen(S, "Deterministic")()
+    assert np.isclose(S.sample(det, S.EulerMaruyama(1), 0.0, 1.0, 1), 2)
+    assert np.allclose(S.simulate(det, S.EulerMaruyama(1.0), 0.0, 1.0, 5)[0], [1, 2, 4, 8, 16, 32])
+    assert S.simulate(gen(S, "SpecialCaseModel1")(), S.EulerMaruyama(0.01), 0.0, [100.0], 1000)[0].shape == (1001, 1)
+    assert S.simulate(gen(S, "SpecialCaseModel2")(), S.EulerMaruyama(0.01), 0.0, [100.0, 100.0], 1000)[0].shape == (1001, 2)
+    assert S.simulate(gen(S, "SpecialCaseModel3")(), S.EulerMaruyama(0.01), 0.0, [100.0] * 3, 1000)[0].shape == (1001, 3)
+    # Milstein has no method for M != 1 (runtests.jl:90,92 are commented out for that reason)
+    with pytest.raises(S.SDEB200Error):
+        S.sample(det, S.Milstein(1.0), 0.0, 1.0, 1)
+
+
+@pytest.mark.parametrize("name,params,x,t", CASES)
+def test_generated_models_match_oracle_path_by_path(gpu, O, name, params, x, t):
+    """Every model: RNG-driven terminal values against the oracle's sample loop on the same normal stream
+    (strict math, then fast math), Euler–Maruyama and — where the reference defines it — Milstein."""
+    S = gpu
+    D, M, _ = O.dims(name)
+    m = gen(S, name)(*params)
+    nsteps, npaths, dt = 48, 130, 1.0 / 64
+    x0 = x[0] if D == 1 else x
+    schemes = [EM] + ([MIL] if M == 1 and name not in ("SpecialCaseModel2",) else [])
+    if name == "SpecialCaseModel2":
+        schemes = [EM, MIL]
+    for sid in schemes:
+        z = O.normals_paths(77, 5, 0, npaths, nsteps, M)
+        ref = O.sample_z(name, sid, params, t, dt, x, z)
+        sch = S.EulerMaruyama(dt) if sid == EM else S.Milstein(dt)
+        for mth in ("strict", "fast"):
+            got = S.sample(m, sch, t, x0, nsteps, npaths, seed=77, stream=5, math=mth).reshape(npaths, D)
+            scale = np.maximum(np.abs(ref), 1e-3)
+            assert np.max(np.abs(got - ref) / scale) <= 1e-10, (name, sid, mth)
+
+
+@pytest.mark.parametrize("name,params,x,t", [c for c in CASES if c[0] in
+                                             ("Heston", "BlackScholes", "TimeDependent", "CoxIngersollRoss",
+                                              "FitzHughNagumo", "Lorenz", "SpecialCaseModel3", "TestModel")])
+def test_generated_models_wiener_driven_strict_bitwise(gpu, O, name, params, x, t):
+    """simulate!(x, model, scheme, t0, x0, w) in strict math: bit-identical to the oracle for generated code."""
+    S = gpu
+    D, M, _ = O.dims(name)
+    m = gen(S, name)(*params)
+    nsteps, npaths, dt = 40, 70, 1.0 / 128
+    z = np.random.default_rng(5).standard_normal((npaths, nsteps, M))
+    w = O.wiener_z(dt, z)
+    for sid in [EM] + ([MIL] if M == 1 else []):
+        ref = O.simulate_wiener(name, sid, params, t, dt, x, w)
+        out = np.empty_like(ref)
+        xs = out[..., 0] if D == 1 else out
+        ws = np.ascontiguousarray(w[..., 0] if (M == 1 and D == 1) else w)
+        sch = S.EulerMaruyama(dt) if sid == EM else S.Milstein(dt)
+        S.simulate_(xs, m, sch, t, x[0] if D == 1 else x, ws, math="strict")
+        assert np.array_equal(out, ref), (name, sid)
+
+
+def test_generated_heston_equals_builtin(gpu):
+    """The hand-written Heston functor and the generated one agree: bit-identical in strict math, <= 1e-12 in
+    fast math (different but algebraically equal forms)."""
+    S = gpu
+    g, b = gen(S, "Heston")(*HESTON_P), S.Heston(*HESTON_P)
+    sch = S.EulerMaruyama(1 / 256)
+    a1 = S.sample(g, sch, 0.0, [100.0, 0.4], 256, 3000, seed=3, math="strict")
+    a2 = S.sample(b, sch, 0.0, [100.0, 0.4], 256, 3000, seed=3, math="strict")
+    assert np.array_equal(a1, a2)
+    f1 = S.sample(g, sch, 0.0, [100.0, 0.4], 256, 3000, seed=3)
+    f2 = S.sample(b, sch, 0.0, [100.0, 0.4], 256, 3000, seed=3)
+    assert rel_err(f1, f2) <= 1e-12 and rel_err(f1, a1) <= 1e-12
+
+
+def test_generated_model_full_paths_and_mlmc(gpu, O):
+    S = gpu
+    m = gen(S, "CoxIngersollRoss")(1.3, 0.04, 0.2)
+    sch = S.Milstein(1 / 64)
+    x, t = S.simulate(m, sch, 0.0, 0.05, 64, 500, seed=2)
+    xs, _ = S.simulate(m, sch, 0.0, 0.05, 64, 500, seed=2, layout="soa")
+    assert np.array_equal(x, xs.T) and np.all(x[:, 0] == 0.05)
+    assert np.array_equal(x[:, -1], S.sample(m, sch, 0.0, 0.05, 64, 500, seed=2))
+    # coupled levels for a generated scalar model
+    coarse, fine = S.EulerMaruyama(1 / 16), S.EulerMaruyama(1 / 64)
+    xc, xf = S.multilevel_sample_level(m, coarse, fine, 4, 0.0, 0.05, 16, 300, seed=9)
+    z = O.normals_paths(9, 0, 0, 300, 64, 1)
+    rc, rf = O.multilevel_sample_z("CoxIngersollRoss", EM, (1.3, 0.04, 0.2), 0.0, 1 / 16, 1 / 64, 4, [0.05], z)
+    assert rel_err(xc, rc[:, 0]) <= 1e-11 and rel_err(xf, rf[:, 0]) <= 1e-11
+
+
+def test_coupled_sampler_needs_matching_dimensions(gpu):
+    # Δw = zero(typeof(x0)) in multilevel.jl:79 only works when D == M
+    S = gpu
+    m = gen(S, "TestModel")(1, 2, 3, 4, 5, 6)
+    with pytest.raises(S.SDEB200Error) as ei:
+        S.multilevel_sample_level(m, S.EulerMaruyama(0.1), S.EulerMaruyama(0.05), 2, 0.0, [0.1, 0.2, 0.3], 4, 10)
+    assert ei.value.code == S._lib.E_UNSUPPORTED
