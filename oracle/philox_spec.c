@@ -35,12 +35,15 @@ static void pair_f64(uint64_t seed, uint32_t stream, uint64_t path, uint32_t P, 
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, r[4];
   oracle_philox4x32_10(ctr, key, r);
   uint64_t X1 = ((uint64_t)r[1] << 32) | r[0], X2 = ((uint64_t)r[3] << 32) | r[2];
-  if (X1 == 0) X1 = 1;
-  int lz = __builtin_clzll(X1);
-  uint64_t Y = X1 << lz;
-  uint64_t mant = (Y >> 11) & ((1ull << 52) - 1);
-  long double m = 1.0L + (long double)mant * 0x1.0p-52L; /* in [1,2) */
-  long double w = 2.0L * ((long double)(lz + 1) * 0.693147180559945309417232121458176568L - logl(m));
+  /* u1 = RN(X1) 2^-64 (round-to-nearest conversion, as cvt.rn.f64.u64); X1 == 0 reads as u1 = 2^-1087 */
+  long double w;
+  if (X1 == 0) {
+    w = 2.0L * 1087.0L * 0.693147180559945309417232121458176568L;
+  } else {
+    double d1 = (double)X1;
+    w = -2.0L * logl((long double)d1 * 0x1.0p-64L);
+  }
+  if (w < 0x1.0p-63L) w = 0x1.0p-63L; /* the device clamps the computed value at 2^-63 (u1 rounded to 1) */
   uint64_t n = (X2 + (1ull << 61)) >> 62;
   int64_t f = (int64_t)(X2 - (n << 62));
   double t = (double)f; /* round-to-nearest, as cvt.rn.f64.s64 */

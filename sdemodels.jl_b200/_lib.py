@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdeb200.so")
+LIB_PATH = os.environ.get("SDEB200_LIB") or os.path.join(_HERE, "libsdeb200.so")  # env override: tuning builds only
 
 OK, E_ARG, E_PARSE, E_NVRTC, E_CUDA, E_NCCL, E_DOMAIN, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
 EULER_MARUYAMA, MILSTEIN = 0, 1

@@ -510,7 +510,10 @@ extern "C" int sdeb200_model_coefficients(sdeb200_model *m, const double *params
 // ---------------------------------------------------------------------------------------------------
 // sample
 // ---------------------------------------------------------------------------------------------------
-static int64_t sample_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * 2); }
+#ifndef SDE_PPT
+#define SDE_PPT 2
+#endif
+static int64_t sample_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SDE_PPT); }
 
 extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
                               int64_t nsteps, int64_t npaths, void *out) {

@@ -24,6 +24,9 @@
 #define SDE_HD static inline
 #endif
 
+#ifndef SDE_PPT
+#define SDE_PPT 2 /* paths per thread in the terminal-value kernel (instruction-level parallelism) */
+#endif
 #ifndef SDE_STRICT
 #define SDE_STRICT 0 /* 1: reference evaluation order, translation unit compiled with -fmad=false */
 #endif
@@ -100,6 +103,21 @@ SDE_HD double rsqrt_seed(double a) {
 #endif
 }
 
+// sqrt by one Goldschmidt iteration + one correction on the MUFU.RSQ64H seed: 6 FP64-pipe instructions, no
+// slow-path branch.  <= 1 ulp for positive normal v; NaN for v < 0 (and for subnormal v, which the seed flushes).
+SDE_HD double sqrt_core(double v) {
+  const double y = rsqrt_seed(v);
+  double g = v * y;
+  double h = hilo2double(double2hi(y) - 0x00100000u, 0); /* y/2: the seed has a zero low word */
+  const double e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  const double d = fma(-g, g, v);
+  return fma(d, h, g);
+}
+SDE_HD double sqrt_fast(double v) { return v == 0.0 ? 0.0 : sqrt_core(v); }
+SDE_HD float sqrt_fast(float v) { return sqrtf(v); }
+
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  counter = (path_lo, path_hi, block, stream), key = seed.
 // The key schedule is loop-invariant per launch; ptxas keeps the ten bumped keys in uniform registers.
@@ -126,21 +144,22 @@ SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 
 // ---------------------------------------------------------------------------------------------------
 // "sdeb200 normal stream v1", FP64: 128 Philox bits -> two N(0, scale2) variates (Box–Muller).
-//   X1 = r1:r0  -> u1 = m 2^-(lz+1), m in [1,2) from the 52 bits below the leading one  (u1 in (0,1))
+//   X1 = r1:r0  -> u1 = RN(X1) 2^-64 = m 2^-k, m in [1,2)                              (u1 in (0,1])
 //   X2 = r3:r2  -> angle = X2 / 2^64 turns, reduced to |x| <= 1/8 turn + quadrant
-//   -2 ln u1 = 2 (lz+1) ln 2 + [ r Q(r) + 2 ln(1/c_j) ],  r = m/c_j - 1, |r| <= 2^-8   (128-entry table)
+//   -2 ln u1 = 2 k ln 2 + [ r Q(r) + 2 ln(1/c_j) ],  r = m/c_j - 1, |r| <= 2^-8          (128-entry table)
 //   radius by a Goldschmidt iteration on the MUFU.RSQ64H seed; sin/cos by even/odd polynomials.
 // 31 FP64-pipe instructions per pair; everything else (bit slicing, quadrant fix-up) is integer work that
 // issues beside the FP64 pipe.  tab: {1/c_j, 2 ln(1/c_j)} pairs, in shared memory on the device.
 // ---------------------------------------------------------------------------------------------------
 SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, double scale2, double &z0, double &z1) {
-  uint64_t X1 = ((uint64_t)r[1] << 32) | r[0];
-  if (X1 == 0) X1 = 1;
-  const int lz = clz64(X1);
-  const uint64_t Y = X1 << lz;
-  const uint32_t yh = (uint32_t)(Y >> 32), yl = (uint32_t)Y;
-  const double m = hilo2double(0x3FF00000u | ((yh << 1) >> 12), (yh << 21) | (yl >> 11));
-  const int j = (int)((yh >> 24) & 0x7Fu);
+  // u1 = RN(X1) 2^-64 (one I2F.F64.U64): exponent field -> k = -floor(log2 u1), mantissa -> m in [1,2).
+  // X1 == 0 (probability 2^-64) reads as u1 = 2^-1087: finite, no special case.
+  const uint64_t X1 = ((uint64_t)r[1] << 32) | r[0];
+  const double d1 = (double)X1;
+  const uint32_t h1 = double2hi(d1);
+  const double m = hilo2double((h1 & 0x000FFFFFu) | 0x3FF00000u, double2lo(d1));
+  const int j = (int)((h1 >> 13) & 0x7Fu);
+  const double kd = (double)(int)(1087u - (h1 >> 20));
   const double inv_c = tab[2 * j], tl = tab[2 * j + 1];
   const double rr = fma(m, inv_c, -1.0);
   double q = SDE_K(SDE_LOG_C4);
@@ -149,23 +168,15 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, double sc
   q = fma(q, rr, SDE_K(SDE_LOG_C1));
   q = fma(q, rr, -2.0);
   double w = fma(rr, q, tl);
-  w = fma((double)(lz + 1), SDE_K(SDE_TWO_LN2), w);
+  w = fma(kd, SDE_K(SDE_TWO_LN2), w);
   // true value >= 2^-52; rounding can push the computed one to <= 0 once in ~2^52 draws: clamp via the high word
   if ((int32_t)double2hi(w) < 0x3C000000) w = 0x1.0p-63;
   w *= scale2;
-  // radius = sqrt(w)
-  const double y = rsqrt_seed(w);
-  double g = w * y;
-  double h = hilo2double(double2hi(y) - 0x00100000u, 0); /* y/2: y has a zero low word */
-  const double e = fma(-g, h, 0.5);
-  g = fma(g, e, g);
-  h = fma(h, e, h);
-  const double d = fma(-g, g, w);
-  g = fma(d, h, g);
-  // angle
-  const uint64_t X2 = ((uint64_t)r[3] << 32) | r[2];
-  const uint32_t n = (uint32_t)((X2 + (1ull << 61)) >> 62);
-  const int64_t f = (int64_t)(X2 - ((uint64_t)n << 62));
+  const double g = sqrt_core(w);  // radius
+  // angle = X2 / 2^64 turns = n/4 + x: the low 62 bits, sign-extended, are the offset from the NEAREST quarter turn
+  const int32_t fh = ((int32_t)(r[3] << 2)) >> 2;
+  const uint32_t n = (r[3] + 0x20000000u) >> 30;
+  const int64_t f = (int64_t)(((uint64_t)(uint32_t)fh << 32) | r[2]);
   const double x = (double)f * 0x1.0p-64;
   const double u = x * x;
   double sp = SDE_K(SDE_SIN_C6);
@@ -766,7 +777,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
 // reference defines Milstein for M == 1 models only (milstein.jl:4): instantiate SCH = 1 only there.
 #define SDE_KERNELS(MODEL, TAG, SCH, SNAME, T, PNAME)                                                            \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_##SNAME##_##PNAME(                \
-      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 2>(a); }                       \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT>(a); }                       \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_mlmc_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, T, SCH>(a); }                            \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_##SNAME##_##PNAME(                \

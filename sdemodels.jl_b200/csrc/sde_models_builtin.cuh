@@ -73,14 +73,15 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
     (void)t;
     static_assert(SCHEME == 0, "the reference defines Milstein for M == 1 models only (milstein.jl:4)");
     const T S = x[0], V = x[1];
-    const T sv = sde_sqrt(V);
 #if SDE_STRICT
+    const T sv = sde_sqrt(V);
     const T mu1 = c[0] * S, mu2 = c[1] * (c[2] - V);
     const T s11 = sv * S, s21 = (c[3] * sv) * c[4], s22 = (c[3] * sv) * c[5];
     x[0] = (S + mu1 * dt) + s11 * dw[0];                  // + 0.0*dw[1] is exact for finite increments
     x[1] = (V + mu2 * dt) + (s21 * dw[0] + s22 * dw[1]);
 #else
     (void)dt;
+    const T sv = sqrt_fast(V);  // <= 1 ulp, branch-free; sqrt(0) = 0, sqrt(V < 0) = NaN like the reference's DomainError
     x[0] = sde_fma(S, sde_fma(sv, dw[0], c[0]), S);
     const T n = sde_fma(c[4], dw[1], c[3] * dw[0]);
     x[1] = sde_fma(sv, n, sde_fma(V, c[1], c[2]));

@@ -136,17 +136,18 @@ def test_generated_heston_equals_builtin(gpu):
 
 def test_generated_model_full_paths_and_mlmc(gpu, O):
     S = gpu
-    m = gen(S, "CoxIngersollRoss")(1.3, 0.04, 0.2)
+    cir = (1.3, 0.09, 0.1)  # far from the r = 0 boundary: no sqrt of a negative rate on either level
+    m = gen(S, "CoxIngersollRoss")(*cir)
     sch = S.Milstein(1 / 64)
-    x, t = S.simulate(m, sch, 0.0, 0.05, 64, 500, seed=2)
-    xs, _ = S.simulate(m, sch, 0.0, 0.05, 64, 500, seed=2, layout="soa")
-    assert np.array_equal(x, xs.T) and np.all(x[:, 0] == 0.05)
-    assert np.array_equal(x[:, -1], S.sample(m, sch, 0.0, 0.05, 64, 500, seed=2))
+    x, t = S.simulate(m, sch, 0.0, 0.09, 64, 500, seed=2)
+    xs, _ = S.simulate(m, sch, 0.0, 0.09, 64, 500, seed=2, layout="soa")
+    assert np.array_equal(x, xs.T) and np.all(x[:, 0] == 0.09)
+    assert np.array_equal(x[:, -1], S.sample(m, sch, 0.0, 0.09, 64, 500, seed=2))
     # coupled levels for a generated scalar model
     coarse, fine = S.EulerMaruyama(1 / 16), S.EulerMaruyama(1 / 64)
-    xc, xf = S.multilevel_sample_level(m, coarse, fine, 4, 0.0, 0.05, 16, 300, seed=9)
+    xc, xf = S.multilevel_sample_level(m, coarse, fine, 4, 0.0, 0.09, 16, 300, seed=9)
     z = O.normals_paths(9, 0, 0, 300, 64, 1)
-    rc, rf = O.multilevel_sample_z("CoxIngersollRoss", EM, (1.3, 0.04, 0.2), 0.0, 1 / 16, 1 / 64, 4, [0.05], z)
+    rc, rf = O.multilevel_sample_z("CoxIngersollRoss", EM, cir, 0.0, 1 / 16, 1 / 64, 4, [0.09], z)
     assert rel_err(xc, rc[:, 0]) <= 1e-11 and rel_err(xf, rf[:, 0]) <= 1e-11
 
 
