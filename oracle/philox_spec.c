@@ -43,7 +43,7 @@ static void pair_f64(uint64_t seed, uint32_t stream, uint64_t path, uint32_t P, 
     double d1 = (double)X1;
     w = -2.0L * logl((long double)d1 * 0x1.0p-64L);
   }
-  if (w < 0x1.0p-63L) w = 0x1.0p-63L; /* the device clamps the computed value at 2^-63 (u1 rounded to 1) */
+  w += 0x1.0p-50L; /* spec: keeps w > 0 when u1 rounds to 1; the device folds it into its log table */
   uint64_t n = (X2 + (1ull << 61)) >> 62;
   int64_t f = (int64_t)(X2 - (n << 62));
   double t = (double)f; /* round-to-nearest, as cvt.rn.f64.s64 */

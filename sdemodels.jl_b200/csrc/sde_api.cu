@@ -18,6 +18,7 @@
 #include "sde_args.h"
 #include "sde_dsl.h"
 #include "sde_ktable.h"
+#include "sde_coeffs.inc"
 
 extern "C" int sde_aot_table_fast(int model, sde_ktable *t);
 extern "C" int sde_aot_table_strict(int model, sde_ktable *t);
@@ -378,6 +379,17 @@ static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const dou
   return 0;
 }
 
+// a->dt and the dt-scaled constants of the FP64 normal transform (sde_device.cuh: make_log_consts)
+static void set_dt(sde_args *a, double dt) {
+  a->dt = dt;
+  a->lk[0] = SDE_LOG_C1_V * dt;
+  a->lk[1] = SDE_LOG_C2_V * dt;
+  a->lk[2] = SDE_LOG_C3_V * dt;
+  a->lk[3] = SDE_LOG_C4_V * dt;
+  a->lk[4] = -2.0 * dt;
+  a->lk[5] = SDE_TWO_LN2_V * dt;
+}
+
 static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o, const double *params,
                       const double *x0) {
   memset(a, 0, sizeof *a);
@@ -389,6 +401,7 @@ static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o
   a->seed_hi = (uint32_t)(o->seed >> 32);
   a->stream = o->stream;
   a->path0 = o->path_offset;
+  set_dt(a, o->dt);
 }
 
 static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t st) {
@@ -694,7 +707,7 @@ static int wiener_device(const sdeb200_opts *o, int dim, int64_t nrows, int64_t 
   sde_args a;
   memset(&a, 0, sizeof a);
   a.t0 = o->t0;
-  a.dt = o->dt;
+  set_dt(&a, o->dt);
   a.seed_lo = (uint32_t)o->seed;
   a.seed_hi = (uint32_t)(o->seed >> 32);
   a.stream = o->stream;
@@ -913,7 +926,7 @@ static int mlmc_args(sde_args *a, sdeb200_model *m, const sdeb200_opts *o, const
                 "the coupled level sampler needs D == M (Δw = zero(typeof(x0)) in src/multilevel.jl:79); "
                 "'%s' has D=%d, M=%d", m->name.c_str(), m->D, m->M);
   fill_args(a, m, o, params, x0);
-  a->dt = dt_fine;
+  set_dt(a, dt_fine);
   a->dt_coarse = o->dt;
   a->substeps = substeps;
   a->nsteps = ncoarse * substeps;

@@ -41,6 +41,7 @@ typedef struct {
   uint32_t seed_lo, seed_hi, stream;
   int32_t payoff_kind, payoff_comp;
   double payoff_k, payoff_disc;
+  double lk[6];      /* dt-scaled constants of the FP64 normal transform (make_log_consts) */
   /* mlmc only */
   double dt_coarse;
   int64_t substeps;

@@ -27,6 +27,9 @@
 #ifndef SDE_PPT
 #define SDE_PPT 2 /* paths per thread in the terminal-value kernel (instruction-level parallelism) */
 #endif
+#ifndef SDE_PHILOX_ROUNDS
+#define SDE_PHILOX_ROUNDS 10 /* Philox4x32-10, the Random123 / cuRAND default; other values are tuning experiments only */
+#endif
 #ifndef SDE_STRICT
 #define SDE_STRICT 0 /* 1: reference evaluation order, translation unit compiled with -fmad=false */
 #endif
@@ -104,9 +107,8 @@ SDE_HD double rsqrt_seed(double a) {
 }
 
 // sqrt by one Goldschmidt iteration + one correction on the MUFU.RSQ64H seed: 6 FP64-pipe instructions, no
-// slow-path branch.  <= 1 ulp for positive normal v; NaN for v < 0 (and for subnormal v, which the seed flushes).
-SDE_HD double sqrt_core(double v) {
-  const double y = rsqrt_seed(v);
+// slow-path branch.  <= 1 ulp for positive normal v.
+SDE_HD double sqrt_from_seed(double v, double y) {
   double g = v * y;
   double h = hilo2double(double2hi(y) - 0x00100000u, 0); /* y/2: the seed has a zero low word */
   const double e = fma(-g, h, 0.5);
@@ -115,7 +117,15 @@ SDE_HD double sqrt_core(double v) {
   const double d = fma(-g, g, v);
   return fma(d, h, g);
 }
-SDE_HD double sqrt_fast(double v) { return v == 0.0 ? 0.0 : sqrt_core(v); }
+SDE_HD double sqrt_core(double v) { return sqrt_from_seed(v, rsqrt_seed(v)); }  // v > 0
+// Model-side sqrt of the FAST math mode: sqrt(0) = 0 (the +inf seed is clamped to 2^1023 with one integer min, so
+// g = 0 * 2^1023 = 0 exactly); v < 0 gives a non-finite result (NaN or -inf) that propagates to the state and is
+// counted as a non-finite path — the reference throws DomainError there.  Subnormal v is flushed.
+SDE_HD double sqrt_fast(double v) {
+  const double y = rsqrt_seed(v);
+  const int32_t hy = (int32_t)double2hi(y);
+  return sqrt_from_seed(v, hilo2double((uint32_t)(hy < 0x7FE00000 ? hy : 0x7FE00000), 0));
+}
 SDE_HD float sqrt_fast(float v) { return sqrtf(v); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -127,7 +137,7 @@ SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int i = 0; i < 10; i++) {
+  for (int i = 0; i < SDE_PHILOX_ROUNDS; i++) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -143,17 +153,27 @@ SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 }
 
 // ---------------------------------------------------------------------------------------------------
-// "sdeb200 normal stream v1", FP64: 128 Philox bits -> two N(0, scale2) variates (Box–Muller).
-//   X1 = r1:r0  -> u1 = RN(X1) 2^-64 = m 2^-k, m in [1,2)                              (u1 in (0,1])
-//   X2 = r3:r2  -> angle = X2 / 2^64 turns, reduced to |x| <= 1/8 turn + quadrant
-//   -2 ln u1 = 2 k ln 2 + [ r Q(r) + 2 ln(1/c_j) ],  r = m/c_j - 1, |r| <= 2^-8          (128-entry table)
-//   radius by a Goldschmidt iteration on the MUFU.RSQ64H seed; sin/cos by even/odd polynomials.
-// 31 FP64-pipe instructions per pair; everything else (bit slicing, quadrant fix-up) is integer work that
-// issues beside the FP64 pipe.  tab: {1/c_j, 2 ln(1/c_j)} pairs, in shared memory on the device.
+// "sdeb200 normal stream v1", FP64: 128 Philox bits -> two N(0, dt) variates (Box–Muller).
+//   X1 = r1:r0  -> u1 = RN(X1) 2^-64 = m 2^-k, m in [1,2)     (one I2F.F64.U64; X1 == 0 reads as u1 = 2^-1087)
+//   X2 = r3:r2  -> angle = X2 / 2^64 turns = n/4 + x, |x| <= 1/8 (nearest quarter turn by sign extension)
+//   w = dt (-2 ln u1 + 2^-50) = k (2 ln2 dt) + r Q_dt(r) + T_j,   r = m/c_j - 1, |r| <= 2^-8   (128-entry table)
+//       the 2^-50 keeps the computed w > 0 when u1 rounds to 1 (no clamp); dt is folded into the constants
+//   radius sqrt(w): Goldschmidt on the MUFU.RSQ64H seed; sin/cos(2 pi x): polynomials in t^2, t = 2^64 x the
+//       integer angle offset itself (power-of-two scaled coefficients, exact) — x is never formed.
+// 29 FP64-pipe instructions per pair; bit slicing and the quadrant fix-up are integer work.
+//   lk[6]  = dt * {Q1, Q2, Q3, Q4, -2, 2 ln 2}   (make_log_consts; kernel-parameter space on the device)
+//   tab    = {1/c_j, dt (2 ln(1/c_j) + 2^-50)} pairs (shared memory on the device, load_log_table)
 // ---------------------------------------------------------------------------------------------------
-SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, double scale2, double &z0, double &z1) {
-  // u1 = RN(X1) 2^-64 (one I2F.F64.U64): exponent field -> k = -floor(log2 u1), mantissa -> m in [1,2).
-  // X1 == 0 (probability 2^-64) reads as u1 = 2^-1087: finite, no special case.
+SDE_HD void make_log_consts(double dt, double *lk) {
+  lk[0] = SDE_LOG_C1_V * dt;
+  lk[1] = SDE_LOG_C2_V * dt;
+  lk[2] = SDE_LOG_C3_V * dt;
+  lk[3] = SDE_LOG_C4_V * dt;
+  lk[4] = -2.0 * dt;
+  lk[5] = SDE_TWO_LN2_V * dt;
+}
+
+SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const double *lk, double &z0, double &z1) {
   const uint64_t X1 = ((uint64_t)r[1] << 32) | r[0];
   const double d1 = (double)X1;
   const uint32_t h1 = double2hi(d1);
@@ -162,23 +182,20 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, double sc
   const double kd = (double)(int)(1087u - (h1 >> 20));
   const double inv_c = tab[2 * j], tl = tab[2 * j + 1];
   const double rr = fma(m, inv_c, -1.0);
-  double q = SDE_K(SDE_LOG_C4);
-  q = fma(q, rr, SDE_K(SDE_LOG_C3));
-  q = fma(q, rr, SDE_K(SDE_LOG_C2));
-  q = fma(q, rr, SDE_K(SDE_LOG_C1));
-  q = fma(q, rr, -2.0);
+  double q = lk[3];
+  q = fma(q, rr, lk[2]);
+  q = fma(q, rr, lk[1]);
+  q = fma(q, rr, lk[0]);
+  q = fma(q, rr, lk[4]);
   double w = fma(rr, q, tl);
-  w = fma(kd, SDE_K(SDE_TWO_LN2), w);
-  // true value >= 2^-52; rounding can push the computed one to <= 0 once in ~2^52 draws: clamp via the high word
-  if ((int32_t)double2hi(w) < 0x3C000000) w = 0x1.0p-63;
-  w *= scale2;
-  const double g = sqrt_core(w);  // radius
-  // angle = X2 / 2^64 turns = n/4 + x: the low 62 bits, sign-extended, are the offset from the NEAREST quarter turn
+  w = fma(kd, lk[5], w);
+  const double g = sqrt_core(w);  // radius, already scaled by sqrt(dt)
+  // angle: the low 62 bits of X2, sign-extended, are the offset t (in 2^-64 turns) from the NEAREST quarter turn n
   const int32_t fh = ((int32_t)(r[3] << 2)) >> 2;
   const uint32_t n = (r[3] + 0x20000000u) >> 30;
   const int64_t f = (int64_t)(((uint64_t)(uint32_t)fh << 32) | r[2]);
-  const double x = (double)f * 0x1.0p-64;
-  const double u = x * x;
+  const double t = (double)f;
+  const double u = t * t;
   double sp = SDE_K(SDE_SIN_C6);
   sp = fma(sp, u, SDE_K(SDE_SIN_C5));
   sp = fma(sp, u, SDE_K(SDE_SIN_C4));
@@ -186,9 +203,8 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, double sc
   sp = fma(sp, u, SDE_K(SDE_SIN_C2));
   sp = fma(sp, u, SDE_K(SDE_SIN_C1));
   sp = fma(sp, u, SDE_K(SDE_SIN_C0));
-  const double s = x * sp;
-  double c = SDE_K(SDE_COS_C7);
-  c = fma(c, u, SDE_K(SDE_COS_C6));
+  const double s = t * sp;
+  double c = SDE_K(SDE_COS_C6);
   c = fma(c, u, SDE_K(SDE_COS_C5));
   c = fma(c, u, SDE_K(SDE_COS_C4));
   c = fma(c, u, SDE_K(SDE_COS_C3));
@@ -253,11 +269,12 @@ template <typename T> struct NPC;
 template <> struct NPC<double> { static constexpr int value = 2; };
 template <> struct NPC<float> { static constexpr int value = 4; };
 
-SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, double scale2, double *z) {
-  normal_pair_f64(r, tab, scale2, z[0], z[1]);
+SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, const double *lk, double scale2, double *z) {
+  (void)scale2;
+  normal_pair_f64(r, tab, lk, z[0], z[1]);
 }
-SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, float scale2, float *z) {
-  (void)tab;
+SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, const double *lk, float scale2, float *z) {
+  (void)tab; (void)lk;
   normal_pair_f32(r[0], r[1], scale2, z[0], z[1]);
   normal_pair_f32(r[2], r[3], scale2, z[2], z[3]);
 }
@@ -270,6 +287,9 @@ constexpr int sde_gcd(int a, int b) { return b == 0 ? a : sde_gcd(b, a % b); }
 #if !defined(__CUDACC__)
 // host twin of the log table, for the CPU unit tests of the transform (tests/host_math_harness.cpp)
 static const double h_log_tab[256] = SDE_LOG_TAB_INIT;
+static inline void h_scaled_log_table(double dt, double *tab) {
+  for (int i = 0; i < 128; i++) { tab[2 * i] = h_log_tab[2 * i]; tab[2 * i + 1] = h_log_tab[2 * i + 1] * dt; }
+}
 #endif
 
 #if defined(__CUDACC__)
@@ -278,8 +298,8 @@ static const double h_log_tab[256] = SDE_LOG_TAB_INIT;
 // ===================================================================================================
 static __device__ const double g_log_tab[256] = SDE_LOG_TAB_INIT;
 
-SDE_D void load_log_table(double *s_tab) {
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = g_log_tab[i];
+SDE_D void load_log_table(double *s_tab, double dt) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = (i & 1) ? g_log_tab[i] * dt : g_log_tab[i];
   __syncthreads();
 }
 
@@ -299,7 +319,7 @@ template <typename T, int M> struct Batch {
 
 template <typename T, int M>
 SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, uint32_t k0, uint32_t k1, const double *s_tab,
-                     T scale2, T *dw) {
+                     const double *lk, T scale2, T *dw) {
   typedef Batch<T, M> B;
   if (M == 0) {
     dw[0] = (T)0;
@@ -309,7 +329,7 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, uint32_t k0,
   for (int b = 0; b < B::NB; b++) {
     uint32_t r[4];
     philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, k0, k1, r);
-    normals_from_block(r, s_tab, scale2, dw + b * B::NPB);
+    normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB);
   }
 }
 
@@ -367,7 +387,7 @@ SDE_D void sample_body(const sde_args &a) {
   typedef Batch<T, M> B;
   __shared__ double s_tab[256];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
-  load_log_table(s_tab);
+  load_log_table(s_tab, a.dt);
 
   Consts<T> cst;
   T prm[SDE_MAXP];
@@ -394,7 +414,7 @@ SDE_D void sample_body(const sde_args &a) {
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
       gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, a.seed_lo,
-                      a.seed_hi, s_tab, dt, dw);
+                      a.seed_hi, s_tab, a.lk, dt, dw);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         const T t = t0 + (T)(it * B::U + u) * dt;
@@ -407,7 +427,7 @@ SDE_D void sample_body(const sde_args &a) {
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
       gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, a.seed_lo,
-                      a.seed_hi, s_tab, dt, dw);
+                      a.seed_hi, s_tab, a.lk, dt, dw);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         if (u < rem) {
@@ -476,7 +496,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   typedef Batch<T, M> B;
   __shared__ double s_tab[256];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
-  load_log_table(s_tab);
+  load_log_table(s_tab, a.dt);
 
   Consts<T> cf, cc;
   T prm[SDE_MAXP];
@@ -501,7 +521,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   int64_t ncoarse = 0;  // coarse steps completed
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[B::NZ];
-    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, dtf, dw);
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, a.lk, dtf, dw);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t fstep = it * B::U + u;
@@ -583,7 +603,7 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M, VEC = 16 / (int)sizeof(T);
   typedef Batch<T, M> B;
   __shared__ double s_tab[256];
-  load_log_table(s_tab);
+  load_log_table(s_tab, a.dt);
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
@@ -627,7 +647,7 @@ SDE_D void simulate_soa_body(const sde_args &a) {
     T dw[VEC][B::NZ];
 #pragma unroll
     for (int v = 0; v < VEC; v++)
-      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, dt, dw[v]);
+      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, a.lk, dt, dw[v]);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;
@@ -655,7 +675,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   typedef Batch<T, M> B;
   __shared__ double s_tab[256];
   __shared__ T s_tile[SDE_BLOCK / 32][32 * LDS];
-  load_log_table(s_tab);
+  load_log_table(s_tab, a.dt);
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
@@ -698,7 +718,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[B::NZ];
-    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, dt, dw);
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, a.lk, dt, dw);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;

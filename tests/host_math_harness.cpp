@@ -15,8 +15,10 @@ extern "C" void h_normals_f64(uint64_t seed, uint32_t stream, uint64_t path, uin
     uint32_t r[4];
     philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(q >> 1), stream, (uint32_t)seed,
                   (uint32_t)(seed >> 32), r);
-    double z[2];
-    normal_pair_f64(r, h_log_tab, scale2, z[0], z[1]);
+    double z[2], tab[256], lk[6];
+    h_scaled_log_table(scale2, tab);
+    make_log_consts(scale2, lk);
+    normal_pair_f64(r, tab, lk, z[0], z[1]);
     out[i] = z[q & 1];
   }
 }
@@ -28,12 +30,15 @@ extern "C" void h_normals_f32(uint64_t seed, uint32_t stream, uint64_t path, uin
     philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(q >> 2), stream, (uint32_t)seed,
                   (uint32_t)(seed >> 32), r);
     float z[4];
-    normals_from_block(r, nullptr, scale2, z);
+    normals_from_block(r, nullptr, nullptr, scale2, z);
     out[i] = z[q & 3];
   }
 }
 // raw transform on chosen bits (edge cases: tails, u1 -> 1, quadrant boundaries)
 extern "C" void h_pair_from_bits(const uint32_t *r4, double scale2, double *z) {
   uint32_t r[4] = {r4[0], r4[1], r4[2], r4[3]};
-  normal_pair_f64(r, h_log_tab, scale2, z[0], z[1]);
+  double tab[256], lk[6];
+  h_scaled_log_table(scale2, tab);
+  make_log_consts(scale2, lk);
+  normal_pair_f64(r, tab, lk, z[0], z[1]);
 }

@@ -283,6 +283,17 @@ def test_negative_variance_raises_domain_error(gpu):
         gpu.sample(m, gpu.EulerMaruyama(0.25), 0.0, [100.0, 0.05], 8, 4096, seed=0)
 
 
+def test_zero_variance_start_is_not_an_error(gpu, O):
+    """sqrt(0) = 0 in the reference; the branch-free fast sqrt must agree (V0 = 0, then V > 0)."""
+    params, x0, nsteps = HESTON_P, [100.0, 0.0], 32
+    dt = 1.0 / nsteps
+    z = O.normals_paths(4, 0, 0, 64, nsteps, 2)
+    ref = O.sample_z("Heston", EM, params, 0.0, dt, x0, z)
+    for mth in ("fast", "strict"):
+        got = gpu.sample(gpu.Heston(*params), gpu.EulerMaruyama(dt), 0.0, x0, nsteps, 64, seed=4, math=mth)
+        assert np.all(np.isfinite(got)) and rel_err(got, ref) <= 1e-11
+
+
 def test_mlmc_estimator_call_price(gpu):
     """C4 (reduced): Heston call, levels 0..5; the telescoping sum matches the finest-level plain estimate
     within 3 SE and the semi-analytic price 22.3375 within bias + 3 SE."""
