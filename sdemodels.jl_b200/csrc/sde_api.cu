@@ -404,6 +404,9 @@ static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o
   set_dt(a, o->dt);
 }
 
+// sample / mlmc kernels walk over chunks grid-stride: cap the grid so each CTA stages its tables once for many chunks
+static int64_t capped(int64_t nchunks) { return std::min<int64_t>(nchunks, 148 * 64); }
+
 static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t st) {
   if (!k) return fail(SDEB200_E_UNSUPPORTED, "kernel not available for this model / scheme");
   if (grid <= 0) return 0;
@@ -551,14 +554,14 @@ extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const dou
   if (is_device_ptr(out)) {
     a.npaths = npaths;
     a.out = out;
-    if ((rc = launch(k, sample_grid(npaths), &a, st))) return rc;
+    if ((rc = launch(k, capped(sample_grid(npaths)), &a, st))) return rc;
   } else {
     rc = run_slabs(npaths, bpp, out, [&](int64_t s0, int64_t n, void *dev, cudaStream_t s) {
       sde_args b = a;
       b.npaths = n;
       b.path0 = o->path_offset + s0;
       b.out = dev;
-      return launch(k, sample_grid(n), &b, s);
+      return launch(k, capped(sample_grid(n)), &b, s);
     });
     if (rc) return rc;
   }
@@ -902,7 +905,7 @@ extern "C" int sdeb200_estimate(sdeb200_model *m, const sdeb200_opts *o, const d
     a.payoff_comp = payoff->comp;
     a.payoff_k = payoff->strike;
     a.payoff_disc = payoff->discount;
-    if ((rc = launch(kt->sample[o->scheme][o->precision], grid, &a, st))) return rc;
+    if ((rc = launch(kt->sample[o->scheme][o->precision], capped(grid), &a, st))) return rc;
     sde_launch_accumulate((const double *)g.partials[0].p, grid, 2 * SDE_MAXF, nq, r.bins, r.ovf, st);
     g.launches++;
   }
@@ -961,7 +964,7 @@ extern "C" int sdeb200_mlmc_sample_level(sdeb200_model *m, const sdeb200_opts *o
     else { if ((rc = g.slab[1].ensure(bytes))) return rc; a.out2 = g.slab[1].p; }
   }
   if ((rc = timed_begin())) return rc;
-  if ((rc = launch(kt->mlmc[o->scheme][o->precision], cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+  if ((rc = launch(kt->mlmc[o->scheme][o->precision], capped(cdiv(npaths, SDE_BLOCK)), &a, st))) return rc;
   if (xf && !fdev) CU(cudaMemcpyAsync(xf, a.out, bytes, cudaMemcpyDeviceToHost, st));
   if (xc && !cdev) CU(cudaMemcpyAsync(xc, a.out2, bytes, cudaMemcpyDeviceToHost, st));
   if ((rc = timed_end())) return rc;
@@ -1058,7 +1061,7 @@ static int queue_level(sdeb200_model *m, const sde_ktable *kt, const sdeb200_opt
   a.payoff_comp = payoff->comp;
   a.payoff_k = payoff->strike;
   a.payoff_disc = payoff->discount;
-  if ((rc = launch(k, grid, &a, st))) return rc;
+  if ((rc = launch(k, capped(grid), &a, st))) return rc;
   sde_launch_accumulate((const double *)g.partials[slot].p, grid, 2 * SDE_MAXF, coupled ? 6 : 2, r.bins, r.ovf, st);
   g.launches++;
   return 0;

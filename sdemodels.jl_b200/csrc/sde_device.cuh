@@ -158,11 +158,12 @@ SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 //   X2 = r3:r2  -> angle = X2 / 2^64 turns = n/4 + x, |x| <= 1/8 (nearest quarter turn by sign extension)
 //   w = dt (-2 ln u1 + 2^-50) = k (2 ln2 dt) + r Q_dt(r) + T_j,   r = m/c_j - 1, |r| <= 2^-8   (128-entry table)
 //       the 2^-50 keeps the computed w > 0 when u1 rounds to 1 (no clamp); dt is folded into the constants
-//   radius sqrt(w): Goldschmidt on the MUFU.RSQ64H seed; sin/cos(2 pi x): polynomials in t^2, t = 2^64 x the
-//       integer angle offset itself (power-of-two scaled coefficients, exact) — x is never formed.
-// 29 FP64-pipe instructions per pair; bit slicing and the quadrant fix-up are integer work.
+//   radius sqrt(w): Goldschmidt on the MUFU.RSQ64H seed; (cos, sin)(2 pi X2 / 2^64): 1024-entry table of cell
+//       centres + a two-term residual rotation in t^2, t the integer offset itself (scaled coefficients, exact).
+// 25 FP64-pipe instructions per pair; the rest is a handful of integer bit-slicing instructions.
 //   lk[6]  = dt * {Q1, Q2, Q3, Q4, -2, 2 ln 2}   (make_log_consts; kernel-parameter space on the device)
-//   tab    = {1/c_j, dt (2 ln(1/c_j) + 2^-50)} pairs (shared memory on the device, load_log_table)
+//   tab    = [0,256): {1/c_j, dt (2 ln(1/c_j) + 2^-50)} pairs; [256, 2304): {cos, sin} of the 1024 cell centres
+//            (shared memory on the device, load_tables)
 // ---------------------------------------------------------------------------------------------------
 SDE_HD void make_log_consts(double dt, double *lk) {
   lk[0] = SDE_LOG_C1_V * dt;
@@ -190,33 +191,21 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const dou
   double w = fma(rr, q, tl);
   w = fma(kd, lk[5], w);
   const double g = sqrt_core(w);  // radius, already scaled by sqrt(dt)
-  // angle: the low 62 bits of X2, sign-extended, are the offset t (in 2^-64 turns) from the NEAREST quarter turn n
-  const int32_t fh = ((int32_t)(r[3] << 2)) >> 2;
-  const uint32_t n = (r[3] + 0x20000000u) >> 30;
-  const int64_t f = (int64_t)(((uint64_t)(uint32_t)fh << 32) | r[2]);
+  // angle = X2 / 2^64 turns = (i + 1/2 + d) / 1024: the top 10 bits pick {cos, sin} of the cell centre from a
+  // 1024-entry table, the low 54 bits (re-centred) are the offset t = 2^54 d, |t| <= 2^53 (exact in a double);
+  // the residual rotation |phi| <= pi/1024 needs two-term polynomials; no quadrant logic.
+  const double *rot = tab + 256 + 2 * (r[3] >> 22);
+  const double C = rot[0], S = rot[1];
+  const int64_t f = (int64_t)(((uint64_t)((r[3] & 0x003FFFFFu) - 0x00200000u) << 32) | r[2]);
   const double t = (double)f;
   const double u = t * t;
-  double sp = SDE_K(SDE_SIN_C6);
-  sp = fma(sp, u, SDE_K(SDE_SIN_C5));
-  sp = fma(sp, u, SDE_K(SDE_SIN_C4));
-  sp = fma(sp, u, SDE_K(SDE_SIN_C3));
-  sp = fma(sp, u, SDE_K(SDE_SIN_C2));
-  sp = fma(sp, u, SDE_K(SDE_SIN_C1));
-  sp = fma(sp, u, SDE_K(SDE_SIN_C0));
-  const double s = t * sp;
-  double c = SDE_K(SDE_COS_C6);
-  c = fma(c, u, SDE_K(SDE_COS_C5));
-  c = fma(c, u, SDE_K(SDE_COS_C4));
-  c = fma(c, u, SDE_K(SDE_COS_C3));
-  c = fma(c, u, SDE_K(SDE_COS_C2));
-  c = fma(c, u, SDE_K(SDE_COS_C1));
-  c = fma(c, u, 1.0);
-  // quadrant n: 0 -> (c, s)   1 -> (-s, c)   2 -> (-c, -s)   3 -> (s, -c)
-  const bool swap = (n & 1u) != 0;
-  const double a = swap ? s : c, b = swap ? c : s;
-  const uint32_t fa = ((n + 1u) & 2u) << 30, fb = (n & 2u) << 30;
-  const double ca = hilo2double(double2hi(a) ^ fa, double2lo(a));
-  const double sb = hilo2double(double2hi(b) ^ fb, double2lo(b));
+  double sp = fma(SDE_K(SDE_ROT_S2), u, SDE_K(SDE_ROT_S1));
+  sp = fma(sp, u, SDE_K(SDE_ROT_S0));
+  const double sn = t * sp;                       // sin(phi)
+  double cm = fma(SDE_K(SDE_ROT_C2), u, SDE_K(SDE_ROT_C1));
+  cm = cm * u;                                    // cos(phi) - 1
+  const double ca = fma(C, cm, fma(-S, sn, C));   // cos(theta_i + phi) = C + C (cos phi - 1) - S sin phi
+  const double sb = fma(S, cm, fma(C, sn, S));    // sin(theta_i + phi) = S + S (cos phi - 1) + C sin phi
   z0 = g * ca;
   z1 = g * sb;
 }
@@ -287,8 +276,10 @@ constexpr int sde_gcd(int a, int b) { return b == 0 ? a : sde_gcd(b, a % b); }
 #if !defined(__CUDACC__)
 // host twin of the log table, for the CPU unit tests of the transform (tests/host_math_harness.cpp)
 static const double h_log_tab[256] = SDE_LOG_TAB_INIT;
-static inline void h_scaled_log_table(double dt, double *tab) {
+static const double h_rot_tab[2048] = SDE_ROT_TAB_INIT;
+static inline void h_scaled_tables(double dt, double *tab) {  // tab[SDE_TAB_DOUBLES]
   for (int i = 0; i < 128; i++) { tab[2 * i] = h_log_tab[2 * i]; tab[2 * i + 1] = h_log_tab[2 * i + 1] * dt; }
+  for (int i = 0; i < 2048; i++) tab[256 + i] = h_rot_tab[i];
 }
 #endif
 
@@ -297,11 +288,17 @@ static inline void h_scaled_log_table(double dt, double *tab) {
 // Device-only part: kernels
 // ===================================================================================================
 static __device__ const double g_log_tab[256] = SDE_LOG_TAB_INIT;
+static __device__ const double g_rot_tab[2048] = SDE_ROT_TAB_INIT;
 
-SDE_D void load_log_table(double *s_tab, double dt) {
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = (i & 1) ? g_log_tab[i] * dt : g_log_tab[i];
+// tables of the FP64 transform -> shared memory (18 KB); the FP32 transform needs none
+template <typename T> SDE_D void load_tables(double *s_tab, double dt) {
+  if (sizeof(T) == 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = (i & 1) ? g_log_tab[i] * dt : g_log_tab[i];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_tab[256 + i] = g_rot_tab[i];
+  }
   __syncthreads();
 }
+template <typename T> struct TabSize { static constexpr int value = sizeof(T) == 8 ? SDE_TAB_DOUBLES : 1; };
 
 template <typename T> struct Consts {
   T c[SDE_MAXC];
@@ -385,9 +382,9 @@ template <class Model, typename T, int SCHEME, int PPT>
 SDE_D void sample_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   typedef Batch<T, M> B;
-  __shared__ double s_tab[256];
+  __shared__ double s_tab[TabSize<T>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
-  load_log_table(s_tab, a.dt);
+  load_tables<T>(s_tab, a.dt);
 
   Consts<T> cst;
   T prm[SDE_MAXP];
@@ -396,7 +393,10 @@ SDE_D void sample_body(const sde_args &a) {
   const T dt = (T)a.dt, t0 = (T)a.t0;
   Model::prepare(prm, dt, cst.c);
 
-  const int64_t base = (int64_t)blockIdx.x * (blockDim.x * PPT);
+  // a CTA walks over chunks (grid-stride): the tables are staged once per CTA, partials stay per chunk
+  const int64_t nchunks = (a.npaths + (int64_t)blockDim.x * PPT - 1) / ((int64_t)blockDim.x * PPT);
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+  const int64_t base = chunk * (blockDim.x * PPT);
   T x[PPT][SDE_MAXD];
   bool live[PPT];
 #pragma unroll
@@ -472,7 +472,8 @@ SDE_D void sample_body(const sde_args &a) {
         }
       }
     }
-    block_reduce_store<2 * SDE_MAXF>(acc, 2 * nf, s_red, a.partials + (int64_t)blockIdx.x * (2 * SDE_MAXF));
+    block_reduce_store<2 * SDE_MAXF>(acc, 2 * nf, s_red, a.partials + chunk * (2 * SDE_MAXF));
+    __syncthreads();  // s_red is reused by the next chunk
     bad = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
   } else if (a.nonfinite) {
@@ -482,6 +483,7 @@ SDE_D void sample_body(const sde_args &a) {
     bad = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
   }
+  }  // chunk loop
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -494,9 +496,9 @@ template <class Model, typename T, int SCHEME>
 SDE_D void mlmc_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   typedef Batch<T, M> B;
-  __shared__ double s_tab[256];
+  __shared__ double s_tab[TabSize<T>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
-  load_log_table(s_tab, a.dt);
+  load_tables<T>(s_tab, a.dt);
 
   Consts<T> cf, cc;
   T prm[SDE_MAXP];
@@ -506,7 +508,9 @@ SDE_D void mlmc_body(const sde_args &a) {
   Model::prepare(prm, dtf, cf.c);
   Model::prepare(prm, dtc, cc.c);
 
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nchunks = (a.npaths + blockDim.x - 1) / blockDim.x;
+  for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+  const int64_t k = chunk * blockDim.x + threadIdx.x;
   const bool live = k < a.npaths;
   const uint64_t gpath = (uint64_t)(a.path0 + k);
   T xf[SDE_MAXD], xc[SDE_MAXD], DW[M > 0 ? M : 1];
@@ -576,7 +580,8 @@ SDE_D void mlmc_body(const sde_args &a) {
         bad = 1;
       }
     }
-    block_reduce_store<2 * SDE_MAXF>(acc, 6, s_red, a.partials + (int64_t)blockIdx.x * (2 * SDE_MAXF));
+    block_reduce_store<2 * SDE_MAXF>(acc, 6, s_red, a.partials + chunk * (2 * SDE_MAXF));
+    __syncthreads();  // s_red is reused by the next chunk
     bad = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
   } else if (a.nonfinite) {
@@ -584,6 +589,7 @@ SDE_D void mlmc_body(const sde_args &a) {
     bad = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
   }
+  }  // chunk loop
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -602,8 +608,8 @@ template <class Model, typename T, int SCHEME>
 SDE_D void simulate_soa_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M, VEC = 16 / (int)sizeof(T);
   typedef Batch<T, M> B;
-  __shared__ double s_tab[256];
-  load_log_table(s_tab, a.dt);
+  __shared__ double s_tab[TabSize<T>::value];
+  load_tables<T>(s_tab, a.dt);
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
@@ -661,6 +667,32 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   }
 }
 
+// Cooperative copy between a warp's shared-memory tile [32 paths][LD] and global memory where path r's row
+// segment starts at g + r*gstride: element e = k*32 + lane of the flattened (32 x ROW) tile, fully unrolled, so a
+// warp instruction moves whole 128-byte row segments and all of a lane's loads are in flight together.
+template <typename T, int ROW, int LD>
+SDE_D void tile_load(T *tile, const T *g, int64_t gstride, int nlive, int ncols, int lane) {
+  T v[ROW];
+#pragma unroll
+  for (int k = 0; k < ROW; k++) {
+    const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW;
+    v[k] = (r < nlive && c < ncols) ? __ldcs(g + r * gstride + c) : (T)0;
+  }
+#pragma unroll
+  for (int k = 0; k < ROW; k++) {
+    const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW;
+    tile[r * LD + c] = v[k];
+  }
+}
+template <typename T, int ROW, int LD>
+SDE_D void tile_store(const T *tile, T *g, int64_t gstride, int nlive, int ncols, int lane) {
+#pragma unroll
+  for (int k = 0; k < ROW; k++) {
+    const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW;
+    if (r < nlive && c < ncols) __stcs(g + r * gstride + c, tile[r * LD + c]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K2b full trajectories written directly in the reference's memory order [path][time][D]:
 //     each warp stages a (32 paths) x (TS time rows) tile in shared memory and writes whole path rows,
@@ -669,13 +701,13 @@ SDE_D void simulate_soa_body(const sde_args &a) {
 template <class Model, typename T, int SCHEME>
 SDE_D void simulate_ref_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
-  constexpr int TS = 32 / D;                 // time rows per tile
-  constexpr int ROW = TS * D;                 // elements per path per tile (<= 32)
+  constexpr int TS = (sizeof(T) == 8 ? 16 : 32) / D;  // time rows per tile: 128-byte row segments per path
+  constexpr int ROW = TS * D;                 // elements per path per tile
   constexpr int LDS = ROW | 1;                // odd stride: conflict-free column writes
   typedef Batch<T, M> B;
-  __shared__ double s_tab[256];
+  __shared__ double s_tab[TabSize<T>::value];
   __shared__ T s_tile[SDE_BLOCK / 32][32 * LDS];
-  load_log_table(s_tab, a.dt);
+  load_tables<T>(s_tab, a.dt);
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
@@ -704,11 +736,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   };
   auto flush = [&]() {
     __syncwarp();
-    const int n = fill * D;
-    for (int r = 0; r < nrow_live; r++) {
-      T *dst = out + ((wbase + r) * nrows + row0) * D;
-      for (int e = lane; e < n; e += 32) __stcs(dst + e, tile[r * LDS + e]);
-    }
+    tile_store<T, ROW, LDS>(tile, out + (wbase * nrows + row0) * D, nrows * D, nrow_live, fill * D, lane);
     __syncwarp();
     row0 += fill;
     fill = 0;
@@ -736,40 +764,68 @@ SDE_D void simulate_ref_body(const sde_args &a) {
 // ---------------------------------------------------------------------------------------------------
 // K3  Wiener-driven trajectories, in place allowed: simulate!(x, model, scheme, t0, x0, w)  [simulation.jl:119-134]
 //     w (a.out2) and x (a.out) both in reference order [path][row][.]; increments = w[i] - w[i-1].
-//     Parity entry point: with SDE_STRICT=1 the arithmetic is the reference's operation for operation.
+//     The only HBM-bound kernel of the path (one load + one store per element): each warp owns 32 paths and
+//     moves (32 paths) x (TS rows) tiles through shared memory, so that global loads and stores are whole
+//     row segments of one path (coalesced) while every lane walks its own path inside the tile
+//     (odd row stride: conflict-free).  A tile is loaded completely before any of it is stored => x === w is safe.
+//     Parity entry point: with SDE_STRICT=1 the arithmetic is the reference's, operation for operation.
 // ---------------------------------------------------------------------------------------------------
 template <class Model, typename T, int SCHEME>
 SDE_D void simulate_wiener_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M, MW = (M > 0 ? M : 1);
+  constexpr int DM = D > MW ? D : MW;
+  constexpr int TS = (sizeof(T) == 8 ? 16 : 32) / DM;  // rows per tile
+  constexpr int WROW = TS * MW, XROW = TS * D;
+  constexpr int WLD = WROW | 1, XLD = XROW | 1;
+  __shared__ T s_w[SDE_BLOCK / 32][32 * WLD];
+  __shared__ T s_x[SDE_BLOCK / 32][32 * XLD];
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
   for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
   const T dt = (T)a.dt, t0 = (T)a.t0;
   Model::prepare(prm, dt, cst.c);
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.npaths) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * blockDim.x + (wid << 5);
+  if (wbase >= a.npaths) return;
+  const int nlive = (int)((a.npaths - wbase) < 32 ? (a.npaths - wbase) : 32);
   const int64_t nrows = a.nsteps + 1;
-  const T *w = (const T *)a.out2 + k * nrows * MW;
-  T *xo = (T *)a.out + k * nrows * D;
+  const T *w = (const T *)a.out2;
+  T *xo = (T *)a.out;
+  T *tw = s_w[wid], *tx = s_x[wid];
   T x[SDE_MAXD], wprev[MW], dw[MW];
-#pragma unroll
-  for (int j = 0; j < MW; j++) wprev[j] = w[j];
 #pragma unroll
   for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
 #pragma unroll
-  for (int d = 0; d < D; d++) xo[d] = x[d];
-  for (int64_t i = 1; i < nrows; i++) {
-    const T t = t0 + (T)(i - 1) * dt;
+  for (int j = 0; j < MW; j++) wprev[j] = (T)0;
+
+  for (int64_t row0 = 0; row0 < nrows; row0 += TS) {
+    const int nr = (int)((nrows - row0) < TS ? (nrows - row0) : TS);
+    // cooperative, coalesced load of the w tile
+    tile_load<T, WROW, WLD>(tw, w + (wbase * nrows + row0) * MW, nrows * MW, nlive, nr * MW, lane);
+    __syncwarp();
+    // every lane integrates its own path over the tile
+    for (int i = 0; i < nr; i++) {
+      const int64_t row = row0 + i;
+      if (row == 0) {
 #pragma unroll
-    for (int j = 0; j < MW; j++) {
-      const T wn = w[i * MW + j];
-      dw[j] = wn - wprev[j];
-      wprev[j] = wn;
+        for (int j = 0; j < MW; j++) wprev[j] = tw[lane * WLD + j];
+      } else {
+        const T t = t0 + (T)(row - 1) * dt;
+#pragma unroll
+        for (int j = 0; j < MW; j++) {
+          const T wn = tw[lane * WLD + i * MW + j];
+          dw[j] = wn - wprev[j];
+          wprev[j] = wn;
+        }
+        Model::template step<SCHEME>(cst.c, t, dt, dw, x);
+      }
+#pragma unroll
+      for (int d = 0; d < D; d++) tx[lane * XLD + i * D + d] = x[d];
     }
-    Model::template step<SCHEME>(cst.c, t, dt, dw, x);
-#pragma unroll
-    for (int d = 0; d < D; d++) xo[i * D + d] = x[d];
+    __syncwarp();
+    tile_store<T, XROW, XLD>(tx, xo + (wbase * nrows + row0) * D, nrows * D, nlive, nr * D, lane);
+    __syncwarp();
   }
 }
 
@@ -804,7 +860,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }
 
 #define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \

@@ -15,8 +15,8 @@ extern "C" void h_normals_f64(uint64_t seed, uint32_t stream, uint64_t path, uin
     uint32_t r[4];
     philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(q >> 1), stream, (uint32_t)seed,
                   (uint32_t)(seed >> 32), r);
-    double z[2], tab[256], lk[6];
-    h_scaled_log_table(scale2, tab);
+    double z[2], tab[SDE_TAB_DOUBLES], lk[6];
+    h_scaled_tables(scale2, tab);
     make_log_consts(scale2, lk);
     normal_pair_f64(r, tab, lk, z[0], z[1]);
     out[i] = z[q & 1];
@@ -37,8 +37,8 @@ extern "C" void h_normals_f32(uint64_t seed, uint32_t stream, uint64_t path, uin
 // raw transform on chosen bits (edge cases: tails, u1 -> 1, quadrant boundaries)
 extern "C" void h_pair_from_bits(const uint32_t *r4, double scale2, double *z) {
   uint32_t r[4] = {r4[0], r4[1], r4[2], r4[3]};
-  double tab[256], lk[6];
-  h_scaled_log_table(scale2, tab);
+  double tab[SDE_TAB_DOUBLES], lk[6];
+  h_scaled_tables(scale2, tab);
   make_log_consts(scale2, lk);
   normal_pair_f64(r, tab, lk, z[0], z[1]);
 }

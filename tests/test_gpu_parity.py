@@ -234,6 +234,17 @@ def test_estimate_equals_mean_of_sample(gpu):
     assert abs(c.mean[0] - pay.mean()) <= 1e-10 and abs(c.stderr[0] - pay.std(ddof=1) / math.sqrt(n)) <= 1e-10
 
 
+def test_estimate_with_more_chunks_than_ctas(gpu):
+    """CTAs walk over chunks grid-stride once the grid is capped: sums still equal the sampled states' sums."""
+    import math
+    m, sch = gpu.BlackScholes(*BS_P), gpu.EulerMaruyama(1 / 8)
+    n = 148 * 64 * 256 * 2 + 12345
+    x = gpu.sample(m, sch, 0.0, 100.0, 8, n, seed=6)
+    e = gpu.estimate(m, sch, gpu.Moments(), 0.0, 100.0, 8, n, seed=6)
+    assert e.n == n and abs(e.sums[0, 0] - math.fsum(x)) / e.sums[0, 0] <= 1e-13
+    assert abs(e.sums[0, 1] - math.fsum(x * x)) / e.sums[0, 1] <= 1e-13
+
+
 def test_estimate_is_invariant_under_sharding(gpu):
     """Bit-identical sums for 1 and 2 shards (host-combined limbs stand in for the NCCL all-reduce)."""
     m, sch = gpu.Heston(*HESTON_P), gpu.EulerMaruyama(1 / 16)

@@ -125,6 +125,22 @@ def main():
         out.append(f"  {hexf(inv[j])}, {hexf(tl[j])}, \\")
     out.append("}")
 
+    # table-driven sincos: angle = (i + 1/2 + d) / 1024 turns, |d| <= 1/2;  t = 2^54 d is the signed integer offset
+    #   sin(2 pi d / 1024) = t * (S0 + S1 T + S2 T^2),  cos = 1 + C1 T + C2 T^2,   T = t^2   (Taylor; |phi| <= 3.07e-3)
+    a = 2 * mp.pi / 1024 / mp.mpf(2) ** 54
+    for nm, v in (("SDE_ROT_S0", a), ("SDE_ROT_S1", -a ** 3 / 6), ("SDE_ROT_S2", a ** 5 / 120),
+                  ("SDE_ROT_C1", -a ** 2 / 2), ("SDE_ROT_C2", a ** 4 / 24)):
+        kidx.append((nm, hexf(v)))
+    phi = mp.pi / 1024
+    report.append(f"ROT: truncation errors sin {mp.nstr(phi ** 7 / 5040, 3)}, cos {mp.nstr(phi ** 6 / 720, 3)}")
+    out.append("// " + report[-1])
+    out.append("// rotation table: {cos, sin}(2 pi (i + 1/2) / 1024), i = 0..1023")
+    out.append("#define SDE_ROT_TAB_INIT { \\")
+    for i in range(1024):
+        th = 2 * mp.pi * (mp.mpf(i) + mp.mpf(1) / 2) / 1024
+        out.append(f"  {hexf(mp.cos(th))}, {hexf(mp.sin(th))}, \\")
+    out.append("}")
+
     out.append("// FP64 constants live in one __constant__ array (uniform-register operands of DFMA on sm_100a);")
     out.append("// SDE_K(name) selects the element on the device and the literal on the host.")
     for i, (nm, hx) in enumerate(kidx):

@@ -15,6 +15,21 @@ if kind == "sample":
     for seed in range(2):
         e = S.estimate(m, sch, S.Moments(), 0.0, [100.0, 0.4], 1024, npaths, seed=seed, precision=prec)
         print(seed, e.mean, S.last_kernel_ms(), npaths * 1024 / S.last_kernel_ms() / 1e6, "G path-steps/s")
+elif kind == "wiener":  # Wiener-driven in-place trajectories: the HBM-bound entry point (one load + one store per element)
+    import torch
+    tdt = torch.float64 if prec == "f64" else torch.float32
+    for name, m, x0, D in (("BlackScholes", S.BlackScholes(0.01, 0.3), 100.0, 1), ("Heston", S.Heston(0.01, 10.0, 0.3, 0.1, 0.4), [100.0, 0.4], 2)):
+        n = npaths // D
+        w = torch.empty((n, 513) if D == 1 else (n, 513, D), dtype=tdt, device="cuda")
+        sch = S.EulerMaruyama(1 / 512)
+        for rep in range(3):
+            S.wiener_(w, 1 / 512, seed=rep)
+            t_w = S.last_kernel_ms()
+            S.simulate_(w, m, sch, 0.0, x0, w)
+            ms = S.last_kernel_ms()
+            nbytes = 2 * w.numel() * w.element_size()
+            print(name, prec, rep, "wiener! %.3f ms (%.0f GB/s written)" % (t_w, nbytes / 2 / t_w / 1e6),
+                  "simulate!(x===w) %.3f ms" % ms, "%.0f GB/s read+write" % (nbytes / ms / 1e6), "mean S_T %.4f" % float(w[:, -1].double().mean() if D == 1 else w[:, -1, 0].double().mean()))
 else:  # full-path BlackScholes Milstein (C3 shape, fewer paths)
     import torch
     m, sch = S.BlackScholes(0.01, 0.3), S.Milstein(1 / 512)

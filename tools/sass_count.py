@@ -30,13 +30,14 @@ def loop_counts(fun):
         m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);", l)
         if m:
             ins.append((int(m.group(1), 16), m.group(2).strip()))
-    best = None
+    loops = []
     for a, t in ins:
         m = re.search(r"BRA\S*\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)", t)
-        if m:
-            tgt = int(m.group(1), 16)
-            if tgt < a and (best is None or a - tgt > best[1] - best[0]):
-                best = (tgt, a)
+        if m and int(m.group(1), 16) < a:
+            loops.append((int(m.group(1), 16), a))
+    # innermost loops only (the kernels wrap the time loop in a chunk loop); the hot one is the largest of those
+    inner = [l for l in loops if not any(o != l and l[0] <= o[0] and o[1] <= l[1] for o in loops)]
+    best = max(inner, key=lambda l: l[1] - l[0])
     cnt = collections.Counter()
     for a, t in ins:
         if best[0] <= a <= best[1]:
