@@ -226,6 +226,15 @@ def main():
             "note": "achieved = 18 algorithmic flops/path-step x path-steps/s (SURVEY §8d); the normal generator "
                     "legitimately executes several times that, see executed_frac",
         }
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "headline_ncu.json")))
+            if prec == "f64":
+                roofline["ncu"] = cap  # pipe utilisation and DRAM bytes of one profiled launch (smaller batch)
+                roofline["traffic_note"] = ("algorithmic traffic is 16 B per path (terminal state), nothing per step: %d bytes "
+                                            "per launch here; ncu measured %d B for %d paths" %
+                                            (16 * P, cap["dram_bytes_read"] + cap["dram_bytes_write"], cap["paths"]))
+        except OSError:
+            pass
         if key in sass:
             fl = sass[key]["fp_flops_per_path_step"]
             roofline["executed_flops_per_path_step"] = fl

@@ -152,6 +152,41 @@ SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
   r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
 }
 
+// The same block function with the key schedule expanded once per thread: the 2 x ROUNDS round keys sit in
+// ordinary registers for the whole time loop (left to itself ptxas re-derives them every iteration with ~14
+// uniform-datapath adds, which cost issue slots like any other instruction).
+struct PhiloxKeys {
+  uint32_t k[2 * SDE_PHILOX_ROUNDS];
+};
+SDE_HD void philox_expand(uint32_t k0, uint32_t k1, PhiloxKeys &ks) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < SDE_PHILOX_ROUNDS; i++) {
+    ks.k[2 * i] = k0 + (uint32_t)i * 0x9E3779B9u;
+    ks.k[2 * i + 1] = k1 + (uint32_t)i * 0xBB67AE85u;
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(ks.k[2 * i]), "+r"(ks.k[2 * i + 1]));  // opaque: keep them, do not rematerialise
+#endif
+  }
+}
+SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &ks, uint32_t (&r)[4]) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int i = 0; i < SDE_PHILOX_ROUNDS; i++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ ks.k[2 * i];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ ks.k[2 * i + 1];
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+  }
+  r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // "sdeb200 normal stream v1", FP64: 128 Philox bits -> two N(0, dt) variates (Box–Muller).
 //   X1 = r1:r0  -> u1 = RN(X1) 2^-64 = m 2^-k, m in [1,2)     (one I2F.F64.U64; X1 == 0 reads as u1 = 2^-1087)
@@ -210,9 +245,10 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const dou
   z1 = g * sb;
 }
 
-// FP32 stream: 128 Philox bits -> four N(0, scale2) variates.  u1 = (r + 1/2) 2^-32, angle = (int32)r' 2^-32
-// turns.  log2 and rsqrt on the MUFU unit, sin/cos by FFMA polynomials (cheaper than two more MUFU ops).
-SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, float &z0, float &z1) {
+// FP32 stream: 128 Philox bits -> four N(0, scale2) variates.  u1 = (r + 1/2) 2^-32, angle = r' / 2^32 turns.
+// log2 and sqrt on the MUFU unit; (cos, sin) from a 256-entry table of cell centres (top 8 bits of r') plus a
+// one-term residual rotation in the 24-bit offset — no quadrant logic.  rotf: {cos, sin} float pairs.
+SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, const float *rotf, float &z0, float &z1) {
 #if defined(__CUDA_ARCH__)
   const float u1 = fmaf(__uint2float_rn(ra), 0x1.0p-32f, 0x1.0p-33f);
   float w = -0x1.62e430p+0f /* 2 ln 2 */ * __log2f(u1);
@@ -227,30 +263,14 @@ SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, float &z0, f
 #else
   const float g = sqrtf(w);
 #endif
-  const uint32_t n = (rb + (1u << 29)) >> 30;
-  const int32_t f = (int32_t)(rb - (n << 30));
-  const float x = (float)f * 0x1.0p-32f;
-  const float u = x * x;
-  float sp = SDE_SINF_C3;
-  sp = fmaf(sp, u, SDE_SINF_C2);
-  sp = fmaf(sp, u, SDE_SINF_C1);
-  sp = fmaf(sp, u, SDE_SINF_C0);
-  const float s = x * sp;
-  float c = SDE_COSF_C4;
-  c = fmaf(c, u, SDE_COSF_C3);
-  c = fmaf(c, u, SDE_COSF_C2);
-  c = fmaf(c, u, SDE_COSF_C1);
-  c = fmaf(c, u, SDE_COSF_C0);
-  const bool swap = (n & 1u) != 0;
-  const float a = swap ? s : c, b = swap ? c : s;
-  const uint32_t fa = ((n + 1u) & 2u) << 30, fb = (n & 2u) << 30;
-#if defined(__CUDA_ARCH__)
-  z0 = g * __uint_as_float(__float_as_uint(a) ^ fa);
-  z1 = g * __uint_as_float(__float_as_uint(b) ^ fb);
-#else
-  z0 = g * (fa ? -a : a);
-  z1 = g * (fb ? -b : b);
-#endif
+  const float *rot = rotf + 2 * (rb >> 24);
+  const float C = rot[0], S = rot[1];
+  const float t = (float)((int32_t)(rb & 0x00FFFFFFu) - 0x00800000);
+  const float u = t * t;
+  const float sn = t * fmaf(SDE_ROTF_S1, u, SDE_ROTF_S0);
+  const float cm = u * fmaf(SDE_ROTF_C2, u, SDE_ROTF_C1);
+  z0 = g * fmaf(C, cm, fmaf(-S, sn, C));
+  z1 = g * fmaf(S, cm, fmaf(C, sn, S));
 }
 
 // Normals per Philox block for each precision.
@@ -263,9 +283,10 @@ SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, const 
   normal_pair_f64(r, tab, lk, z[0], z[1]);
 }
 SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, const double *lk, float scale2, float *z) {
-  (void)tab; (void)lk;
-  normal_pair_f32(r[0], r[1], scale2, z[0], z[1]);
-  normal_pair_f32(r[2], r[3], scale2, z[2], z[3]);
+  (void)lk;
+  const float *rotf = (const float *)tab;
+  normal_pair_f32(r[0], r[1], scale2, rotf, z[0], z[1]);
+  normal_pair_f32(r[2], r[3], scale2, rotf, z[2], z[3]);
 }
 
 #if defined(__CUDACC__)
@@ -277,6 +298,7 @@ constexpr int sde_gcd(int a, int b) { return b == 0 ? a : sde_gcd(b, a % b); }
 // host twin of the log table, for the CPU unit tests of the transform (tests/host_math_harness.cpp)
 static const double h_log_tab[256] = SDE_LOG_TAB_INIT;
 static const double h_rot_tab[2048] = SDE_ROT_TAB_INIT;
+static const float h_rotf_tab[512] = SDE_ROTF_TAB_INIT;
 static inline void h_scaled_tables(double dt, double *tab) {  // tab[SDE_TAB_DOUBLES]
   for (int i = 0; i < 128; i++) { tab[2 * i] = h_log_tab[2 * i]; tab[2 * i + 1] = h_log_tab[2 * i + 1] * dt; }
   for (int i = 0; i < 2048; i++) tab[256 + i] = h_rot_tab[i];
@@ -289,16 +311,20 @@ static inline void h_scaled_tables(double dt, double *tab) {  // tab[SDE_TAB_DOU
 // ===================================================================================================
 static __device__ const double g_log_tab[256] = SDE_LOG_TAB_INIT;
 static __device__ const double g_rot_tab[2048] = SDE_ROT_TAB_INIT;
+static __device__ const float g_rotf_tab[512] = SDE_ROTF_TAB_INIT;
 
-// tables of the FP64 transform -> shared memory (18 KB); the FP32 transform needs none
+// tables of the transforms -> shared memory: FP64 18 KB (log + rotation), FP32 2 KB (rotation, float pairs)
 template <typename T> SDE_D void load_tables(double *s_tab, double dt) {
   if (sizeof(T) == 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = (i & 1) ? g_log_tab[i] * dt : g_log_tab[i];
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_tab[256 + i] = g_rot_tab[i];
+  } else {
+    float *f = (float *)s_tab;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) f[i] = g_rotf_tab[i];
   }
   __syncthreads();
 }
-template <typename T> struct TabSize { static constexpr int value = sizeof(T) == 8 ? SDE_TAB_DOUBLES : 1; };
+template <typename T> struct TabSize { static constexpr int value = sizeof(T) == 8 ? SDE_TAB_DOUBLES : 256; };
 
 template <typename T> struct Consts {
   T c[SDE_MAXC];
@@ -315,7 +341,7 @@ template <typename T, int M> struct Batch {
 };
 
 template <typename T, int M>
-SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, uint32_t k0, uint32_t k1, const double *s_tab,
+SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const PhiloxKeys &ks, const double *s_tab,
                      const double *lk, T scale2, T *dw) {
   typedef Batch<T, M> B;
   if (M == 0) {
@@ -325,7 +351,7 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, uint32_t k0,
 #pragma unroll
   for (int b = 0; b < B::NB; b++) {
     uint32_t r[4];
-    philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, k0, k1, r);
+    philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, ks, r);
     normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB);
   }
 }
@@ -385,6 +411,8 @@ SDE_D void sample_body(const sde_args &a) {
   __shared__ double s_tab[TabSize<T>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
   load_tables<T>(s_tab, a.dt);
+  PhiloxKeys ks;
+  philox_expand(a.seed_lo, a.seed_hi, ks);
 
   Consts<T> cst;
   T prm[SDE_MAXP];
@@ -413,8 +441,8 @@ SDE_D void sample_body(const sde_args &a) {
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
-      gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, a.seed_lo,
-                      a.seed_hi, s_tab, a.lk, dt, dw);
+      gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, ks,
+                      s_tab, a.lk, dt, dw);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         const T t = t0 + (T)(it * B::U + u) * dt;
@@ -426,8 +454,8 @@ SDE_D void sample_body(const sde_args &a) {
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
-      gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, a.seed_lo,
-                      a.seed_hi, s_tab, a.lk, dt, dw);
+      gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, ks,
+                      s_tab, a.lk, dt, dw);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         if (u < rem) {
@@ -499,6 +527,8 @@ SDE_D void mlmc_body(const sde_args &a) {
   __shared__ double s_tab[TabSize<T>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
   load_tables<T>(s_tab, a.dt);
+  PhiloxKeys ks;
+  philox_expand(a.seed_lo, a.seed_hi, ks);
 
   Consts<T> cf, cc;
   T prm[SDE_MAXP];
@@ -525,7 +555,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   int64_t ncoarse = 0;  // coarse steps completed
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[B::NZ];
-    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, a.lk, dtf, dw);
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dtf, dw);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t fstep = it * B::U + u;
@@ -610,6 +640,8 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
   load_tables<T>(s_tab, a.dt);
+  PhiloxKeys ks;
+  philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
@@ -653,7 +685,7 @@ SDE_D void simulate_soa_body(const sde_args &a) {
     T dw[VEC][B::NZ];
 #pragma unroll
     for (int v = 0; v < VEC; v++)
-      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, a.lk, dt, dw[v]);
+      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dt, dw[v]);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;
@@ -708,6 +740,8 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   __shared__ double s_tab[TabSize<T>::value];
   __shared__ T s_tile[SDE_BLOCK / 32][32 * LDS];
   load_tables<T>(s_tab, a.dt);
+  PhiloxKeys ks;
+  philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
@@ -746,7 +780,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[B::NZ];
-    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, a.seed_lo, a.seed_hi, s_tab, a.lk, dt, dw);
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dt, dw);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;

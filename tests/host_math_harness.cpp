@@ -30,7 +30,7 @@ extern "C" void h_normals_f32(uint64_t seed, uint32_t stream, uint64_t path, uin
     philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(q >> 2), stream, (uint32_t)seed,
                   (uint32_t)(seed >> 32), r);
     float z[4];
-    normals_from_block(r, nullptr, nullptr, scale2, z);
+    normals_from_block(r, (const double *)h_rotf_tab, nullptr, scale2, z);
     out[i] = z[q & 3];
   }
 }

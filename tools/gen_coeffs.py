@@ -141,6 +141,21 @@ def main():
         out.append(f"  {hexf(mp.cos(th))}, {hexf(mp.sin(th))}, \\")
     out.append("}")
 
+    # FP32 twin: 256 cells, t = 2^24 d (24-bit signed offset), sin = t (S0 + S1 T), cos - 1 = C1 T
+    af = 2 * mp.pi / 256 / mp.mpf(2) ** 24
+    import struct as _st
+    f32 = lambda v: _st.unpack("f", _st.pack("f", float(v)))[0]
+    out.append(f"#define SDE_ROTF_S0 {float(f32(af)).hex()}f")
+    out.append(f"#define SDE_ROTF_S1 {float(f32(-af ** 3 / 6)).hex()}f")
+    out.append(f"#define SDE_ROTF_C1 {float(f32(-af ** 2 / 2)).hex()}f")
+    out.append(f"#define SDE_ROTF_C2 {float(f32(af ** 4 / 24)).hex()}f")
+    out.append("// FP32 rotation table: {cos, sin}(2 pi (i + 1/2) / 256), i = 0..255")
+    out.append("#define SDE_ROTF_TAB_INIT { \\")
+    for i in range(256):
+        th = 2 * mp.pi * (mp.mpf(i) + mp.mpf(1) / 2) / 256
+        out.append(f"  {float(f32(mp.cos(th))).hex()}f, {float(f32(mp.sin(th))).hex()}f, \\")
+    out.append("}")
+
     out.append("// FP64 constants live in one __constant__ array (uniform-register operands of DFMA on sm_100a);")
     out.append("// SDE_K(name) selects the element on the device and the literal on the host.")
     for i, (nm, hx) in enumerate(kidx):

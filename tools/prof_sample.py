@@ -15,6 +15,13 @@ if kind == "sample":
     for seed in range(2):
         e = S.estimate(m, sch, S.Moments(), 0.0, [100.0, 0.4], 1024, npaths, seed=seed, precision=prec)
         print(seed, e.mean, S.last_kernel_ms(), npaths * 1024 / S.last_kernel_ms() / 1e6, "G path-steps/s")
+elif kind == "bench":  # the bench.py step: fused sample + reduce WITH the terminal states kept in HBM
+    import torch
+    m, sch = S.Heston(0.01, 10.0, 0.3, 0.1, 0.4), S.EulerMaruyama(1 / 1024)
+    term = torch.empty((npaths, 2), dtype=torch.float64 if prec == "f64" else torch.float32, device="cuda")
+    for seed in range(2):
+        e = S.estimate(m, sch, S.Moments(), 0.0, [100.0, 0.4], 1024, npaths, seed=seed, precision=prec, terminal=term)
+        print(seed, e.mean, S.last_kernel_ms(), npaths * 1024 / S.last_kernel_ms() / 1e6, "G path-steps/s", float(term[:, 0].mean()))
 elif kind == "wiener":  # Wiener-driven in-place trajectories: the HBM-bound entry point (one load + one store per element)
     import torch
     tdt = torch.float64 if prec == "f64" else torch.float32
