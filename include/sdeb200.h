@@ -43,9 +43,10 @@ extern "C" {
                                   outputs are still written */
 #define SDEB200_E_UNSUPPORTED (-7) /* not defined by the reference either (e.g. Milstein with M != 1, milstein.jl:4) */
 
-/* schemes: src/schemes/schemes.jl:34,37 */
+/* schemes: src/schemes/schemes.jl:34,37,42 */
 #define SDEB200_EULER_MARUYAMA 0
 #define SDEB200_MILSTEIN 1
+#define SDEB200_RUNGE_KUTTA 2 /* src/schemes/runge_kutta.jl:4-11 — derivative-free Milstein, M == 1 like Milstein */
 /* arithmetic type of state and noise */
 #define SDEB200_F64 0
 #define SDEB200_F32 1
@@ -66,7 +67,7 @@ typedef struct sdeb200_model sdeb200_model;
 
 /* Run options shared by all drivers.  Zero-initialise, then set what differs. */
 typedef struct {
-  int32_t scheme;      /* SDEB200_EULER_MARUYAMA | SDEB200_MILSTEIN       (the scheme's type) */
+  int32_t scheme;      /* SDEB200_EULER_MARUYAMA | SDEB200_MILSTEIN | SDEB200_RUNGE_KUTTA  (the scheme's type) */
   int32_t precision;   /* SDEB200_F64 | SDEB200_F32 */
   int32_t math;        /* SDEB200_MATH_FAST | SDEB200_MATH_STRICT */
   int32_t reserved;

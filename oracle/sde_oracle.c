@@ -193,7 +193,8 @@ int oracle_diffusion(int id, const double *p, double t, const double *x, double 
  * step: src/schemes/euler_maruyama.jl:1-6 and src/schemes/milstein.jl:4-10.
  * Evaluation order per SURVEY Appendix A: x0 + μ*Δt + σ*Δw == (x0 + μ*Δt) + (σ*Δw),
  * static mat-vec row i = σ[i,1]*Δw[1] + σ[i,2]*Δw[2] + ... left to right.
- * scheme: 0 = EulerMaruyama, 1 = Milstein (M == 1 only, as in the reference).
+ * scheme: 0 = EulerMaruyama, 1 = Milstein, 2 = RungeKutta (src/schemes/runge_kutta.jl:4-11, the derivative-free
+ * Milstein); 1 and 2 for M == 1 only, as in the reference.
  * ------------------------------------------------------------------------------------------ */
 static int step(const model_def *m, int scheme, const double *p, double dt, double t, const double *x0,
                 const double *dw, double *x1) {
@@ -229,6 +230,20 @@ static int step(const model_def *m, int scheme, const double *p, double dt, doub
       }
       x1[i] = ((x0[i] + mu[i] * dt) + sig[i * MAXM] * dw[0]) + (js * c) / 2.0;
     }
+    return 0;
+  }
+  if (scheme == 2) {
+    /* x0hat = x0 + μ*Δt + vec(σ)*sqrt(Δt); σpred = diffusion(model, t0, x0hat);
+     * x = x0 + μ*Δt + σ*Δw + (σpred - σ)*(Δw.^2 - Δt)/(2*sqrt(Δt))          runge_kutta.jl:7-9 */
+    if (m->M != 1) return -2;
+    double xh[MAXD], sp[MAXD * MAXM];
+    const double sq = sqrt(dt);
+    memset(sp, 0, sizeof sp);
+    for (int i = 0; i < m->D; i++) xh[i] = (x0[i] + mu[i] * dt) + sig[i * MAXM] * sq;
+    m->diffusion(p, t, xh, sp);
+    const double c = dw[0] * dw[0] - dt, den = 2.0 * sq;
+    for (int i = 0; i < m->D; i++)
+      x1[i] = ((x0[i] + mu[i] * dt) + sig[i * MAXM] * dw[0]) + ((sp[i * MAXM] - sig[i * MAXM]) * c) / den;
     return 0;
   }
   return -3;

@@ -48,6 +48,7 @@ template <int DIM> struct WienerN {
 
 XSCHEME(BlackScholes, TAGGED(bs), 0, em)
 XSCHEME(BlackScholes, TAGGED(bs), 1, mil)
+XSCHEME(BlackScholes, TAGGED(bs), 2, rk)
 XCOEF(BlackScholes, TAGGED(bs))
 XSCHEME(Heston, TAGGED(heston), 0, em)
 XCOEF(Heston, TAGGED(heston))
@@ -72,6 +73,7 @@ extern "C" int SDE_AOT_TABLE(int model, sde_ktable *t) {
   if (model == 0) {
     XFILL((*t), TAGGED(bs), 0, em)
     XFILL((*t), TAGGED(bs), 1, mil)
+    XFILL((*t), TAGGED(bs), 2, rk)
     XCOEFFILL((*t), TAGGED(bs))
     return 0;
   }

@@ -368,12 +368,13 @@ extern "C" int sdeb200_model_compile(sdeb200_model *m, int precision, int math) 
 static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0) {
   if (!m || !o || !x0) return fail(SDEB200_E_ARG, "null argument");
   if (!params && !m->params.empty()) return fail(SDEB200_E_ARG, "params is NULL but the model has %zu", m->params.size());
-  if (o->scheme != SDEB200_EULER_MARUYAMA && o->scheme != SDEB200_MILSTEIN)
+  if (o->scheme < SDEB200_EULER_MARUYAMA || o->scheme > SDEB200_RUNGE_KUTTA)
     return fail(SDEB200_E_ARG, "unknown scheme %d", o->scheme);
-  if (o->scheme == SDEB200_MILSTEIN && m->M != 1)
+  if (o->scheme != SDEB200_EULER_MARUYAMA && m->M != 1)
     return fail(SDEB200_E_UNSUPPORTED,
-                "Milstein is defined for models with one Wiener process only (M == 1), as in the reference "
-                "(src/schemes/milstein.jl:4); '%s' has M == %d", m->name.c_str(), m->M);
+                "%s is defined for models with one Wiener process only (M == 1), as in the reference "
+                "(src/schemes/milstein.jl:4, runge_kutta.jl:4); '%s' has M == %d",
+                o->scheme == SDEB200_MILSTEIN ? "Milstein" : "RungeKutta", m->name.c_str(), m->M);
   if (o->precision < 0 || o->precision > 1 || o->math < 0 || o->math > 1) return fail(SDEB200_E_ARG, "bad precision/math");
   if (!(o->dt > 0.0) || !isfinite(o->dt)) return fail(SDEB200_E_ARG, "scheme Δt must be positive and finite");
   return 0;

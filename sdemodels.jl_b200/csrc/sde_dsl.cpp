@@ -796,6 +796,13 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
         o << "    c[" << NP + (int)i << "] = " << ep.ex(hoisted[i]) << ";  // " << to_str(hoisted[i]) << "\n";
     }
     o << "  }\n";
+    if (M == 1) {  // diffusion column at an arbitrary state: RungeKutta evaluates it at the predictor (runge_kutta.jl:8)
+      Emit es = em;
+      for (int i = 0; i < D; i++) es.sym[vars[i]] = "xx[" + std::to_string(i) + "]";
+      o << "  template <typename T> SDE_HD static void sigma_col(const T *c, T t, const T *xx, T *s) {\n    (void)c; (void)t; (void)xx;\n";
+      for (int i = 0; i < D; i++) o << "    s[" << i << "] = " << es.ex(hdiff[i][0]) << ";\n";
+      o << "  }\n";
+    }
     o << "  template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {\n";
     o << "    (void)c; (void)t; (void)dw;\n";
     for (int i = 0; i < D; i++) o << "    const T x" << i << " = x[" << i << "];  // " << vars[i] << "\n";
@@ -828,6 +835,20 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
         }
         if (js.empty()) js = em.lit(0, true);
         o << "      y" << i << " = y" << i << " + ((" << js << ") * cc) / " << em.lit(2, true) << ";\n";
+      }
+      o << "    }\n";
+    }
+    if (M == 1) {
+      // x0hat = x0 + μΔt + σ√Δt; σpred = diffusion(x0hat); + (σpred - σ)(Δw² - Δt)/(2√Δt)   runge_kutta.jl:7-9
+      o << "    if (SCHEME == 2) {\n      const T sq = sqrt(dt);\n      T xh[" << D << "], sp[" << D << "];\n";
+      for (int i = 0; i < D; i++) {
+        const std::string si = is_val(diffm[i][0], 0) ? em.lit(0, true) : "s" + std::to_string(i) + "_0";
+        o << "      xh[" << i << "] = (x" << i << " + mu" << i << " * dt) + " << si << " * sq;\n";
+      }
+      o << "      sigma_col(c, t, xh, sp);\n      const T cc = dw[0] * dw[0] - dt, den = " << em.lit(2, true) << " * sq;\n";
+      for (int i = 0; i < D; i++) {
+        const std::string si = is_val(diffm[i][0], 0) ? em.lit(0, true) : "s" + std::to_string(i) + "_0";
+        o << "      y" << i << " = y" << i << " + ((sp[" << i << "] - " << si << ") * cc) / den;\n";
       }
       o << "    }\n";
     }

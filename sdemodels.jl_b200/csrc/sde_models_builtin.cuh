@@ -28,7 +28,9 @@ struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
     c[1] = p[1];
 #if !SDE_STRICT
     c[2] = p[0] * dt;                 // r Δt
-    c[3] = (T)0.5 * p[1] * p[1];      // σ²/2
+    c[3] = (T)0.5 * p[1] * p[1];      // σ²/2                                   (Milstein)
+    const T sq = sde_sqrt(dt);
+    c[4] = p[1] * (p[0] * dt + p[1] * sq) / ((T)2 * sq);  // σ (rΔt + σ√Δt) / (2√Δt)   (RungeKutta: (σpred-σ)/(2√Δt) per unit S)
 #else
     (void)dt;
 #endif
@@ -40,10 +42,17 @@ struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
     const T mu = c[0] * S, sg = c[1] * S;
     T y = (S + mu * dt) + sg * w;
     if (SCHEME == 1) y = y + ((c[1] * sg) * (w * w - dt)) / (T)2;  // ∂σ = σ exactly (ForwardDiff dual of σ*x)
+    if (SCHEME == 2) {                                              // runge_kutta.jl:7-9
+      const T sq = sde_sqrt(dt);
+      const T xh = (S + mu * dt) + sg * sq;
+      const T sp = c[1] * xh;
+      y = y + ((sp - sg) * (w * w - dt)) / ((T)2 * sq);
+    }
     x[0] = y;
 #else
     T a = sde_fma(c[1], w, c[2]);
     if (SCHEME == 1) a = sde_fma(c[3], sde_fma(w, w, -dt), a);
+    if (SCHEME == 2) a = sde_fma(c[4], sde_fma(w, w, -dt), a);
     x[0] = sde_fma(S, a, S);
 #endif
   }
@@ -71,7 +80,7 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
   }
   template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
     (void)t;
-    static_assert(SCHEME == 0, "the reference defines Milstein for M == 1 models only (milstein.jl:4)");
+    static_assert(SCHEME == 0, "the reference defines Milstein / RungeKutta for M == 1 models only (milstein.jl:4)");
     const T S = x[0], V = x[1];
 #if SDE_STRICT
     const T sv = sde_sqrt(V);

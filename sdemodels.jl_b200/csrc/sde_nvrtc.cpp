@@ -64,6 +64,7 @@ int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision,
   const char *T = precision == 0 ? "double" : "float", *P = precision == 0 ? "f64" : "f32";
   src += std::string("\nSDE_KERNELS(sdeb200::GenModel, gen, 0, em, ") + T + ", " + P + ")\n";
   if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 1, mil, ") + T + ", " + P + ")\n";
+  if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 2, rk, ") + T + ", " + P + ")\n";
   src += "SDE_KERNELS_COEF(sdeb200::GenModel, gen)\n";
   const char *hdr_src[] = {sde_embedded_device_cuh, sde_embedded_args_h, sde_embedded_coeffs_inc};
   const char *hdr_name[] = {"sde_device.cuh", "sde_args.h", "sde_coeffs.inc"};
@@ -117,8 +118,8 @@ int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precisio
     *dst = (const void *)k;
     return true;
   };
-  const int nsch = M == 1 ? 2 : 1;
-  const char *sn[2] = {"em", "mil"};
+  const int nsch = M == 1 ? 3 : 1;
+  const char *sn[3] = {"em", "mil", "rk"};
   for (int s = 0; s < nsch; s++) {
     const std::string suf = std::string("_") + sn[s] + "_" + P;
     if (!get("sdek_gen_sample" + suf, &kt->sample[s][precision]) || !get("sdek_gen_mlmc" + suf, &kt->mlmc[s][precision]) ||

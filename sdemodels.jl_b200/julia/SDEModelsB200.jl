@@ -18,7 +18,7 @@
 module SDEModelsB200
 
 using SDEModels
-using SDEModels: AbstractSDE, AbstractScheme, EulerMaruyama, Milstein, MultilevelScheme, subdivide, dim
+using SDEModels: AbstractSDE, AbstractScheme, EulerMaruyama, Milstein, RungeKutta, MultilevelScheme, subdivide, dim
 using StaticArrays
 import SDEModels: sample, simulate, simulate!
 
@@ -56,6 +56,7 @@ SDEModels.subdivide(b::B200, n) = B200(subdivide(b.scheme, n), b.seed, b.precisi
 
 scheme_id(::EulerMaruyama) = Int32(0)
 scheme_id(::Milstein)      = Int32(1)
+scheme_id(::RungeKutta)    = Int32(2)
 opts(b::B200, t0; dt = b.scheme.Δt, stream = b.stream) =
   Opts(scheme_id(b.scheme), b.precision === Float32 ? 1 : 0, b.strict ? 1 : 0, 0, Float64(t0), Float64(dt),
        b.seed, stream, 0, b.path_offset)

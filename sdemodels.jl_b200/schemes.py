@@ -27,6 +27,12 @@ class Milstein(_UnconditionalScheme):
     _id = _lib.MILSTEIN
 
 
+class RungeKutta(_UnconditionalScheme):
+    """src/schemes/runge_kutta.jl:4-11 — derivative-free Milstein (diffusion re-evaluated at a predictor state);
+    models with one Wiener process only, as in the reference."""
+    _id = _lib.RUNGE_KUTTA
+
+
 def subdivide(scheme, nsubsteps):
     """subdivide(scheme::T, n) = T(scheme.Δt / n)   (schemes.jl:53-54)"""
     return type(scheme)(scheme.dt / nsubsteps)

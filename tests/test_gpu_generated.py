@@ -10,7 +10,7 @@ from conftest import BS_P, HESTON_P
 from test_dsl import CASES, MODELS
 
 pytestmark = pytest.mark.gpu
-EM, MIL = 0, 1
+EM, MIL, RK = 0, 1, 2
 
 
 def rel_err(a, b):
@@ -75,6 +75,8 @@ def test_reference_simulation_testset(gpu):
     # Milstein has no method for M != 1 (runtests.jl:90,92 are commented out for that reason)
     with pytest.raises(S.SDEB200Error):
         S.sample(det, S.Milstein(1.0), 0.0, 1.0, 1)
+    with pytest.raises(S.SDEB200Error):
+        S.sample(m2, S.RungeKutta(0.01), 0.0, [100.0, 0.4], 10, 10)  # runge_kutta.jl:4: AbstractSDE{D,1} only
 
 
 @pytest.mark.parametrize("name,params,x,t", CASES)
@@ -86,13 +88,11 @@ def test_generated_models_match_oracle_path_by_path(gpu, O, name, params, x, t):
     m = gen(S, name)(*params)
     nsteps, npaths, dt = 48, 130, 1.0 / 64
     x0 = x[0] if D == 1 else x
-    schemes = [EM] + ([MIL] if M == 1 and name not in ("SpecialCaseModel2",) else [])
-    if name == "SpecialCaseModel2":
-        schemes = [EM, MIL]
+    schemes = [EM] + ([MIL, RK] if M == 1 else [])
     for sid in schemes:
         z = O.normals_paths(77, 5, 0, npaths, nsteps, M)
         ref = O.sample_z(name, sid, params, t, dt, x, z)
-        sch = S.EulerMaruyama(dt) if sid == EM else S.Milstein(dt)
+        sch = (S.EulerMaruyama, S.Milstein, S.RungeKutta)[sid](dt)
         for mth in ("strict", "fast"):
             got = S.sample(m, sch, t, x0, nsteps, npaths, seed=77, stream=5, math=mth).reshape(npaths, D)
             scale = np.maximum(np.abs(ref), 1e-3)
@@ -110,12 +110,12 @@ def test_generated_models_wiener_driven_strict_bitwise(gpu, O, name, params, x, 
     nsteps, npaths, dt = 40, 70, 1.0 / 128
     z = np.random.default_rng(5).standard_normal((npaths, nsteps, M))
     w = O.wiener_z(dt, z)
-    for sid in [EM] + ([MIL] if M == 1 else []):
+    for sid in [EM] + ([MIL, RK] if M == 1 else []):
         ref = O.simulate_wiener(name, sid, params, t, dt, x, w)
         out = np.empty_like(ref)
         xs = out[..., 0] if D == 1 else out
         ws = np.ascontiguousarray(w[..., 0] if (M == 1 and D == 1) else w)
-        sch = S.EulerMaruyama(dt) if sid == EM else S.Milstein(dt)
+        sch = (S.EulerMaruyama, S.Milstein, S.RungeKutta)[sid](dt)
         S.simulate_(xs, m, sch, t, x[0] if D == 1 else x, ws, math="strict")
         assert np.array_equal(out, ref), (name, sid)
 

@@ -10,7 +10,7 @@ from conftest import BS_P, HESTON_P
 
 pytestmark = pytest.mark.gpu
 
-EM, MIL = 0, 1
+EM, MIL, RK = 0, 1, 2
 
 
 def rel_err(a, b):
@@ -26,6 +26,7 @@ def wiener_paths(O, npaths, nsteps, dim, dt, seed):
 CASES = [
     ("BlackScholes", BS_P, 100.0, EM, 252),
     ("BlackScholes", BS_P, 100.0, MIL, 512),
+    ("BlackScholes", BS_P, 100.0, RK, 128),
     ("Heston", HESTON_P, [100.0, 0.4], EM, 1024),
 ]
 
@@ -35,7 +36,7 @@ def _model(gpu, name, params):
 
 
 def _scheme(gpu, sid, dt):
-    return gpu.EulerMaruyama(dt) if sid == EM else gpu.Milstein(dt)
+    return (gpu.EulerMaruyama, gpu.Milstein, gpu.RungeKutta)[sid](dt)
 
 
 @pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
@@ -318,3 +319,45 @@ def test_mlmc_estimator_call_price(gpu):
     assert np.all(est.nonfinite == 0) and list(est.n) == n
     assert np.all(np.abs(est.level_mean[1:]) < 1.0) and est.level_var[-1] < est.level_var[1]
     assert abs(est.mean - 22.3374853590066) <= 3 * est.stderr + 0.15
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("npaths,nsteps", [(1, 1), (31, 3), (1000, 37), (4097, 17)])
+def test_no_out_of_bounds_writes(gpu, precision, npaths, nsteps):
+    """compute-sanitizer is closed on this pool: every device output is carved out of a larger buffer whose guard
+    zones (sentinel values on both sides) must be untouched after the kernels ran, for ragged sizes."""
+    import torch
+    S = gpu
+    tdt = torch.float64 if precision == "f64" else torch.float32
+    G = 4096
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        full = torch.full((n + 2 * G,), -12345.0, dtype=tdt, device="cuda")
+        return full[G:G + n].view(*shape), full
+
+    def intact(full):
+        return bool((full[:G] == -12345.0).all() and (full[-G:] == -12345.0).all())
+
+    he, bs = S.Heston(*HESTON_P), S.BlackScholes(*BS_P)
+    for m, x0, D, sch in ((he, [100.0, 0.4], 2, S.EulerMaruyama(1 / 64)), (bs, 100.0, 1, S.Milstein(1 / 64))):
+        shp = (npaths, D) if D > 1 else (npaths,)
+        v, f = guarded(shp)
+        S.sample(m, sch, 0.0, x0, nsteps, npaths, seed=1, precision=precision, out=v)
+        assert intact(f) and bool(torch.isfinite(v).all())
+        shp = (npaths, nsteps + 1, D) if D > 1 else (npaths, nsteps + 1)
+        v, f = guarded(shp)
+        S.simulate(m, sch, 0.0, x0, nsteps, npaths, seed=1, precision=precision, out=v)
+        assert intact(f) and bool(torch.isfinite(v).all())
+        w, fw = guarded(shp)
+        S.wiener_(w, 1 / 64, seed=2)
+        assert intact(fw) and bool((w[:, 0] == 0).all())
+        S.simulate_(w, m, sch, 0.0, x0, w)
+        assert intact(fw) and bool(torch.isfinite(w).all())
+        shp = (nsteps + 1, D, npaths) if D > 1 else (nsteps + 1, npaths)
+        v, f = guarded(shp)
+        S.simulate(m, sch, 0.0, x0, nsteps, npaths, seed=1, precision=precision, out=v, layout="soa")
+        assert intact(f) and bool(torch.isfinite(v).all())
+        v, f = guarded((npaths, D) if D > 1 else (npaths,))
+        S.estimate(m, sch, S.Moments(), 0.0, x0, nsteps, npaths, seed=1, precision=precision, terminal=v)
+        assert intact(f) and bool(torch.isfinite(v).all())

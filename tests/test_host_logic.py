@@ -19,6 +19,7 @@ def test_scheme_types(S):
     f = S.subdivide(e, 4)
     assert isinstance(f, S.EulerMaruyama) and f.dt == 0.1 / 4
     assert isinstance(S.subdivide(S.Milstein(0.5), 2), S.Milstein)
+    assert S.subdivide(S.RungeKutta(0.5), 5) == S.RungeKutta(0.1)
 
 
 @pytest.mark.parametrize("substeps,lo,hi,budget", [(4, 0, 4, 1000), (2, 0, 8, 2 ** 20), (2, 0, 8, 2 ** 34), (3, 1, 5, 12345.6),

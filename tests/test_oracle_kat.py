@@ -112,6 +112,13 @@ def test_step_formulas_by_hand(O):
     assert np.isclose(em, (S + (r * S) * dt) + (s * S) * dw, rtol=0, atol=1e-12)
     mil = O.sample_z("BlackScholes", MIL, BS_P, 0.0, dt, S, np.array([[[dw / math.sqrt(dt)]]]))[0, 0]
     assert np.isclose(mil, ((S + (r * S) * dt) + (s * S) * dw) + ((s * (s * S)) * (dw * dw - dt)) / 2, rtol=0, atol=1e-12)
+    # runge_kutta.jl:7-9
+    rk = O.sample_z("BlackScholes", 2, BS_P, 0.0, dt, S, np.array([[[dw / math.sqrt(dt)]]]))[0, 0]
+    sq = math.sqrt(dt)
+    xh = (S + (r * S) * dt) + (s * S) * sq
+    assert np.isclose(rk, ((S + (r * S) * dt) + (s * S) * dw) + ((s * xh - s * S) * (dw * dw - dt)) / (2 * sq), rtol=0, atol=1e-12)
+    # for a diffusion linear in the state the derivative-free scheme equals Milstein up to rounding
+    assert abs(rk - mil) < 1e-3 and abs(rk - mil) > 0
     rr, k, th, sg, rho = HESTON_P
     S, V, d1, d2 = 100.0, 0.4, 0.011, -0.02
     sd = math.sqrt(dt)
