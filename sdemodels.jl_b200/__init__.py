@@ -10,8 +10,8 @@ from ._lib import DomainError, SDEB200Error
 from .distributed import comm_info, init as init_distributed, shard_range
 from .models import (AbstractSDE, REGISTRY, diffusion, dim, drift, fieldnames, registry_model, sde_model,
                      variables)
-from .multilevel import (MultilevelEstimate, MultilevelScheme, cost, ml_estimate, multilevel_sample_level,
-                         multilevel_simulate_level, npaths, schemes)
+from .multilevel import (AdaptiveMLMC, MultilevelEstimate, MultilevelScheme, cost, ml_estimate, mlmc_adaptive,
+                         multilevel_sample_level, multilevel_simulate_level, npaths, schemes)
 from .schemes import EulerMaruyama, Milstein, RungeKutta, subdivide
 from .simulation import (Call, Component, Estimate, Moments, Put, estimate, sample, sample_, simulate, simulate_,
                          wiener_)

@@ -180,3 +180,79 @@ def ml_estimate(model, s, payoff, t0, x0, nsteps, n, *, seed=0, precision="f64",
     var = np.maximum(res[:, 1] / good - m * m, 0.0) * good / np.maximum(good - 1, 1)
     return MultilevelEstimate(float(m.sum()), float(np.sqrt((var / good).sum())), m, var, res[:, 2] / good,
                               ntot.astype(np.int64), bad.astype(np.int64), res[:, :6].copy())
+
+
+@dataclass
+class AdaptiveMLMC:
+    mean: float
+    stderr: float            # sqrt(sum_l V_l / N_l)
+    bias_estimate: float     # |E[Y_L]| / (substeps^alpha - 1), alpha = 1 (weak order of the schemes on the path)
+    levels: range
+    n: np.ndarray            # paths used per level
+    level_mean: np.ndarray
+    level_var: np.ndarray
+    cost: np.ndarray         # fine + coarse steps per path, per level
+    iterations: int
+
+
+def mlmc_adaptive(model, scheme, substeps, payoff, t0, x0, nsteps, eps, *, lmin=2, lmax=10, n0=1 << 14, seed=0,
+                  precision="f64", math="fast", stream=0, alpha=1.0):
+    """Giles' adaptive multilevel estimator on top of the per-level exact sums (the reference
+    stops at the raw level samples, multilevel.jl:52-63).  Levels 0..L with base `scheme`; N_l is raised to
+    ceil(2 eps^-2 sqrt(V_l / C_l) sum_k sqrt(V_k C_k)); a level is added while the extrapolated bias
+    |E[Y_L]| / (substeps^alpha - 1) exceeds eps / sqrt(2).  Additional paths of a level CONTINUE its path
+    numbering (path_offset = paths already done), so the final sums equal those of one run with the final N_l."""
+    from . import simulation as sim
+    L_ = _lib.lib()
+    v0, _ = sim._x0(model, x0)
+    p = sim._params(model)
+    pay = sim._payoff(payoff)
+    sums = np.zeros((lmax + 1, 2))
+    done = np.zeros(lmax + 1, dtype=np.int64)
+
+    def run(level, n_add):
+        if n_add <= 0:
+            return
+        if level == 0:
+            e = sim.estimate(model, scheme, payoff, t0, x0, nsteps, int(n_add), seed=seed, precision=precision,
+                             math=math, stream=stream, path_offset=int(done[0]))
+            sums[0] += e.sums[0]
+        else:
+            coarse = subdivide(scheme, substeps ** (level - 1))
+            fine = subdivide(scheme, substeps ** level)
+            o = sim._opts(coarse, t0, seed, precision, math, stream + level, int(done[level]))
+            out = np.zeros(8)
+            _lib.check(L_.sdeb200_mlmc_estimate_level(model._handle, C.byref(o), p.ctypes.data_as(_PD),
+                                                      v0.ctypes.data_as(_PD), fine.dt, substeps,
+                                                      nsteps * substeps ** (level - 1), int(n_add), C.byref(pay),
+                                                      out.ctypes.data_as(_PD)))
+            sums[level] += out[:2]
+        done[level] += n_add
+
+    L = lmin
+    for l in range(L + 1):
+        run(l, n0)
+    it = 0
+    while True:
+        it += 1
+        n = done[:L + 1].astype(np.float64)
+        m = sums[:L + 1, 0] / n
+        var = np.maximum(sums[:L + 1, 1] / n - m * m, 1e-300)
+        cost = np.array([nsteps * substeps ** l * (1.0 + (1.0 / substeps if l else 0.0)) for l in range(L + 1)])
+        want = np.ceil(2.0 / eps ** 2 * np.sqrt(var / cost) * np.sum(np.sqrt(var * cost))).astype(np.int64)
+        extra = np.maximum(want - done[:L + 1], 0)
+        if np.any(extra > 0.01 * done[:L + 1]):
+            for l in range(L + 1):
+                run(l, int(extra[l]))
+            continue
+        bias = abs(m[L]) / (substeps ** alpha - 1.0)
+        if bias > eps / np.sqrt(2.0) and L < lmax:
+            L += 1
+            run(L, n0)
+            continue
+        break
+    n = done[:L + 1].astype(np.float64)
+    m = sums[:L + 1, 0] / n
+    var = np.maximum(sums[:L + 1, 1] / n - m * m, 0.0)
+    return AdaptiveMLMC(float(m.sum()), float(np.sqrt((var / n).sum())), float(abs(m[L]) / (substeps ** alpha - 1.0)),
+                        range(0, L + 1), done[:L + 1].copy(), m, var, cost, it)

@@ -361,3 +361,21 @@ def test_no_out_of_bounds_writes(gpu, precision, npaths, nsteps):
         v, f = guarded((npaths, D) if D > 1 else (npaths,))
         S.estimate(m, sch, S.Moments(), 0.0, x0, nsteps, npaths, seed=1, precision=precision, terminal=v)
         assert intact(f) and bool(torch.isfinite(v).all())
+
+
+def test_adaptive_mlmc_driver(gpu):
+    """The caller one level above the hot path: Giles' adaptive allocation on the per-level sums.
+    Heston call, eps = 0.05: the estimate lands within 3 eps of the semi-analytic price, the finer levels get
+    geometrically fewer paths, and extending a level reproduces the sums of a single run with the final counts."""
+    import math
+    S = gpu
+    m = S.Heston(*HESTON_P)
+    pay = S.Call(100.0, math.exp(-0.01))
+    r = S.mlmc_adaptive(m, S.EulerMaruyama(1 / 16), 2, pay, 0.0, [100.0, 0.4], 16, 0.05, seed=3)
+    assert abs(r.mean - 22.3374853590066) <= 3 * 0.05
+    assert r.stderr <= 0.05 and r.bias_estimate <= 0.05
+    assert np.all(np.diff(r.n[1:]) <= 0) and r.n[0] > r.n[-1]
+    # the same per-level counts in one shot give the same exact sums
+    ml = S.MultilevelScheme(S.EulerMaruyama(1 / 16), 2, r.levels)
+    one = S.ml_estimate(m, ml, pay, 0.0, [100.0, 0.4], 16, list(r.n), seed=3)
+    assert np.allclose(one.level_mean, r.level_mean, rtol=1e-12, atol=1e-12)
