@@ -153,6 +153,9 @@ def simulate_(x, model, scheme, t0, x0, w=None, *, seed=0, precision=None, math=
     L = _lib.lib()
     v0, scalar = _x0(model, x0)
     is_torch = hasattr(x, "data_ptr")
+    for arr in (x, w):
+        if arr is not None and not (arr.is_contiguous() if hasattr(arr, "is_contiguous") else arr.flags.c_contiguous):
+            raise ValueError("simulate_ works in place: x and w must be C-contiguous")
     if precision is None:
         precision = "f32" if str(x.dtype).endswith("float32") else "f64"
     o = _opts(scheme, t0, seed, precision, math, stream, path_offset)
