@@ -55,10 +55,10 @@ XCOEF(Heston, TAGGED(heston))
 
 #define XWIENER(DIM, TAG) XWIENER2(DIM, TAG)
 #define XWIENER2(DIM, TAG)                                                                                  \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_f64(const __grid_constant__ sde_args a) { \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_f64(const __grid_constant__ sde_args a) { \
     sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, double, 0>(a);                                         \
   }                                                                                                          \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_f32(const __grid_constant__ sde_args a) { \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_f32(const __grid_constant__ sde_args a) { \
     sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, float, 0>(a);                                          \
   }
 XWIENER(1, TAGGED(wiener1))

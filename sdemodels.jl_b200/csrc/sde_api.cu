@@ -408,15 +408,32 @@ static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o
 // sample / mlmc kernels walk over chunks grid-stride: cap the grid so each CTA stages its tables once for many chunks
 static int64_t capped(int64_t nchunks) { return std::min<int64_t>(nchunks, 148 * 64); }
 
-static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t st) {
+static inline size_t esize(int precision);
+static inline int64_t cdiv(int64_t a, int64_t b);
+static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t st, size_t smem = 0) {
   if (!k) return fail(SDEB200_E_UNSUPPORTED, "kernel not available for this model / scheme");
   if (grid <= 0) return 0;
   if (grid > 2147483647LL) return fail(SDEB200_E_ARG, "too many paths for one launch");
+  if (smem > 0) {  // static + dynamic shared memory above 48 KB needs an opt-in, once per kernel
+    static std::vector<const void *> opted;
+    if (std::find(opted.begin(), opted.end(), k) == opted.end()) {
+      CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      opted.push_back(k);
+    }
+  }
   void *args[1] = {(void *)a};
-  CU(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(SDE_BLOCK), args, 0, st));
+  CU(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(SDE_BLOCK), args, smem, st));
   g.launches++;
   return 0;
 }
+
+// reference-layout trajectory kernels (simulate_ref_body): a warp stages 64 paths x TS rows; see sde_device.cuh
+static const int SIMREF_PW = SDE_SIMREF_PW;
+static size_t simref_smem(int D, int precision) {
+  const int ts = (precision == SDEB200_F64 ? 16 : 32) / D, row = ts * D, lds = row | 1;
+  return (size_t)(SDE_BLOCK / 32) * 32 * SIMREF_PW * lds * esize(precision);
+}
+static int64_t simref_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SIMREF_PW); }
 
 static bool is_device_ptr(const void *p) {
   cudaPointerAttributes at;
@@ -602,14 +619,14 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
     if (dev) {
       a.npaths = npaths;
       a.out = out;
-      if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+      if ((rc = launch(k, simref_grid(npaths), &a, st, simref_smem(m->D, o->precision)))) return rc;
     } else {
       rc = run_slabs(npaths, bpp, out, [&](int64_t s0, int64_t n, void *d, cudaStream_t s) {
         sde_args b = a;
         b.npaths = n;
         b.path0 = o->path_offset + s0;
         b.out = d;
-        return launch(k, cdiv(n, SDE_BLOCK), &b, s);
+        return launch(k, simref_grid(n), &b, s, simref_smem(m->D, o->precision));
       });
       if (rc) return rc;
     }
@@ -719,7 +736,7 @@ static int wiener_device(const sdeb200_opts *o, int dim, int64_t nrows, int64_t 
   a.nsteps = nrows - 1;
   a.npaths = npaths;
   a.out = dev;
-  return launch(k, cdiv(npaths, SDE_BLOCK), &a, st);
+  return launch(k, simref_grid(npaths), &a, st, simref_smem(dim, o->precision));
 }
 
 extern "C" int sdeb200_wiener(const sdeb200_opts *o, int dim, int64_t nrows, int64_t npaths, void *w) {

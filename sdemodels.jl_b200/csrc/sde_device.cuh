@@ -702,24 +702,46 @@ SDE_D void simulate_soa_body(const sde_args &a) {
 // Cooperative copy between a warp's shared-memory tile [32 paths][LD] and global memory where path r's row
 // segment starts at g + r*gstride: element e = k*32 + lane of the flattened (32 x ROW) tile, fully unrolled, so a
 // warp instruction moves whole 128-byte row segments and all of a lane's loads are in flight together.
-template <typename T, int ROW, int LD>
+template <typename T, int ROW, int LD, int NROWS = 32>
 SDE_D void tile_load(T *tile, const T *g, int64_t gstride, int nlive, int ncols, int lane) {
-  T v[ROW];
+  constexpr int NK = ROW * (NROWS / 32);
+  T v[NK];
+  if ((32 % ROW) == 0 && nlive == NROWS && ncols == ROW) {  // full tile: no predicates, pointer bumps only
+    constexpr int RPI = (32 % ROW) == 0 ? 32 / ROW : 1;     // rows covered by one warp instruction
+    const int rr = lane / ROW, cc = lane - rr * ROW;
+    const T *gp = g + rr * gstride + cc;
 #pragma unroll
-  for (int k = 0; k < ROW; k++) {
+    for (int k = 0; k < NK; k++) { v[k] = __ldcs(gp); gp += RPI * gstride; }
+    T *tp = tile + rr * LD + cc;
+#pragma unroll
+    for (int k = 0; k < NK; k++) tp[k * RPI * LD] = v[k];
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
     const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW;
     v[k] = (r < nlive && c < ncols) ? __ldcs(g + r * gstride + c) : (T)0;
   }
 #pragma unroll
-  for (int k = 0; k < ROW; k++) {
+  for (int k = 0; k < NK; k++) {
     const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW;
     tile[r * LD + c] = v[k];
   }
 }
-template <typename T, int ROW, int LD>
+template <typename T, int ROW, int LD, int NROWS = 32>
 SDE_D void tile_store(const T *tile, T *g, int64_t gstride, int nlive, int ncols, int lane) {
+  constexpr int NK = ROW * (NROWS / 32);
+  if ((32 % ROW) == 0 && nlive == NROWS && ncols == ROW) {
+    constexpr int RPI = (32 % ROW) == 0 ? 32 / ROW : 1;
+    const int rr = lane / ROW, cc = lane - rr * ROW;
+    const T *tp = tile + rr * LD + cc;
+    T *gp = g + rr * gstride + cc;
 #pragma unroll
-  for (int k = 0; k < ROW; k++) {
+    for (int k = 0; k < NK; k++) { __stcs(gp, tp[k * RPI * LD]); gp += RPI * gstride; }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
     const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW;
     if (r < nlive && c < ncols) __stcs(g + r * gstride + c, tile[r * LD + c]);
   }
@@ -733,12 +755,13 @@ SDE_D void tile_store(const T *tile, T *g, int64_t gstride, int nlive, int ncols
 template <class Model, typename T, int SCHEME>
 SDE_D void simulate_ref_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
+  constexpr int PW = SDE_SIMREF_PW;           // paths per lane: a warp owns 32 * PW consecutive paths
   constexpr int TS = (sizeof(T) == 8 ? 16 : 32) / D;  // time rows per tile: 128-byte row segments per path
   constexpr int ROW = TS * D;                 // elements per path per tile
   constexpr int LDS = ROW | 1;                // odd stride: conflict-free column writes
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
-  __shared__ T s_tile[SDE_BLOCK / 32][32 * LDS];
+  extern __shared__ __align__(16) unsigned char s_dyn[];   // [warps][32 * PW rows][LDS]: sde_simref_smem_bytes()
   load_tables<T>(s_tab, a.dt);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
@@ -750,43 +773,49 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   Model::prepare(prm, dt, cst.c);
 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t wbase = ((int64_t)blockIdx.x * blockDim.x + (wid << 5));  // first path of this warp
+  const int64_t wbase = ((int64_t)blockIdx.x * blockDim.x + (wid << 5)) * PW;  // first path of this warp
   if (wbase >= a.npaths) return;
-  const int64_t k = wbase + lane;
-  const int nrow_live = (int)((a.npaths - wbase) < 32 ? (a.npaths - wbase) : 32);
-  T *tile = s_tile[wid];
+  const int nrow_live = (int)((a.npaths - wbase) < 32 * PW ? (a.npaths - wbase) : 32 * PW);
+  T *tile = (T *)s_dyn + wid * (32 * PW * LDS);
   T *out = (T *)a.out;
   const int64_t nrows = a.nsteps + 1;
-  T x[SDE_MAXD];
+  T x[PW][SDE_MAXD];
 #pragma unroll
-  for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
+  for (int p = 0; p < PW; p++)
+#pragma unroll
+    for (int d = 0; d < SDE_MAXD; d++) x[p][d] = d < D ? (T)a.x0[d] : (T)0;
 
   int fill = 0;          // time rows currently staged
   int64_t row0 = 0;      // first staged time row
   auto stage = [&]() {
 #pragma unroll
-    for (int d = 0; d < D; d++) tile[lane * LDS + fill * D + d] = x[d];
+    for (int p = 0; p < PW; p++)
+#pragma unroll
+      for (int d = 0; d < D; d++) tile[(lane + 32 * p) * LDS + fill * D + d] = x[p][d];
     fill++;
   };
   auto flush = [&]() {
     __syncwarp();
-    tile_store<T, ROW, LDS>(tile, out + (wbase * nrows + row0) * D, nrows * D, nrow_live, fill * D, lane);
+    tile_store<T, ROW, LDS, 32 * PW>(tile, out + (wbase * nrows + row0) * D, nrows * D, nrow_live, fill * D, lane);
     __syncwarp();
     row0 += fill;
     fill = 0;
   };
   stage();
-  const uint64_t gpath = (uint64_t)(a.path0 + k);
+  const uint64_t gpath = (uint64_t)(a.path0 + wbase + lane);
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
-    T dw[B::NZ];
-    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dt, dw);
+    T dw[PW][B::NZ];
+#pragma unroll
+    for (int p = 0; p < PW; p++)
+      gen_batch<T, M>(gpath + (uint64_t)(32 * p), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dt, dw[p]);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;
       if (i < a.nsteps) {
         const T t = t0 + (T)i * dt;
-        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x);
+#pragma unroll
+        for (int p = 0; p < PW; p++) Model::template step<SCHEME>(cst.c, t, dt, dw[p] + u * (M > 0 ? M : 0), x[p]);
         if (fill == TS) flush();
         stage();
       }
@@ -892,7 +921,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
       const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, T, SCH>(a); }                            \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }
