@@ -47,6 +47,8 @@ extern "C" {
 #define SDEB200_EULER_MARUYAMA 0
 #define SDEB200_MILSTEIN 1
 #define SDEB200_RUNGE_KUTTA 2 /* src/schemes/runge_kutta.jl:4-11 — derivative-free Milstein, M == 1 like Milstein */
+#define SDEB200_EXACT 3       /* closed-form one-step samplers (src/simulation.jl:50-57,78-89): built-in BlackScholes
+                                 (black_scholes.jl:3-13) and OrnsteinUhlenbeck (ornstein_uhlenbeck.jl:3-13) only */
 /* arithmetic type of state and noise */
 #define SDEB200_F64 0
 #define SDEB200_F32 1
@@ -67,7 +69,7 @@ typedef struct sdeb200_model sdeb200_model;
 
 /* Run options shared by all drivers.  Zero-initialise, then set what differs. */
 typedef struct {
-  int32_t scheme;      /* SDEB200_EULER_MARUYAMA | SDEB200_MILSTEIN | SDEB200_RUNGE_KUTTA  (the scheme's type) */
+  int32_t scheme;      /* SDEB200_EULER_MARUYAMA | SDEB200_MILSTEIN | SDEB200_RUNGE_KUTTA | SDEB200_EXACT */
   int32_t precision;   /* SDEB200_F64 | SDEB200_F32 */
   int32_t math;        /* SDEB200_MATH_FAST | SDEB200_MATH_STRICT */
   int32_t reserved;
@@ -104,7 +106,8 @@ int sdeb200_measure_peak(int precision, double *tflops, double *ms); /* FMA-chai
  * explicit parameter order, the macro's trailing arguments (codegen.jl:116-118). */
 int sdeb200_model_create(const char *name, const char *eqs_utf8, const char *const *param_names, int nparams,
                          sdeb200_model **out);
-/* "BlackScholes" (black_scholes.jl:1) or "Heston" (models.jl:44-48): ahead-of-time compiled functors. */
+/* "BlackScholes" (black_scholes.jl:1), "Heston" (models.jl:44-48) or "OrnsteinUhlenbeck" (ornstein_uhlenbeck.jl:1):
+ * ahead-of-time compiled functors. */
 int sdeb200_model_builtin(const char *name, sdeb200_model **out);
 void sdeb200_model_free(sdeb200_model *m);
 /* dim(model) == (D, M) (models.jl:3-5); kind: 0 AbstractSDE, 1 StateIndependentDiffusion, 2 JumpSDE (rejected) */

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libsde_oracle.so")
 
-EULER_MARUYAMA, MILSTEIN, RUNGE_KUTTA = 0, 1, 2
+EULER_MARUYAMA, MILSTEIN, RUNGE_KUTTA, EXACT = 0, 1, 2, 3
 
 
 def build(force=False):

@@ -40,16 +40,28 @@
  * ------------------------------------------------------------------------------------------ */
 typedef void (*coef_fn)(const double *p, double t, const double *x, double *out);
 
+/* Exact one-step sampler given the standard normal the distribution's rand() would draw
+ * (Distributions 0.21: rand(LogNormal(μ,σ)) = exp(randn()*σ + μ), rand(Normal(μ,σ)) = μ + σ*randn()). */
+typedef void (*exact_fn)(const double *p, double dt, const double *x0, double z, double *x1);
+
 typedef struct {
   const char *name;
   int D, M, nparams;
   coef_fn drift, diffusion, ddiffusion;
+  exact_fn exact;
 } model_def;
 
 /* BlackScholes: dS = r*S*dt + σ*S*dW            params (r, σ)   black_scholes.jl:1 */
 static void bs_drift(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[0] * x[0]; }
 static void bs_diff(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[1] * x[0]; }
 static void bs_ddiff(const double *p, double t, const double *x, double *o) { (void)t; (void)x; o[0] = p[1]; }
+
+/* sample(model::BlackScholes, scheme::Exact, t0, x0): black_scholes.jl:3-13 */
+static void bs_exact(const double *p, double dt, const double *x0, double z, double *x1) {
+  double mu = log(x0[0]) + (p[0] - 0.5 * (p[1] * p[1])) * dt;
+  double d = sqrt(dt) * p[1];
+  x1[0] = exp(z * d + mu);
+}
 
 /* Heston: models.jl:44-48, params (r, κ, θ, σ, ρ); generated form README.md:42-59 / SURVEY §3.5 */
 static void heston_drift(const double *p, double t, const double *x, double *o) {
@@ -116,6 +128,13 @@ static void cir_ddiff(const double *p, double t, const double *x, double *o) { (
 static void ou_drift(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[0] * (p[1] - x[0]); }
 static void ou_diff(const double *p, double t, const double *x, double *o) { (void)t; (void)x; o[0] = p[2]; }
 
+/* sample(model::OrnsteinUhlenbeck, scheme::Exact, t0, x0): ornstein_uhlenbeck.jl:3-13 */
+static void ou_exact(const double *p, double dt, const double *x0, double z, double *x1) {
+  double m = x0[0] * exp(-p[0] * dt) + p[1] * (1.0 - exp(-p[0] * dt));
+  double d = sqrt(1.0 - exp(-2.0 * p[0] * dt)) * p[2] / sqrt(2.0 * p[0]);
+  x1[0] = m + d * z;
+}
+
 /* FitzHughNagumo (models.jl:39-42), params (ɛ, s, γ, β, σ1, σ2), D=2, M=2 */
 static void fhn_drift(const double *p, double t, const double *x, double *o) {
   (void)t;
@@ -147,19 +166,19 @@ enum {
 };
 
 static const model_def MODELS[M_COUNT] = {
-  {"BlackScholes", 1, 1, 2, bs_drift, bs_diff, bs_ddiff},
-  {"Heston", 2, 2, 5, heston_drift, heston_diff, 0},
-  {"Deterministic", 1, 0, 0, det_drift, zero_diff, 0},
-  {"Wiener", 1, 1, 0, wien_drift, wien_diff, wien_ddiff},
-  {"TimeDependent", 1, 1, 2, td_drift, td_diff, td_ddiff},
-  {"TestModel", 3, 4, 6, tm_drift, tm_diff, 0},
-  {"SpecialCaseModel1", 1, 2, 0, wien_drift, sc1_diff, 0},
-  {"SpecialCaseModel2", 2, 1, 0, zero_drift3, sc2_diff, sc2_ddiff},
-  {"SpecialCaseModel3", 3, 2, 0, zero_drift3, sc3_diff, 0},
-  {"CoxIngersollRoss", 1, 1, 3, cir_drift, cir_diff, cir_ddiff},
-  {"OrnsteinUhlenbeck", 1, 1, 3, ou_drift, ou_diff, wien_ddiff},
-  {"FitzHughNagumo", 2, 2, 6, fhn_drift, fhn_diff, 0},
-  {"Lorenz", 3, 3, 6, lor_drift, lor_diff, 0},
+  {"BlackScholes", 1, 1, 2, bs_drift, bs_diff, bs_ddiff, bs_exact},
+  {"Heston", 2, 2, 5, heston_drift, heston_diff, 0, 0},
+  {"Deterministic", 1, 0, 0, det_drift, zero_diff, 0, 0},
+  {"Wiener", 1, 1, 0, wien_drift, wien_diff, wien_ddiff, 0},
+  {"TimeDependent", 1, 1, 2, td_drift, td_diff, td_ddiff, 0},
+  {"TestModel", 3, 4, 6, tm_drift, tm_diff, 0, 0},
+  {"SpecialCaseModel1", 1, 2, 0, wien_drift, sc1_diff, 0, 0},
+  {"SpecialCaseModel2", 2, 1, 0, zero_drift3, sc2_diff, sc2_ddiff, 0},
+  {"SpecialCaseModel3", 3, 2, 0, zero_drift3, sc3_diff, 0, 0},
+  {"CoxIngersollRoss", 1, 1, 3, cir_drift, cir_diff, cir_ddiff, 0},
+  {"OrnsteinUhlenbeck", 1, 1, 3, ou_drift, ou_diff, wien_ddiff, ou_exact},
+  {"FitzHughNagumo", 2, 2, 6, fhn_drift, fhn_diff, 0, 0},
+  {"Lorenz", 3, 3, 6, lor_drift, lor_diff, 0, 0},
 };
 
 int oracle_model_count(void) { return M_COUNT; }
@@ -198,6 +217,11 @@ int oracle_diffusion(int id, const double *p, double t, const double *x, double 
  * ------------------------------------------------------------------------------------------ */
 static int step(const model_def *m, int scheme, const double *p, double dt, double t, const double *x0,
                 const double *dw, double *x1) {
+  if (scheme == 3) { /* Exact: `dw` carries the plain standard normal (src/simulation.jl:50-57 calls sample(model, Exact, t, x)) */
+    if (!m->exact) return -2;
+    m->exact(p, dt, x0, dw[0], x1);
+    return 0;
+  }
   double mu[MAXD], sig[MAXD * MAXM];
   memset(sig, 0, sizeof sig);
   m->drift(p, t, x0, mu);
@@ -273,7 +297,7 @@ int oracle_sample_z(int id, int scheme, const double *p, double t0, double dt, c
     for (int i = 0; i < m->D; i++) x[i] = x0[i];
     for (int64_t i = 1; i <= nsteps; i++) {
       double ti = t0 + (double)(i - 1) * dt;
-      for (int j = 0; j < M; j++) dw[j] = sdt * (m->M > 0 ? z[(k * nsteps + (i - 1)) * M + j] : 0.0);
+      for (int j = 0; j < M; j++) dw[j] = (scheme == 3 ? 1.0 : sdt) * (m->M > 0 ? z[(k * nsteps + (i - 1)) * M + j] : 0.0);
       rc |= step(m, scheme, p, dt, ti, x, dw, xn);
       for (int d = 0; d < m->D; d++) x[d] = xn[d];
     }
@@ -309,7 +333,7 @@ int oracle_simulate_z(int id, int scheme, const double *p, double t0, double dt,
     for (int d = 0; d < D; d++) xk[d] = x0[d];
     for (int64_t i = 2; i <= nrows; i++) {
       double t = t0 + (double)(i - 2) * dt, dw[MAXM];
-      for (int j = 0; j < M; j++) dw[j] = sdt * (m->M > 0 ? z[(k * (nrows - 1) + (i - 2)) * M + j] : 0.0);
+      for (int j = 0; j < M; j++) dw[j] = (scheme == 3 ? 1.0 : sdt) * (m->M > 0 ? z[(k * (nrows - 1) + (i - 2)) * M + j] : 0.0);
       rc |= step(m, scheme, p, dt, t, xk + (i - 2) * D, dw, xk + (i - 1) * D);
     }
   }

@@ -12,7 +12,7 @@ from .models import (AbstractSDE, REGISTRY, diffusion, dim, drift, fieldnames, r
                      variables)
 from .multilevel import (AdaptiveMLMC, MultilevelEstimate, MultilevelScheme, cost, ml_estimate, mlmc_adaptive,
                          multilevel_sample_level, multilevel_simulate_level, npaths, schemes)
-from .schemes import EulerMaruyama, Milstein, RungeKutta, subdivide
+from .schemes import EulerMaruyama, Exact, Milstein, RungeKutta, subdivide
 from .simulation import (Call, Component, Estimate, Moments, Put, estimate, sample, sample_, simulate, simulate_,
                          wiener_)
 

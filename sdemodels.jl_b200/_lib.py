@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDEB200_LIB") or os.path.join(_HERE, "libsdeb200.so")  # env override: tuning builds only
 
 OK, E_ARG, E_PARSE, E_NVRTC, E_CUDA, E_NCCL, E_DOMAIN, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
-EULER_MARUYAMA, MILSTEIN, RUNGE_KUTTA = 0, 1, 2
+EULER_MARUYAMA, MILSTEIN, RUNGE_KUTTA, EXACT = 0, 1, 2, 3
 F64, F32 = 0, 1
 MATH_FAST, MATH_STRICT = 0, 1
 LAYOUT_REFERENCE, LAYOUT_SOA = 0, 1

@@ -6,6 +6,7 @@
 
 using sdeb200::BlackScholes;
 using sdeb200::Heston;
+using sdeb200::OrnsteinUhlenbeck;
 
 namespace sdeb200 {
 // wiener!(w, Δt) (src/simulation.jl:22-35) is the in-place running sum w[i] = w[i-1] + sqrt(Δt)*z: the
@@ -50,6 +51,22 @@ XSCHEME(BlackScholes, TAGGED(bs), 0, em)
 XSCHEME(BlackScholes, TAGGED(bs), 1, mil)
 XSCHEME(BlackScholes, TAGGED(bs), 2, rk)
 XCOEF(BlackScholes, TAGGED(bs))
+#define XEXACT(MODEL, TAG) XEXACT2(MODEL, TAG)
+#define XEXACT2(MODEL, TAG) SDE_KERNELS_EXACT(MODEL, TAG, double, f64) SDE_KERNELS_EXACT(MODEL, TAG, float, f32)
+#define XEXACTFILL(T, TAG) XEXACTFILL2(T, TAG)
+#define XEXACTFILL2(T, TAG)                                              \
+  T.sample[3][0] = (const void *)sdek_##TAG##_sample_exact_f64;          \
+  T.sample[3][1] = (const void *)sdek_##TAG##_sample_exact_f32;          \
+  T.simsoa[3][0] = (const void *)sdek_##TAG##_simsoa_exact_f64;          \
+  T.simsoa[3][1] = (const void *)sdek_##TAG##_simsoa_exact_f32;          \
+  T.simref[3][0] = (const void *)sdek_##TAG##_simref_exact_f64;          \
+  T.simref[3][1] = (const void *)sdek_##TAG##_simref_exact_f32;
+XEXACT(BlackScholes, TAGGED(bs))
+XSCHEME(OrnsteinUhlenbeck, TAGGED(ou), 0, em)
+XSCHEME(OrnsteinUhlenbeck, TAGGED(ou), 1, mil)
+XSCHEME(OrnsteinUhlenbeck, TAGGED(ou), 2, rk)
+XEXACT(OrnsteinUhlenbeck, TAGGED(ou))
+XCOEF(OrnsteinUhlenbeck, TAGGED(ou))
 XSCHEME(Heston, TAGGED(heston), 0, em)
 XCOEF(Heston, TAGGED(heston))
 
@@ -66,7 +83,7 @@ XWIENER(2, TAGGED(wiener2))
 XWIENER(3, TAGGED(wiener3))
 XWIENER(4, TAGGED(wiener4))
 
-// model: 0 = BlackScholes, 1 = Heston
+// model: 0 = BlackScholes, 1 = Heston, 2 = OrnsteinUhlenbeck
 extern "C" int SDE_AOT_TABLE(int model, sde_ktable *t) {
   sde_ktable z = {};
   *t = z;
@@ -74,7 +91,16 @@ extern "C" int SDE_AOT_TABLE(int model, sde_ktable *t) {
     XFILL((*t), TAGGED(bs), 0, em)
     XFILL((*t), TAGGED(bs), 1, mil)
     XFILL((*t), TAGGED(bs), 2, rk)
+    XEXACTFILL((*t), TAGGED(bs))
     XCOEFFILL((*t), TAGGED(bs))
+    return 0;
+  }
+  if (model == 2) {
+    XFILL((*t), TAGGED(ou), 0, em)
+    XFILL((*t), TAGGED(ou), 1, mil)
+    XFILL((*t), TAGGED(ou), 2, rk)
+    XEXACTFILL((*t), TAGGED(ou))
+    XCOEFFILL((*t), TAGGED(ou))
     return 0;
   }
   if (model == 1) {

@@ -262,6 +262,7 @@ extern "C" int sdeb200_measure_peak(int precision, double *tflops, double *ms_ou
 struct sdeb200_model {
   std::string name;
   int D = 0, M = 0, kind = 0, builtin = -1;
+  bool has_exact = false;
   std::vector<std::string> params, vars, drift, diffusion;  // diffusion row-major D x max(M,1)
   std::string source;                                       // generated functor (empty for built-ins)
   sde_ktable kt[2];                                         // [math]
@@ -282,10 +283,15 @@ extern "C" int sdeb200_model_builtin(const char *name, sdeb200_model **out) {
     m->params = {"r", "κ", "θ", "σ", "ρ"}; m->vars = {"S", "V"};
     m->drift = {"r * S", "κ * (θ - V)"};
     m->diffusion = {"sqrt(V) * S", "0", "σ * sqrt(V) * ρ", "σ * sqrt(V) * sqrt(1 - ρ ^ 2)"};
+  } else if (m->name == "OrnsteinUhlenbeck") {
+    m->builtin = 2; m->D = 1; m->M = 1; m->kind = 1;
+    m->params = {"θ", "μ", "σ"}; m->vars = {"x"};
+    m->drift = {"θ * (μ - x)"}; m->diffusion = {"σ"};
   } else {
     delete m;
-    return fail(SDEB200_E_ARG, "no built-in model named '%s' (BlackScholes, Heston)", name);
+    return fail(SDEB200_E_ARG, "no built-in model named '%s' (BlackScholes, Heston, OrnsteinUhlenbeck)", name);
   }
+  m->has_exact = m->builtin == 0 || m->builtin == 2;
   sde_aot_table_fast(m->builtin, &m->kt[0]);
   sde_aot_table_strict(m->builtin, &m->kt[1]);
   for (int a = 0; a < 2; a++)
@@ -368,9 +374,13 @@ extern "C" int sdeb200_model_compile(sdeb200_model *m, int precision, int math) 
 static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0) {
   if (!m || !o || !x0) return fail(SDEB200_E_ARG, "null argument");
   if (!params && !m->params.empty()) return fail(SDEB200_E_ARG, "params is NULL but the model has %zu", m->params.size());
-  if (o->scheme < SDEB200_EULER_MARUYAMA || o->scheme > SDEB200_RUNGE_KUTTA)
+  if (o->scheme < SDEB200_EULER_MARUYAMA || o->scheme > SDEB200_EXACT)
     return fail(SDEB200_E_ARG, "unknown scheme %d", o->scheme);
-  if (o->scheme != SDEB200_EULER_MARUYAMA && m->M != 1)
+  if (o->scheme == SDEB200_EXACT && !m->has_exact)
+    return fail(SDEB200_E_UNSUPPORTED, "the reference defines an Exact sampler for BlackScholes, OrnsteinUhlenbeck, "
+                "CoxIngersollRoss and Merton only; the B200 path implements the first two (built-in models), not '%s'",
+                m->name.c_str());
+  if (o->scheme != SDEB200_EULER_MARUYAMA && o->scheme != SDEB200_EXACT && m->M != 1)
     return fail(SDEB200_E_UNSUPPORTED,
                 "%s is defined for models with one Wiener process only (M == 1), as in the reference "
                 "(src/schemes/milstein.jl:4, runge_kutta.jl:4); '%s' has M == %d",
@@ -381,14 +391,16 @@ static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const dou
 }
 
 // a->dt and the dt-scaled constants of the FP64 normal transform (sde_device.cuh: make_log_consts)
-static void set_dt(sde_args *a, double dt) {
+static void set_dt(sde_args *a, double dt, int scheme = SDEB200_EULER_MARUYAMA) {
   a->dt = dt;
-  a->lk[0] = SDE_LOG_C1_V * dt;
-  a->lk[1] = SDE_LOG_C2_V * dt;
-  a->lk[2] = SDE_LOG_C3_V * dt;
-  a->lk[3] = SDE_LOG_C4_V * dt;
-  a->lk[4] = -2.0 * dt;
-  a->lk[5] = SDE_TWO_LN2_V * dt;
+  const double v = scheme == SDEB200_EXACT ? 1.0 : dt;  // Exact samplers draw plain N(0,1) (rand(LogNormal / Normal))
+  a->noise_var = v;
+  a->lk[0] = SDE_LOG_C1_V * v;
+  a->lk[1] = SDE_LOG_C2_V * v;
+  a->lk[2] = SDE_LOG_C3_V * v;
+  a->lk[3] = SDE_LOG_C4_V * v;
+  a->lk[4] = -2.0 * v;
+  a->lk[5] = SDE_TWO_LN2_V * v;
 }
 
 static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o, const double *params,
@@ -402,7 +414,7 @@ static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o
   a->seed_hi = (uint32_t)(o->seed >> 32);
   a->stream = o->stream;
   a->path0 = o->path_offset;
-  set_dt(a, o->dt);
+  set_dt(a, o->dt, o->scheme);
 }
 
 // sample / mlmc kernels walk over chunks grid-stride: cap the grid so each CTA stages its tables once for many chunks

@@ -43,7 +43,8 @@ typedef struct {
   uint32_t seed_lo, seed_hi, stream;
   int32_t payoff_kind, payoff_comp;
   double payoff_k, payoff_disc;
-  double lk[6];      /* dt-scaled constants of the FP64 normal transform (make_log_consts) */
+  double lk[6];      /* noise_var-scaled constants of the FP64 normal transform (make_log_consts) */
+  double noise_var;  /* variance of the generated increments: dt for the step schemes, 1 for Exact (plain N(0,1)) */
   /* mlmc only */
   double dt_coarse;
   int64_t substeps;

@@ -410,7 +410,7 @@ SDE_D void sample_body(const sde_args &a) {
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
-  load_tables<T>(s_tab, a.dt);
+  load_tables<T>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
 
@@ -442,7 +442,7 @@ SDE_D void sample_body(const sde_args &a) {
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
       gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, ks,
-                      s_tab, a.lk, dt, dw);
+                      s_tab, a.lk, (T)a.noise_var, dw);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         const T t = t0 + (T)(it * B::U + u) * dt;
@@ -455,7 +455,7 @@ SDE_D void sample_body(const sde_args &a) {
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
       gen_batch<T, M>(gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, ks,
-                      s_tab, a.lk, dt, dw);
+                      s_tab, a.lk, (T)a.noise_var, dw);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         if (u < rem) {
@@ -526,7 +526,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
-  load_tables<T>(s_tab, a.dt);
+  load_tables<T>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
 
@@ -555,7 +555,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   int64_t ncoarse = 0;  // coarse steps completed
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[B::NZ];
-    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dtf, dw);
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t fstep = it * B::U + u;
@@ -639,7 +639,7 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M, VEC = 16 / (int)sizeof(T);
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
-  load_tables<T>(s_tab, a.dt);
+  load_tables<T>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
@@ -685,7 +685,7 @@ SDE_D void simulate_soa_body(const sde_args &a) {
     T dw[VEC][B::NZ];
 #pragma unroll
     for (int v = 0; v < VEC; v++)
-      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dt, dw[v]);
+      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v]);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;
@@ -762,7 +762,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
   extern __shared__ __align__(16) unsigned char s_dyn[];   // [warps][32 * PW rows][LDS]: sde_simref_smem_bytes()
-  load_tables<T>(s_tab, a.dt);
+  load_tables<T>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
@@ -808,7 +808,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
     T dw[PW][B::NZ];
 #pragma unroll
     for (int p = 0; p < PW; p++)
-      gen_batch<T, M>(gpath + (uint64_t)(32 * p), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, dt, dw[p]);
+      gen_batch<T, M>(gpath + (uint64_t)(32 * p), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[p]);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;
@@ -925,6 +925,16 @@ SDE_D void coef_eval_body(const sde_args &a) {
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }
+
+// Exact one-step samplers exist for a few models only and have no Wiener-driven or coupled form
+// (src/simulation.jl:50-57,78-89): terminal and full-trajectory kernels, scheme id 3.
+#define SDE_KERNELS_EXACT(MODEL, TAG, T, PNAME)                                                                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_exact_##PNAME(                    \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, 3, SDE_PPT>(a); }                   \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_exact_##PNAME(                    \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, 3>(a); }                      \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_exact_##PNAME(                 \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, 3>(a); }
 
 #define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \
   SDE_KERNELS(MODEL, TAG, SCH, SNAME, double, f64)  \

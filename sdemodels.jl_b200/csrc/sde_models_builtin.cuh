@@ -20,12 +20,18 @@ SDE_HD double sde_sqrt(double v) { return sqrt(v); }
 SDE_HD float sde_sqrt(float v) { return sqrtf(v); }
 SDE_HD double sde_fma(double a, double b, double c) { return fma(a, b, c); }
 SDE_HD float sde_fma(float a, float b, float c) { return fmaf(a, b, c); }
+SDE_HD double sde_exp(double v) { return exp(v); }
+SDE_HD float sde_exp(float v) { return expf(v); }
+SDE_HD double sde_log(double v) { return log(v); }
+SDE_HD float sde_log(float v) { return logf(v); }
 
 struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
   static constexpr int D = 1, M = 1, NP = 2;
   template <typename T> SDE_HD static void prepare(const T *p, T dt, T *c) {
     c[0] = p[0];
     c[1] = p[1];
+    c[5] = (p[0] - (T)0.5 * (p[1] * p[1])) * dt;  // (r - 0.5σ²)Δt      Exact: black_scholes.jl:5
+    c[6] = sde_sqrt(dt) * p[1];                   // d = sqrt(Δt)σ      Exact: black_scholes.jl:6
 #if !SDE_STRICT
     c[2] = p[0] * dt;                 // r Δt
     c[3] = (T)0.5 * p[1] * p[1];      // σ²/2                                   (Milstein)
@@ -38,6 +44,10 @@ struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
   template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
     (void)t;
     const T S = x[0], w = dw[0];
+    if (SCHEME == 3) {  // rand(LogNormal(log(x0) + (r-σ²/2)Δt, sqrt(Δt)σ)) = exp(randn()*d + μ); dw is a plain N(0,1) here
+      x[0] = sde_exp(w * c[6] + (sde_log(S) + c[5]));
+      return;
+    }
 #if SDE_STRICT
     const T mu = c[0] * S, sg = c[1] * S;
     T y = (S + mu * dt) + sg * w;
@@ -60,6 +70,38 @@ struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
     (void)t;
     mu[0] = p[0] * x[0];
     sig[0] = p[1] * x[0];
+  }
+};
+
+struct OrnsteinUhlenbeck {  // dx = θ*(μ-x)*dt + σ*dW, params (θ, μ, σ)   ornstein_uhlenbeck.jl:1
+  static constexpr int D = 1, M = 1, NP = 3;
+  template <typename T> SDE_HD static void prepare(const T *p, T dt, T *c) {
+    c[0] = p[0];
+    c[1] = p[1];
+    c[2] = p[2];
+    // Exact (ornstein_uhlenbeck.jl:3-8): Normal(x0 e^{-θΔt} + μ(1 - e^{-θΔt}), sqrt(1 - e^{-2θΔt}) σ / sqrt(2θ))
+    c[3] = sde_exp(-p[0] * dt);
+    c[4] = p[1] * ((T)1 - sde_exp(-p[0] * dt));
+    c[5] = sde_sqrt((T)1 - sde_exp((T)-2 * p[0] * dt)) * p[2] / sde_sqrt((T)2 * p[0]);
+  }
+  template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
+    (void)t;
+    const T X = x[0], w = dw[0];
+    if (SCHEME == 3) {  // rand(Normal(m, d)) = m + d*randn(); dw is a plain N(0,1) here
+      x[0] = (X * c[3] + c[4]) + c[5] * w;
+      return;
+    }
+    const T mu = c[0] * (c[1] - X);
+    // σ does not depend on x: the Milstein correction ∂σ*σ*(Δw²-Δt)/2 and the RungeKutta one (σpred-σ)(…) are exactly 0
+    T y = (X + mu * dt) + c[2] * w;
+    if (SCHEME == 1) y = y + (((T)0 * c[2]) * (w * w - dt)) / (T)2;
+    if (SCHEME == 2) y = y + ((c[2] - c[2]) * (w * w - dt)) / ((T)2 * sde_sqrt(dt));
+    x[0] = y;
+  }
+  SDE_HD static void coefficients(const double *p, double t, const double *x, double *mu, double *sig) {
+    (void)t;
+    mu[0] = p[0] * (p[1] - x[0]);
+    sig[0] = p[2];
   }
 };
 

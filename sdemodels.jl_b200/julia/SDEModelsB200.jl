@@ -57,6 +57,7 @@ SDEModels.subdivide(b::B200, n) = B200(subdivide(b.scheme, n), b.seed, b.precisi
 scheme_id(::EulerMaruyama) = Int32(0)
 scheme_id(::Milstein)      = Int32(1)
 scheme_id(::RungeKutta)    = Int32(2)
+scheme_id(::SDEModels.Exact) = Int32(3)   # built-in BlackScholes / OrnsteinUhlenbeck only
 opts(b::B200, t0; dt = b.scheme.Δt, stream = b.stream) =
   Opts(scheme_id(b.scheme), b.precision === Float32 ? 1 : 0, b.strict ? 1 : 0, 0, Float64(t0), Float64(dt),
        b.seed, stream, 0, b.path_offset)
@@ -89,7 +90,7 @@ function handle(::Type{T}) where {T<:AbstractSDE}
   get!(handles, T) do
     h = Ref{Ptr{Cvoid}}(C_NULL)
     nm = string(nameof(T))
-    if T === SDEModels.BlackScholes || T === SDEModels.Heston      # hand-written ahead-of-time functors
+    if T === SDEModels.BlackScholes || T === SDEModels.Heston || T === SDEModels.OrnsteinUhlenbeck   # ahead-of-time functors
       check(ccall((:sdeb200_model_builtin, lib), Cint, (Cstring, Ref{Ptr{Cvoid}}), nm, h))
     else
       names = [string(f) for f in fieldnames(T)]                   # explicit order = the struct's field order

@@ -83,11 +83,12 @@ _cache = {}
 
 
 def registry_model(name, generated=False):
-    """Model types of the reference's registry.  BlackScholes and Heston default to the hand-written
-    ahead-of-time functors; `generated=True` builds them from their equations like any other model."""
+    """Model types of the reference's registry.  BlackScholes, Heston and OrnsteinUhlenbeck default to the
+    hand-written ahead-of-time functors (the first and the last also carry their Exact samplers);
+    `generated=True` builds them from their equations like any other model."""
     key = (name, generated)
     if key not in _cache:
-        if name in ("BlackScholes", "Heston") and not generated:
+        if name in ("BlackScholes", "Heston", "OrnsteinUhlenbeck") and not generated:
             _cache[key] = _builtin(name)
         else:
             _cache[key] = sde_model(name, REGISTRY[name])

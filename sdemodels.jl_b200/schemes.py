@@ -33,6 +33,12 @@ class RungeKutta(_UnconditionalScheme):
     _id = _lib.RUNGE_KUTTA
 
 
+class Exact(_UnconditionalScheme):
+    """Closed-form one-step sampling (src/simulation.jl:50-57,78-89): BlackScholes (black_scholes.jl:3-13) and
+    OrnsteinUhlenbeck (ornstein_uhlenbeck.jl:3-13) — the built-in model types."""
+    _id = _lib.EXACT
+
+
 def subdivide(scheme, nsubsteps):
     """subdivide(scheme::T, n) = T(scheme.Δt / n)   (schemes.jl:53-54)"""
     return type(scheme)(scheme.dt / nsubsteps)

@@ -34,7 +34,7 @@ def test_header_constants_match_python(S):
     assert int(consts["SDEB200_NBINS"]) == L.NBINS and int(consts["SDEB200_SHARD_ALIGN"]) == L.SHARD_ALIGN
     for k, v in (("E_ARG", L.E_ARG), ("E_PARSE", L.E_PARSE), ("E_NVRTC", L.E_NVRTC), ("E_CUDA", L.E_CUDA),
                  ("E_NCCL", L.E_NCCL), ("E_DOMAIN", L.E_DOMAIN), ("E_UNSUPPORTED", L.E_UNSUPPORTED),
-                 ("MILSTEIN", L.MILSTEIN), ("RUNGE_KUTTA", L.RUNGE_KUTTA), ("F32", L.F32), ("MATH_STRICT", L.MATH_STRICT), ("LAYOUT_SOA", L.LAYOUT_SOA),
+                 ("MILSTEIN", L.MILSTEIN), ("RUNGE_KUTTA", L.RUNGE_KUTTA), ("EXACT", L.EXACT), ("F32", L.F32), ("MATH_STRICT", L.MATH_STRICT), ("LAYOUT_SOA", L.LAYOUT_SOA),
                  ("PAYOFF_CALL", L.PAYOFF_CALL), ("PAYOFF_PUT", L.PAYOFF_PUT), ("PAYOFF_COMPONENT", L.PAYOFF_COMPONENT)):
         assert int(consts["SDEB200_" + k]) == v
 

@@ -379,3 +379,49 @@ def test_adaptive_mlmc_driver(gpu):
     ml = S.MultilevelScheme(S.EulerMaruyama(1 / 16), 2, r.levels)
     one = S.ml_estimate(m, ml, pay, 0.0, [100.0, 0.4], 16, list(r.n), seed=3)
     assert np.allclose(one.level_mean, r.level_mean, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,params,x0", [("BlackScholes", BS_P, 100.0), ("OrnsteinUhlenbeck", (2.0, 0.7, 0.3), 1.1)])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_exact_samplers_match_oracle(gpu, O, name, params, x0, precision):
+    """Exact scheme (simulation.jl:50-57,78-89): terminal values and trajectories against the oracle on the same
+    N(0,1) stream; device exp/log differ from libm by an ulp or two per step."""
+    S = gpu
+    m = getattr(S, name)(*params)
+    nsteps, npaths, dt = 12, 500, 1.0 / 12
+    z = O.normals_paths(31, 2, 0, npaths, nsteps, 1, precision)
+    ref = O.simulate_z(name, 3, params, 0.0, dt, x0, z)[..., 0]
+    x, t = S.simulate(m, S.Exact(dt), 0.0, x0, nsteps, npaths, seed=31, stream=2, precision=precision)
+    xs, _ = S.simulate(m, S.Exact(dt), 0.0, x0, nsteps, npaths, seed=31, stream=2, precision=precision, layout="soa")
+    term = S.sample(m, S.Exact(dt), 0.0, x0, nsteps, npaths, seed=31, stream=2, precision=precision)
+    tol = 1e-11 if precision == "f64" else 2e-4
+    assert rel_err(x, ref) <= tol
+    assert np.array_equal(x, xs.T) and np.array_equal(x[:, -1], term)
+    for mth in ("strict",):
+        ts = S.sample(m, S.Exact(dt), 0.0, x0, nsteps, npaths, seed=31, stream=2, precision=precision, math=mth)
+        assert rel_err(ts, ref[:, -1]) <= tol
+
+
+def test_exact_blackscholes_is_bias_free(gpu):
+    """One exact step to T = 1: the call price matches Black–Scholes (12.368267) within 3 SE —
+    the cross-check for the discretised schemes."""
+    import math
+    S = gpu
+    m = S.BlackScholes(*BS_P)
+    e = S.estimate(m, S.Exact(1.0), S.Call(100.0, math.exp(-0.01)), 0.0, 100.0, 1, 4 * 10 ** 6, seed=5)
+    assert abs(e.mean[0] - 12.368267463784079) <= 3 * e.stderr[0]
+    mom = S.estimate(m, S.Exact(0.25), S.Moments(), 0.0, 100.0, 4, 4 * 10 ** 6, seed=6)
+    assert abs(mom.mean[0] - 100 * math.exp(0.01)) <= 3 * mom.stderr[0]
+
+
+def test_exact_only_where_the_reference_defines_it(gpu):
+    S = gpu
+    with pytest.raises(S.SDEB200Error) as ei:
+        S.sample(S.Heston(*HESTON_P), S.Exact(0.1), 0.0, [100.0, 0.4], 4, 8)
+    assert ei.value.code == S._lib.E_UNSUPPORTED
+    gen = S.sde_model("BSgen", S.REGISTRY["BlackScholes"])(*BS_P)
+    with pytest.raises(S.SDEB200Error):
+        S.sample(gen, S.Exact(0.1), 0.0, 100.0, 4, 8)
+    ml = S.MultilevelScheme(S.Exact(0.1), 2, range(0, 3))
+    with pytest.raises(S.SDEB200Error):   # the coupled sampler needs a step(model, scheme, ...) method
+        S.sample(S.BlackScholes(*BS_P), ml, 0.0, 100.0, 2, 4)

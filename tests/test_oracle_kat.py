@@ -157,3 +157,27 @@ def test_normal_stream_statistics(O):
         assert abs((z ** 4).mean() - 3) < 4 * math.sqrt(96 / n)
         # pairs (cos, sin branches) are uncorrelated
         assert abs(np.mean(z[0::2] * z[1::2])) < 4 / math.sqrt(n / 2)
+
+
+def test_exact_samplers(O):
+    """sample(model, ::Exact, t0, x0) for BlackScholes (black_scholes.jl:3-13) and OrnsteinUhlenbeck
+    (ornstein_uhlenbeck.jl:3-13): formulas by hand, and the bias-free moments of the exact transition."""
+    r, s = BS_P
+    dt, z = 0.5, 0.3
+    got = O.sample_z("BlackScholes", 3, BS_P, 0.0, dt, 100.0, np.array([[[z]]]))[0, 0]
+    assert got == math.exp(z * (math.sqrt(dt) * s) + (math.log(100.0) + (r - 0.5 * (s * s)) * dt))
+    th, mu, sg = 2.0, 0.7, 0.3
+    got = O.sample_z("OrnsteinUhlenbeck", 3, (th, mu, sg), 0.0, dt, 1.1, np.array([[[z]]]))[0, 0]
+    m = 1.1 * math.exp(-th * dt) + mu * (1.0 - math.exp(-th * dt))
+    d = math.sqrt(1.0 - math.exp(-2 * th * dt)) * sg / math.sqrt(2 * th)
+    assert got == m + d * z
+    n = 400000
+    zz = np.random.default_rng(7).standard_normal((n, 4, 1))
+    x = O.sample_z("BlackScholes", 3, BS_P, 0.0, 0.25, 100.0, zz)[:, 0]
+    assert abs(x.mean() - 100.0 * math.exp(0.01)) <= 4 * x.std() / math.sqrt(n)          # no discretisation bias
+    y = O.sample_z("OrnsteinUhlenbeck", 3, (th, mu, sg), 0.0, 0.25, 1.1, zz)[:, 0]
+    assert abs(y.mean() - (1.1 * math.exp(-th) + mu * (1 - math.exp(-th)))) <= 4 * y.std() / math.sqrt(n)
+    assert abs(y.var() - sg ** 2 / (2 * th) * (1 - math.exp(-2 * th))) <= 0.01 * y.var()
+    import pytest
+    with pytest.raises(RuntimeError):   # no Exact method for Heston in the reference
+        O.sample_z("Heston", 3, HESTON_P, 0.0, 0.1, [100.0, 0.4], np.zeros((1, 1, 2)))
