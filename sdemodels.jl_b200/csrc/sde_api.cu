@@ -445,6 +445,13 @@ static size_t simref_smem(int D, int precision) {
   const int ts = (precision == SDEB200_F64 ? 16 : 32) / D, row = ts * D, lds = row | 1;
   return (size_t)(SDE_BLOCK / 32) * 32 * SIMREF_PW * lds * esize(precision);
 }
+// Wiener-driven kernel (simulate_wiener_body): per warp a w tile [32][WLD] and an x tile [32][XLD]
+static size_t simw_smem(int D, int M, int precision) {
+  const int mw = M > 0 ? M : 1, dm = D > mw ? D : mw;
+  const int ts = (SDE_SIMW_ROWBYTES / (int)esize(precision)) / dm;
+  const int wld = (ts * mw) | 1, xld = (ts * D) | 1;
+  return (size_t)(SDE_BLOCK / 32) * 32 * (wld + xld) * esize(precision);
+}
 static int64_t simref_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SIMREF_PW); }
 
 static bool is_device_ptr(const void *p) {
@@ -704,7 +711,7 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
     a.npaths = npaths;
     a.out = x;
     a.out2 = (void *)w;
-    if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+    if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, simw_smem(m->D, m->M, o->precision)))) return rc;
   } else {
     const size_t wb = (size_t)nrows * MW * es, xb = (size_t)nrows * m->D * es;
     int64_t slab = (int64_t)((size_t)(128u << 20) / std::max(wb, xb));
@@ -719,7 +726,7 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
       b.npaths = n;
       b.out = g.slab[0].p;
       b.out2 = g.win[0].p;
-      if ((rc = launch(k, cdiv(n, SDE_BLOCK), &b, st))) return rc;
+      if ((rc = launch(k, cdiv(n, SDE_BLOCK), &b, st, simw_smem(m->D, m->M, o->precision)))) return rc;
       CU(cudaMemcpyAsync((char *)x + (size_t)s0 * xb, g.slab[0].p, (size_t)n * xb,
                          xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
@@ -1040,13 +1047,13 @@ extern "C" int sdeb200_mlmc_simulate_level(sdeb200_model *m, const sdeb200_opts 
   a.nsteps = nf - 1;
   a.out = dxf;
   a.out2 = dxf;
-  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, simw_smem(m->D, m->M, o->precision)))) return rc;
   fill_args(&a, m, o, params, x0);
   a.npaths = npaths;
   a.nsteps = nc - 1;
   a.out = dxc;
   a.out2 = dxc;
-  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st))) return rc;
+  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, simw_smem(m->D, m->M, o->precision)))) return rc;
   if (!fdev) CU(cudaMemcpyAsync(xf, dxf, fb, cudaMemcpyDeviceToHost, st));
   if (!cdev) CU(cudaMemcpyAsync(xc, dxc, cb, cudaMemcpyDeviceToHost, st));
   return timed_end();

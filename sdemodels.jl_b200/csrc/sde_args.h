@@ -20,6 +20,10 @@ typedef long long int64_t;
 #define SDE_BLOCK 128     /* threads per CTA for every path kernel */
 #define SDE_TAB_DOUBLES 2304 /* FP64 transform tables in shared memory: 256 (log) + 2048 (rotation) */
 #define SDE_SIMREF_PW 1   /* paths per lane in the reference-layout trajectory kernels (2 measured slower: 128 registers) */
+#ifndef SDE_SIMW_ROWBYTES
+#define SDE_SIMW_ROWBYTES 128 /* contiguous bytes per path and tile in the Wiener-driven kernel */
+#define SDE_SIMW_MINBLOCKS 5
+#endif
 #define SDE_NBINS 68      /* 32-bit limbs of the exact (Kulisch-style) accumulator, held in int64 */
 #define SDE_SHARD_ALIGN 1024 /* shards start on multiples of this many paths => chunking is G-invariant */
 

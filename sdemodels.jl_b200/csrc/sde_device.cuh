@@ -837,11 +837,12 @@ template <class Model, typename T, int SCHEME>
 SDE_D void simulate_wiener_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M, MW = (M > 0 ? M : 1);
   constexpr int DM = D > MW ? D : MW;
-  constexpr int TS = (sizeof(T) == 8 ? 16 : 32) / DM;  // rows per tile
+  constexpr int TS = (SDE_SIMW_ROWBYTES / (int)sizeof(T)) / DM;  // rows per tile
   constexpr int WROW = TS * MW, XROW = TS * D;
   constexpr int WLD = WROW | 1, XLD = XROW | 1;
-  __shared__ T s_w[SDE_BLOCK / 32][32 * WLD];
-  __shared__ T s_x[SDE_BLOCK / 32][32 * XLD];
+  extern __shared__ __align__(16) unsigned char s_dyn[];   // [warps][32][WLD] then [warps][32][XLD]: sde_simw_smem_bytes()
+  T (*s_w)[32 * WLD] = (T (*)[32 * WLD])s_dyn;
+  T (*s_x)[32 * XLD] = (T (*)[32 * XLD])((T *)s_dyn + (SDE_BLOCK / 32) * 32 * WLD);
   Consts<T> cst;
   T prm[SDE_MAXP];
 #pragma unroll
@@ -923,7 +924,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMW_MINBLOCKS) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }
 
 // Exact one-step samplers exist for a few models only and have no Wiener-driven or coupled form
