@@ -158,6 +158,12 @@ int sdeb200_mlmc_simulate_level(sdeb200_model *m, const sdeb200_opts *o, const d
                                 double dt_fine, int64_t substeps, int64_t ncoarse, int64_t npaths, void *xc,
                                 void *xf);
 
+/* logtransition(model, scheme::EulerMaruyama, times, data) (src/schemes/schemes.jl:64-76, euler_maruyama.jl:8-13):
+ * Gaussian one-step log-densities along stored trajectories on the uniform grid t0 + i*dt.
+ * x[npaths][nrows][D] -> out[npaths][nrows-1]; out[k][i] is the log-density of x[k][i+1] given x[k][i]. */
+int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, const double *params, int64_t nrows,
+                          int64_t npaths, const void *x, void *out);
+
 /* ---- fused estimators (north_star (c); no reference analogue, oracle = mean(payoff.(sample(...)))) ---- */
 /* Terminal-value run with the payoff reduced on the fly: warp shuffles + CTA reduction to per-chunk partials,
  * exact integer accumulation, and — when a communicator is up — ONE ncclAllReduce over all ranks.

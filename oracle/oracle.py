@@ -143,6 +143,19 @@ def simulate_wiener(model, scheme, params, t0, dt, x0, w, inplace=False):
     return x
 
 
+def logtransition(model, params, t0, dt, x):
+    """logtransition(model, EulerMaruyama(dt), times, data) (schemes.jl:64-76): x[npaths, nrows, D] -> [npaths, nrows-1]."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    npaths, nrows = x.shape[0], x.shape[1]
+    out = np.zeros((npaths, nrows - 1))
+    p = _pv(params)
+    rc = lib().oracle_logtransition(model_id(model), _ptr(p), C.c_double(t0), C.c_double(dt), C.c_int64(nrows),
+                                    C.c_int64(npaths), _ptr(x), _ptr(out))
+    if rc:
+        raise RuntimeError(f"oracle_logtransition rc={rc}")
+    return out
+
+
 def level_dt(base_dt, substeps, level):
     return lib().oracle_level_dt(base_dt, substeps, level)
 

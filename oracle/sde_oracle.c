@@ -366,6 +366,73 @@ int oracle_simulate_wiener(int id, int scheme, const double *p, double t0, doubl
 }
 
 /* ------------------------------------------------------------------------------------------
+ * logtransition(model, ::EulerMaruyama, times, data): src/schemes/schemes.jl:64-76 with
+ * _normal_transition_params of euler_maruyama.jl:8-13 — Gaussian one-step log-densities along
+ * stored trajectories.  x[npaths][nrows][D] -> out[npaths][nrows-1]; times t0 + i*dt.
+ *   μ = x0 + drift*Δt;  Σ = Δt*σ*σ';  z = μ - x1;  -0.5*(D*log(2π) + log(det(Σ)) + dot(z, Σ\z))
+ * D == 1 and D == 2 use the closed forms StaticArrays uses (det = a11 a22 - a12 a21, Cramer solve);
+ * larger D go through a Cholesky factorisation (equal up to rounding).
+ * ------------------------------------------------------------------------------------------ */
+int oracle_logtransition(int id, const double *p, double t0, double dt, int64_t nrows, int64_t npaths,
+                         const double *x, double *out) {
+  if (id < 0 || id >= M_COUNT) return -1;
+  const model_def *m = &MODELS[id];
+  const int D = m->D, M = m->M;
+  const double log2pi = log(2.0 * 3.14159265358979323846);
+  for (int64_t k = 0; k < npaths; k++)
+    for (int64_t i = 1; i < nrows; i++) {
+      const double *xa = x + (k * nrows + i - 1) * D, *xb = xa + D;
+      const double t = t0 + (double)(i - 1) * dt;
+      double mu[MAXD], sig[MAXD * MAXM], S[MAXD][MAXD], z[MAXD];
+      memset(sig, 0, sizeof sig);
+      m->drift(p, t, xa, mu);
+      m->diffusion(p, t, xa, sig);
+      for (int a = 0; a < D; a++) z[a] = (xa[a] + mu[a] * dt) - xb[a];
+      for (int a = 0; a < D; a++)
+        for (int b = 0; b < D; b++) {
+          double acc = 0.0;
+          for (int j = 0; j < M; j++) acc = (j == 0) ? (dt * sig[a * MAXM + j]) * sig[b * MAXM + j]
+                                                     : acc + (dt * sig[a * MAXM + j]) * sig[b * MAXM + j];
+          S[a][b] = acc;
+        }
+      double logdet, q;
+      if (D == 1) {
+        logdet = log(S[0][0]);
+        q = z[0] * (z[0] / S[0][0]);
+      } else if (D == 2) {
+        double det = S[0][0] * S[1][1] - S[0][1] * S[1][0];
+        double y0 = (S[1][1] * z[0] - S[0][1] * z[1]) / det, y1 = (S[0][0] * z[1] - S[1][0] * z[0]) / det;
+        logdet = log(det);
+        q = z[0] * y0 + z[1] * y1;
+      } else {
+        double L[MAXD][MAXD];
+        double ld = 0.0;
+        int ok = 1;
+        memset(L, 0, sizeof L);
+        for (int a = 0; a < D && ok; a++)
+          for (int b = 0; b <= a; b++) {
+            double s2 = S[a][b];
+            for (int c = 0; c < b; c++) s2 -= L[a][c] * L[b][c];
+            if (a == b) { if (!(s2 > 0.0)) { ok = 0; break; } L[a][a] = sqrt(s2); ld += 2.0 * log(L[a][a]); }
+            else L[a][b] = s2 / L[b][b];
+          }
+        if (!ok) { out[k * (nrows - 1) + i - 1] = NAN; continue; }
+        double y[MAXD];
+        q = 0.0;
+        for (int a = 0; a < D; a++) {
+          double s2 = z[a];
+          for (int c = 0; c < a; c++) s2 -= L[a][c] * y[c];
+          y[a] = s2 / L[a][a];
+          q += y[a] * y[a];
+        }
+        logdet = ld;
+      }
+      out[k * (nrows - 1) + i - 1] = -0.5 * (((double)D * log2pi + logdet) + q);
+    }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Multilevel: src/multilevel.jl
  * ------------------------------------------------------------------------------------------ */
 static int64_t ipow(int64_t b, int64_t e) { int64_t r = 1; while (e-- > 0) r *= b; return r; }

@@ -13,8 +13,8 @@ from .models import (AbstractSDE, REGISTRY, diffusion, dim, drift, fieldnames, r
 from .multilevel import (AdaptiveMLMC, MultilevelEstimate, MultilevelScheme, cost, ml_estimate, mlmc_adaptive,
                          multilevel_sample_level, multilevel_simulate_level, npaths, schemes)
 from .schemes import EulerMaruyama, Exact, Milstein, RungeKutta, subdivide
-from .simulation import (Call, Component, Estimate, Moments, Put, estimate, sample, sample_, simulate, simulate_,
-                         wiener_)
+from .simulation import (Call, Component, Estimate, Moments, Put, estimate, logtransition, sample, sample_, simulate,
+                         simulate_, wiener_)
 
 
 def __getattr__(name):

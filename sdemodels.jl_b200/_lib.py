@@ -69,6 +69,7 @@ SYMBOLS = {
     "sdeb200_simulate": (_I, [_VP, _PO, _PD, _PD, _I64, _I64, _I, _VP]),
     "sdeb200_simulate_wiener": (_I, [_VP, _PO, _PD, _PD, _I64, _I64, _VP, _VP]),
     "sdeb200_wiener": (_I, [_PO, _I, _I64, _I64, _VP]),
+    "sdeb200_logtransition": (_I, [_VP, _PO, _PD, _I64, _I64, _VP, _VP]),
     "sdeb200_mlmc_sample_level": (_I, [_VP, _PO, _PD, _PD, _D, _I64, _I64, _I64, _VP, _VP]),
     "sdeb200_mlmc_simulate_level": (_I, [_VP, _PO, _PD, _PD, _D, _I64, _I64, _I64, _VP, _VP]),
     "sdeb200_estimate": (_I, [_VP, _PO, _PD, _PD, _I64, _I64, _PP, _VP, _PD]),

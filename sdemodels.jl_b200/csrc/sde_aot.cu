@@ -31,7 +31,7 @@ template <int DIM> struct WienerN {
 #define SDE_AOT_WIENER sde_aot_wiener_fast
 #endif
 #define XSCHEME(MODEL, TAG, SCH, SNAME) SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)
-#define XCOEF(MODEL, TAG) SDE_KERNELS_COEF(MODEL, TAG)
+#define XCOEF(MODEL, TAG) SDE_KERNELS_COEF(MODEL, TAG) SDE_KERNELS_LOGT(MODEL, TAG, double, f64) SDE_KERNELS_LOGT(MODEL, TAG, float, f32)
 #define XFILL(T, TAG, s, SNAME) XFILL2(T, TAG, s, SNAME)
 #define XFILL2(T, TAG, s, SNAME)                                                      \
   T.sample[s][0] = (const void *)sdek_##TAG##_sample_##SNAME##_f64;                    \
@@ -45,7 +45,10 @@ template <int DIM> struct WienerN {
   T.simw[s][0] = (const void *)sdek_##TAG##_simw_##SNAME##_f64;                        \
   T.simw[s][1] = (const void *)sdek_##TAG##_simw_##SNAME##_f32;
 #define XCOEFFILL(T, TAG) XCOEFFILL2(T, TAG)
-#define XCOEFFILL2(T, TAG) T.coef = (const void *)sdek_##TAG##_coef;
+#define XCOEFFILL2(T, TAG)                              \
+  T.coef = (const void *)sdek_##TAG##_coef;             \
+  T.logt[0] = (const void *)sdek_##TAG##_logt_f64;      \
+  T.logt[1] = (const void *)sdek_##TAG##_logt_f32;
 
 XSCHEME(BlackScholes, TAGGED(bs), 0, em)
 XSCHEME(BlackScholes, TAGGED(bs), 1, mil)

@@ -737,6 +737,68 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// logtransition along stored trajectories
+// ---------------------------------------------------------------------------------------------------
+static size_t logt_smem(int D, int precision) {
+  const int ts = (SDE_SIMW_ROWBYTES / (int)esize(precision)) / D;
+  const int xld = (ts * D) | 1, old = ts | 1;
+  return (size_t)(SDE_BLOCK / 32) * 32 * (xld + old) * esize(precision);
+}
+
+extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, const double *params, int64_t nrows,
+                                     int64_t npaths, const void *x, void *out) {
+  if (!m || !o) return fail(SDEB200_E_ARG, "null argument");
+  if (!params && !m->params.empty()) return fail(SDEB200_E_ARG, "params is NULL");
+  if (o->scheme != SDEB200_EULER_MARUYAMA)
+    return fail(SDEB200_E_UNSUPPORTED, "logtransition is implemented for EulerMaruyama (src/schemes/euler_maruyama.jl:8-13)");
+  if (o->precision < 0 || o->precision > 1 || !(o->dt > 0.0)) return fail(SDEB200_E_ARG, "bad precision / Δt");
+  if (nrows < 1 || npaths < 0 || ((!x || !out) && npaths > 0 && nrows > 1)) return fail(SDEB200_E_ARG, "bad nrows/npaths/x/out");
+  int rc = ensure_up();
+  if (rc) return rc;
+  sdeb200_opts oc = *o;
+  oc.math = SDEB200_MATH_FAST;
+  const sde_ktable *kt;
+  if ((rc = get_ktable(m, &oc, &kt))) return rc;
+  if (npaths == 0 || nrows == 1) return SDEB200_OK;
+  const void *k = kt->logt[o->precision];
+  cudaStream_t st = g.stream();
+  const size_t es = esize(o->precision);
+  const size_t xb = (size_t)nrows * m->D * es, ob = (size_t)(nrows - 1) * es;
+  double x0[SDE_MAXD] = {0, 0, 0, 0};
+  sde_args a;
+  fill_args(&a, m, &oc, params, x0);
+  a.nsteps = nrows - 1;
+  const bool xdev = is_device_ptr(x), odev = is_device_ptr(out);
+  const size_t smem = logt_smem(m->D, o->precision);
+  if ((rc = timed_begin())) return rc;
+  if (xdev && odev) {
+    a.npaths = npaths;
+    a.out = out;
+    a.out2 = (void *)x;
+    if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, smem))) return rc;
+  } else {
+    int64_t slab = (int64_t)((size_t)(128u << 20) / xb);
+    slab = std::max<int64_t>(32, std::min<int64_t>(slab, npaths));
+    if ((rc = g.win[0].ensure((size_t)slab * xb))) return rc;
+    if ((rc = g.slab[0].ensure((size_t)slab * ob))) return rc;
+    for (int64_t s0 = 0; s0 < npaths; s0 += slab) {
+      const int64_t n = std::min<int64_t>(slab, npaths - s0);
+      CU(cudaMemcpyAsync(g.win[0].p, (const char *)x + (size_t)s0 * xb, (size_t)n * xb,
+                         xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+      sde_args b = a;
+      b.npaths = n;
+      b.out = g.slab[0].p;
+      b.out2 = g.win[0].p;
+      if ((rc = launch(k, cdiv(n, SDE_BLOCK), &b, st, smem))) return rc;
+      CU(cudaMemcpyAsync((char *)out + (size_t)s0 * ob, g.slab[0].p, (size_t)n * ob,
+                         odev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  return timed_end();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // wiener!
 // ---------------------------------------------------------------------------------------------------
 static int wiener_device(const sdeb200_opts *o, int dim, int64_t nrows, int64_t npaths, int64_t path0, void *dev,

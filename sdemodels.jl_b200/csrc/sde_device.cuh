@@ -893,6 +893,121 @@ SDE_D void simulate_wiener_body(const sde_args &a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K7  logtransition(model, ::EulerMaruyama, times, data)  [schemes.jl:64-76, euler_maruyama.jl:8-13]:
+//     Gaussian one-step log-densities along stored trajectories, x (a.out2) [path][row][D] -> a.out [path][row-1].
+//     Streaming and HBM-bound (D reads, 1 write per transition); same tile staging as K3.  The arithmetic is done
+//     in double for both storage precisions (it is free next to the memory traffic).
+//       μ = x0 + drift Δt;  Σ = Δt σ σ';  z = μ - x1;  -0.5 (D log 2π + log det Σ + z' Σ⁻¹ z)
+// ---------------------------------------------------------------------------------------------------
+template <int D> SDE_D double gauss_logpdf_terms(const double (&S)[SDE_MAXD][SDE_MAXD], const double *z) {
+  double logdet, q;
+  if (D == 1) {
+    logdet = log(S[0][0]);
+    q = z[0] * (z[0] / S[0][0]);
+  } else if (D == 2) {  // closed forms (StaticArrays: det = a11 a22 - a12 a21, Cramer solve)
+    const double det = S[0][0] * S[1][1] - S[0][1] * S[1][0];
+    const double y0 = (S[1][1] * z[0] - S[0][1] * z[1]) / det, y1 = (S[0][0] * z[1] - S[1][0] * z[0]) / det;
+    logdet = log(det);
+    q = z[0] * y0 + z[1] * y1;
+  } else {  // Cholesky
+    double L[SDE_MAXD][SDE_MAXD], y[SDE_MAXD];
+    double ld = 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+#pragma unroll
+      for (int b = 0; b <= a; b++) {
+        double s2 = S[a][b];
+#pragma unroll
+        for (int c = 0; c < b; c++) s2 -= L[a][c] * L[b][c];
+        if (a == b) {
+          ok = ok && (s2 > 0.0);
+          L[a][a] = sqrt(s2);
+          ld += 2.0 * log(L[a][a]);
+        } else {
+          L[a][b] = s2 / L[b][b];
+        }
+      }
+    }
+    q = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; a++) {
+      double s2 = z[a];
+#pragma unroll
+      for (int c = 0; c < a; c++) s2 -= L[a][c] * y[c];
+      y[a] = s2 / L[a][a];
+      q += y[a] * y[a];
+    }
+    logdet = ok ? ld : nan("");
+  }
+  return -0.5 * (((double)D * 0x1.d67f1c864beb5p+0 /* log 2π */ + logdet) + q);
+}
+
+template <class Model, typename T>
+SDE_D void logtransition_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M;
+  constexpr int TS = (SDE_SIMW_ROWBYTES / (int)sizeof(T)) / D;  // rows per tile
+  constexpr int XROW = TS * D, XLD = XROW | 1, OLD = TS | 1;
+  extern __shared__ __align__(16) unsigned char s_dyn[];   // [warps][32][XLD] then [warps][32][OLD]
+  T (*s_x)[32 * XLD] = (T (*)[32 * XLD])s_dyn;
+  T (*s_o)[32 * OLD] = (T (*)[32 * OLD])((T *)s_dyn + (SDE_BLOCK / 32) * 32 * XLD);
+  double prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = a.params[i];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t wbase = (int64_t)blockIdx.x * blockDim.x + (wid << 5);
+  if (wbase >= a.npaths) return;
+  const int nlive = (int)((a.npaths - wbase) < 32 ? (a.npaths - wbase) : 32);
+  const int64_t nrows = a.nsteps + 1;
+  const T *xin = (const T *)a.out2;
+  T *out = (T *)a.out;
+  T *tx = s_x[wid], *to = s_o[wid];
+  double xp[SDE_MAXD];
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++) xp[d] = 0.0;
+  for (int64_t row0 = 0; row0 < nrows; row0 += TS) {
+    const int nr = (int)((nrows - row0) < TS ? (nrows - row0) : TS);
+    tile_load<T, XROW, XLD>(tx, xin + (wbase * nrows + row0) * D, nrows * D, nlive, nr * D, lane);
+    __syncwarp();
+    for (int i = 0; i < nr; i++) {
+      const int64_t row = row0 + i;
+      double xc[SDE_MAXD];
+#pragma unroll
+      for (int d = 0; d < SDE_MAXD; d++) xc[d] = d < D ? (double)tx[lane * XLD + i * D + d] : 0.0;
+      if (row > 0) {
+        double mu[SDE_MAXD], sig[SDE_MAXD * SDE_MAXM], S[SDE_MAXD][SDE_MAXD], z[SDE_MAXD];
+#pragma unroll
+        for (int q = 0; q < SDE_MAXD * SDE_MAXM; q++) sig[q] = 0.0;
+        Model::coefficients(prm, a.t0 + (double)(row - 1) * a.dt, xp, mu, sig);
+#pragma unroll
+        for (int p = 0; p < D; p++) z[p] = (xp[p] + mu[p] * a.dt) - xc[p];
+#pragma unroll
+        for (int p = 0; p < D; p++)
+#pragma unroll
+          for (int q = 0; q < D; q++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+              const double term = (a.dt * sig[p * SDE_MAXM + j]) * sig[q * SDE_MAXM + j];
+              acc = j == 0 ? term : acc + term;
+            }
+            S[p][q] = acc;
+          }
+        to[lane * OLD + i] = (T)gauss_logpdf_terms<D>(S, z);  // transition ending at tile row i
+      }
+#pragma unroll
+      for (int d = 0; d < SDE_MAXD; d++) xp[d] = xc[d];  // carried into the next tile as well
+    }
+    __syncwarp();
+    // tile row i holds the transition (row0 + i - 1) -> (row0 + i): output column row0 + i - 1; row 0 has none
+    const int i0 = row0 == 0 ? 1 : 0;
+    if (nr > i0)
+      tile_store<T, TS, OLD>(to + i0, out + wbase * (nrows - 1) + (row0 - 1 + i0), nrows - 1, nlive, nr - i0, lane);
+    __syncwarp();
+  }
+}
+
 // K6  drift / diffusion evaluation at one point (functor known-answer tests, test/runtests.jl:61-82).
 //     out[0..D) = drift, out[D .. D + D*max(M,1)) = diffusion, row-major.
 template <class Model>
@@ -940,6 +1055,10 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \
   SDE_KERNELS(MODEL, TAG, SCH, SNAME, double, f64)  \
   SDE_KERNELS(MODEL, TAG, SCH, SNAME, float, f32)
+
+#define SDE_KERNELS_LOGT(MODEL, TAG, T, PNAME)                                                                   \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##_logt_##PNAME(                          \
+      const __grid_constant__ sde_args a) { sdeb200::logtransition_body<MODEL, T>(a); }
 
 #define SDE_KERNELS_COEF(MODEL, TAG)                                                                             \
   extern "C" __global__ void sdek_##TAG##_coef(const __grid_constant__ sde_args a) {                            \

@@ -66,6 +66,7 @@ int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision,
   if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 1, mil, ") + T + ", " + P + ")\n";
   if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 2, rk, ") + T + ", " + P + ")\n";
   src += "SDE_KERNELS_COEF(sdeb200::GenModel, gen)\n";
+  src += std::string("SDE_KERNELS_LOGT(sdeb200::GenModel, gen, ") + T + ", " + P + ")\n";
   const char *hdr_src[] = {sde_embedded_device_cuh, sde_embedded_args_h, sde_embedded_coeffs_inc};
   const char *hdr_name[] = {"sde_device.cuh", "sde_args.h", "sde_coeffs.inc"};
   nvrtcProgram prog = nullptr;
@@ -129,7 +130,7 @@ int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precisio
       return SDEB200_E_CUDA;
     }
   }
-  if (!get("sdek_gen_coef", &kt->coef)) {
+  if (!get(std::string("sdek_gen_logt_") + P, &kt->logt[precision]) || !get("sdek_gen_coef", &kt->coef)) {
     cudaLibraryUnload(lib);
     return SDEB200_E_CUDA;
   }

@@ -20,7 +20,7 @@ module SDEModelsB200
 using SDEModels
 using SDEModels: AbstractSDE, AbstractScheme, EulerMaruyama, Milstein, RungeKutta, MultilevelScheme, subdivide, dim
 using StaticArrays
-import SDEModels: sample, simulate, simulate!
+import SDEModels: sample, simulate, simulate!, logtransition
 
 export B200, estimate, Call, Put, Moments, Component, @sde_model_b200, b200_init
 
@@ -137,6 +137,17 @@ function simulate!(x::AbstractArray, model::AbstractSDE, b::B200, t0, x0, w::Abs
               (Ptr{Cvoid}, Ref{Opts}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
               handle(typeof(model)), o, params(model), state(x0), nrows, npaths, w, x))
   x
+end
+
+# -- logtransition(model, scheme, times, data): src/schemes/schemes.jl:64-76 (EulerMaruyama, uniform grid) -------------------
+function logtransition(model::AbstractSDE{D,M}, b::B200{EulerMaruyama}, times, data::AbstractVector) where {D,M}
+  nrows = length(data)
+  out = Vector{b.precision}(undef, nrows - 1)
+  o = Ref(opts(b, first(times)))
+  check(ccall((:sdeb200_logtransition, lib), Cint,
+              (Ptr{Cvoid}, Ref{Opts}, Ptr{Float64}, Int64, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+              handle(typeof(model)), o, params(model), nrows, 1, data, out))
+  out
 end
 
 # -- multilevel: src/multilevel.jl:52-63 — level loop in Julia, one coupled kernel per level pair -------------------------

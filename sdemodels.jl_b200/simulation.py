@@ -200,6 +200,36 @@ def wiener_(w, dt, *, seed=0, stream=0, path_offset=0, math="fast"):
     return w
 
 
+def logtransition(model, scheme, times, data, *, out=None, device=False):
+    """logtransition(model, scheme, times, data)   (src/schemes/schemes.jl:64-76 with euler_maruyama.jl:8-13)
+
+    Gaussian Euler–Maruyama log-densities of the transitions data[i-1] -> data[i] along stored trajectories.
+    `data`: ([npaths,] nrows) for scalar models, ([npaths,] nrows, D) otherwise (what `simulate` returns);
+    `times`: the uniform grid t0 + Δt*(0:nrows-1) (or just t0).  Returns ([npaths,] nrows-1)."""
+    L = _lib.lib()
+    D = model._D
+    is_torch = hasattr(data, "data_ptr")
+    precision = "f32" if str(data.dtype).endswith("float32") else "f64"
+    shp = tuple(data.shape)
+    if D > 1:
+        if shp[-1] != D:
+            raise ValueError(f"data must carry {D} state components on its last axis")
+        shp = shp[:-1]
+    single = len(shp) == 1
+    n, nrows = (1, shp[0]) if single else (int(np.prod(shp[:-1], dtype=np.int64)), shp[-1])
+    t = np.atleast_1d(np.asarray(times, dtype=np.float64))
+    if len(t) > 1 and (len(t) != nrows or not np.allclose(np.diff(t), scheme.dt, rtol=1e-9, atol=1e-15)):
+        raise ValueError("times must be the uniform grid t0 + scheme.Δt*(0:nrows-1)")
+    if not (data.is_contiguous() if is_torch else data.flags.c_contiguous):
+        raise ValueError("data must be C-contiguous")
+    buf = _Buf((nrows - 1,) if single else (n, nrows - 1), precision, out, device or is_torch)
+    o = _opts(scheme, float(t[0]), 0, precision)
+    p = _params(model)
+    _lib.check(L.sdeb200_logtransition(model._handle, C.byref(o), p.ctypes.data_as(_PD), nrows, n,
+                                       data.data_ptr() if is_torch else data.ctypes.data, buf.ptr))
+    return buf.arr
+
+
 # ---------------------------------------------------------------------------------------------------
 # fused estimators (new: the reference returns raw states, SURVEY F7)
 # ---------------------------------------------------------------------------------------------------

@@ -158,3 +158,30 @@ def test_coupled_sampler_needs_matching_dimensions(gpu):
     with pytest.raises(S.SDEB200Error) as ei:
         S.multilevel_sample_level(m, S.EulerMaruyama(0.1), S.EulerMaruyama(0.05), 2, 0.0, [0.1, 0.2, 0.3], 4, 10)
     assert ei.value.code == S._lib.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name,params,x,t", [c for c in CASES if c[0] in
+                                             ("BlackScholes", "Heston", "Lorenz", "CoxIngersollRoss", "TimeDependent", "FitzHughNagumo")])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_logtransition_matches_oracle(gpu, O, name, params, x, t, precision):
+    """logtransition along stored trajectories (schemes.jl:64-76, euler_maruyama.jl:8-13): built-in and generated
+    functors, ragged sizes (rows not a multiple of the tile, paths not a multiple of the warp), host and device data."""
+    import torch
+    S = gpu
+    D, M, _ = O.dims(name)
+    m = (getattr(S, name) if name in ("BlackScholes", "Heston") else gen(S, name))(*params)
+    dt = 1.0 / 256
+    for npaths, nsteps in ((1, 1), (37, 5), (100, 45)):
+        z = np.random.default_rng(3).standard_normal((npaths, nsteps, M))
+        paths = O.simulate_z(name, 0, params, t, dt, x, z)
+        data = paths[..., 0] if D == 1 else paths
+        data = np.ascontiguousarray(data.astype(np.float32 if precision == "f32" else np.float64))
+        ref = O.logtransition(name, params, t, dt, data.reshape(npaths, nsteps + 1, D).astype(np.float64))
+        got = S.logtransition(m, S.EulerMaruyama(dt), t + dt * np.arange(nsteps + 1), data)
+        assert got.shape == (npaths, nsteps) and got.dtype == data.dtype
+        tol = 1e-11 if precision == "f64" else 2e-5
+        assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= tol, (name, npaths, nsteps)
+        dev = S.logtransition(m, S.EulerMaruyama(dt), t, torch.from_numpy(data).cuda())
+        assert np.array_equal(dev.cpu().numpy(), got)
+    one = S.logtransition(m, S.EulerMaruyama(dt), t, data[0])
+    assert one.shape == (nsteps,) and np.array_equal(one, got[0])

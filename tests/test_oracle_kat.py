@@ -181,3 +181,23 @@ def test_exact_samplers(O):
     import pytest
     with pytest.raises(RuntimeError):   # no Exact method for Heston in the reference
         O.sample_z("Heston", 3, HESTON_P, 0.0, 0.1, [100.0, 0.4], np.zeros((1, 1, 2)))
+
+
+def test_logtransition_against_scipy(O):
+    """logtransition(model, EulerMaruyama, times, data) (schemes.jl:64-76): the oracle against an independent
+    evaluation of the same Gaussian log-density (scipy) for D = 1, 2, 3."""
+    from scipy.stats import multivariate_normal
+    LP = (10.0, 28.0, 8 / 3, 0.1, 0.2, 0.3)
+    for name, p, x0, dt, M in (("BlackScholes", BS_P, [100.0], 0.01, 1), ("Heston", HESTON_P, [100.0, 0.4], 0.01, 2),
+                               ("Lorenz", LP, [1.0, 2.0, 3.0], 0.001, 3)):
+        z = np.random.default_rng(0).standard_normal((3, 7, M))
+        x = O.simulate_z(name, 0, p, 0.5, dt, x0, z)
+        lt = O.logtransition(name, p, 0.5, dt, x)
+        assert lt.shape == (3, 7)
+        for k in range(3):
+            for i in range(1, 8):
+                xa, xb = x[k, i - 1], x[k, i]
+                mu = xa + O.drift(name, p, 0.5 + (i - 1) * dt, xa) * dt
+                sg = O.diffusion(name, p, 0.5 + (i - 1) * dt, xa)
+                want = multivariate_normal(mu, dt * sg @ sg.T).logpdf(xb)
+                assert abs(lt[k, i - 1] - want) <= 1e-9 * max(1.0, abs(want))
