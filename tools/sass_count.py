@@ -37,7 +37,12 @@ def loop_counts(fun):
             loops.append((int(m.group(1), 16), a))
     # innermost loops only (the kernels wrap the time loop in a chunk loop); the hot one is the largest of those
     inner = [l for l in loops if not any(o != l and l[0] <= o[0] and o[1] <= l[1] for o in loops)]
-    best = max(inner, key=lambda l: l[1] - l[0])
+    # the time loop is the first innermost loop that contains a full Philox block (out-of-line helpers, if any, come
+    # later in the listing and may have loops of their own)
+    def philox(l):
+        return sum(1 for a, t in ins if l[0] <= a <= l[1] and "IMAD.WIDE" in t)
+    cands = [l for l in sorted(inner) if philox(l) >= 9]
+    best = cands[0] if cands else max(inner, key=lambda l: l[1] - l[0])
     cnt = collections.Counter()
     for a, t in ins:
         if best[0] <= a <= best[1]:
