@@ -425,3 +425,33 @@ def test_exact_only_where_the_reference_defines_it(gpu):
     ml = S.MultilevelScheme(S.Exact(0.1), 2, range(0, 3))
     with pytest.raises(S.SDEB200Error):   # the coupled sampler needs a step(model, scheme, ...) method
         S.sample(S.BlackScholes(*BS_P), ml, 0.0, 100.0, 2, 4)
+
+
+def test_large_host_buffers_go_through_the_slab_pipelines(gpu):
+    """Host arrays larger than one staging slab (256 MB / 128 MB): the double-buffered device->host pipeline of
+    sample/simulate, the strided 2-D copies of the SoA layout and the host path of simulate! must reproduce the
+    device-resident results bit for bit."""
+    import torch
+    S = gpu
+    he, bs = S.Heston(*HESTON_P), S.BlackScholes(*BS_P)
+    n = 18_000_000                                    # 288 MB of (S, V) terminals: two slabs
+    sch = S.EulerMaruyama(1 / 256)
+    host = S.sample(he, sch, 0.0, [100.0, 0.4], 4, n, seed=3)
+    dev = S.sample(he, sch, 0.0, [100.0, 0.4], 4, n, seed=3, device=True)
+    assert np.array_equal(host, dev.cpu().numpy())
+    del dev
+    n2, steps = 300_000, 128                          # 310 MB of trajectories
+    for lay in ("reference", "soa"):
+        xh, _ = S.simulate(bs, S.Milstein(1 / steps), 0.0, 100.0, steps, n2, seed=4, layout=lay)
+        xd, _ = S.simulate(bs, S.Milstein(1 / steps), 0.0, 100.0, steps, n2, seed=4, layout=lay, device=True)
+        assert np.array_equal(xh, xd.cpu().numpy()), lay
+        del xd
+    w = xh if xh.shape[0] == n2 else np.ascontiguousarray(xh.T)   # any (n2, steps+1) array will do as a Wiener path
+    wd = torch.from_numpy(w).cuda()
+    S.simulate_(wd, bs, S.EulerMaruyama(1 / steps), 0.0, 100.0, wd)
+    wh = w.copy()
+    S.simulate_(wh, bs, S.EulerMaruyama(1 / steps), 0.0, 100.0, wh)  # host in place: 2 slabs of 128 MB
+    assert np.array_equal(wh, wd.cpu().numpy())
+    lt_h = S.logtransition(bs, S.EulerMaruyama(1 / steps), 0.0, wh)
+    lt_d = S.logtransition(bs, S.EulerMaruyama(1 / steps), 0.0, wd)
+    assert np.array_equal(lt_h, lt_d.cpu().numpy())
