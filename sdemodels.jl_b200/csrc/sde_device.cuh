@@ -127,6 +127,12 @@ SDE_HD double sqrt_fast(double v) {
   return sqrt_from_seed(v, hilo2double((uint32_t)(hy < 0x7FE00000 ? hy : 0x7FE00000), 0));
 }
 SDE_HD float sqrt_fast(float v) { return sqrtf(v); }
+// sqrt as emitted by the @sde_model code generator: IEEE in STRICT math, the branch-free form in FAST math
+#if SDE_STRICT
+#define SDE_SQRT(x) sqrt(x)
+#else
+#define SDE_SQRT(x) sdeb200::sqrt_fast(x)
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  counter = (path_lo, path_hi, block, stream), key = seed.

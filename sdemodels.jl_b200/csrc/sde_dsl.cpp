@@ -567,7 +567,7 @@ struct Emit {
       return "pow(" + ex(a[0]) + ", " + ex(a[1]) + ")";
     }
     static const std::map<std::string, std::string> fn = {
-        {"sqrt", "sqrt"}, {"exp", "exp"}, {"log", "log"}, {"sin", "sin"}, {"cos", "cos"}, {"tan", "tan"},
+        {"sqrt", "SDE_SQRT"}, {"exp", "exp"}, {"log", "log"}, {"sin", "sin"}, {"cos", "cos"}, {"tan", "tan"},
         {"tanh", "tanh"}, {"sinh", "sinh"}, {"cosh", "cosh"}, {"atan", "atan"}, {"abs", "fabs"},
         {"log1p", "log1p"}, {"expm1", "expm1"}, {"max", "fmax"}, {"min", "fmin"}};
     if (f == "inv" && a.size() == 1) return "(" + lit(1, true) + " / " + ex(a[0]) + ")";
