@@ -564,7 +564,7 @@ extern "C" int sdeb200_model_coefficients(sdeb200_model *m, const double *params
 // sample
 // ---------------------------------------------------------------------------------------------------
 #ifndef SDE_PPT
-#define SDE_PPT 2
+#define SDE_PPT 4
 #endif
 static int64_t sample_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SDE_PPT); }
 

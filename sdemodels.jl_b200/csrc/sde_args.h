@@ -17,7 +17,9 @@ typedef long long int64_t;
 #define SDE_MAXP 16       /* model parameters (struct fields of the generated model type) */
 #define SDE_MAXC 32       /* per-thread prepared constants (raw parameters + hoisted sub-expressions) */
 #define SDE_MAXF 4        /* payoff features reduced per path */
+#ifndef SDE_BLOCK
 #define SDE_BLOCK 128     /* threads per CTA for every path kernel */
+#endif
 #define SDE_TAB_DOUBLES 2304 /* FP64 transform tables in shared memory: 256 (log) + 2048 (rotation) */
 #define SDE_SIMREF_PW 1   /* paths per lane in the reference-layout trajectory kernels (2 measured slower: 128 registers) */
 #ifndef SDE_SIMW_ROWBYTES

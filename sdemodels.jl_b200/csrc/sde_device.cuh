@@ -25,7 +25,7 @@
 #endif
 
 #ifndef SDE_PPT
-#define SDE_PPT 2 /* paths per thread in the terminal-value kernel (instruction-level parallelism) */
+#define SDE_PPT 4 /* paths per thread in the terminal-value kernel (instruction-level parallelism) */
 #endif
 #ifndef SDE_PHILOX_ROUNDS
 #define SDE_PHILOX_ROUNDS 10 /* Philox4x32-10, the Random123 / cuRAND default; other values are tuning experiments only */

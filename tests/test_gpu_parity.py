@@ -239,7 +239,7 @@ def test_estimate_with_more_chunks_than_ctas(gpu):
     """CTAs walk over chunks grid-stride once the grid is capped: sums still equal the sampled states' sums."""
     import math
     m, sch = gpu.BlackScholes(*BS_P), gpu.EulerMaruyama(1 / 8)
-    n = 148 * 64 * 256 * 2 + 12345
+    n = 148 * 64 * 512 * 2 + 12345
     x = gpu.sample(m, sch, 0.0, 100.0, 8, n, seed=6)
     e = gpu.estimate(m, sch, gpu.Moments(), 0.0, 100.0, 8, n, seed=6)
     assert e.n == n and abs(e.sums[0, 0] - math.fsum(x)) / e.sums[0, 0] <= 1e-13

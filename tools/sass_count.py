@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "sdemodels.jl_b200", "csrc", "build", "sde_aot_fast.o")
-PPT = 2
+PPT = 4
 # kernel -> path-steps per iteration of its main loop (PPT paths x U steps per Philox batch)
 KERNELS = {
     "heston_sample_em_f64": ("sdek_heston_f_sample_em_f64", PPT * 1, "D"),
