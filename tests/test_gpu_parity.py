@@ -455,3 +455,23 @@ def test_large_host_buffers_go_through_the_slab_pipelines(gpu):
     lt_h = S.logtransition(bs, S.EulerMaruyama(1 / steps), 0.0, wh)
     lt_d = S.logtransition(bs, S.EulerMaruyama(1 / steps), 0.0, wd)
     assert np.array_equal(lt_h, lt_d.cpu().numpy())
+
+
+def test_empty_and_degenerate_sizes(gpu):
+    """nsteps = 0 returns the start point (the reference's loops simply do not run), npaths = 0 returns empty
+    arrays and an empty estimate, a single path works through every driver."""
+    S = gpu
+    he, bs = S.Heston(*HESTON_P), S.BlackScholes(*BS_P)
+    sch = S.EulerMaruyama(0.01)
+    x = S.sample(he, sch, 0.0, [100.0, 0.4], 0, 5)
+    assert np.array_equal(x, np.tile([100.0, 0.4], (5, 1)))
+    xs, t = S.simulate(bs, sch, 0.0, 100.0, 0, 3)
+    assert xs.shape == (3, 1) and np.all(xs == 100.0) and t.shape == (1,)
+    assert S.sample(he, sch, 0.0, [100.0, 0.4], 7, 0).shape == (0, 2)
+    assert S.simulate(bs, sch, 0.0, 100.0, 7, 0)[0].shape == (0, 8)
+    e = S.estimate(he, sch, S.Moments(), 0.0, [100.0, 0.4], 7, 0)
+    assert e.n == 0 and np.all(e.sums == 0)
+    one = S.sample(bs, S.Milstein(0.01), 0.0, 100.0, 10)
+    assert isinstance(one, float) and np.isfinite(one)
+    assert S.simulate(he, sch, 0.0, [100.0, 0.4], 10)[0].shape == (11, 2)
+    assert S.logtransition(bs, sch, 0.0, np.array([100.0])).shape == (0,)
