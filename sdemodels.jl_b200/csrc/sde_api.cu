@@ -651,7 +651,7 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
     }
   } else {
     const void *k = kt->simsoa[o->scheme][o->precision];
-    const int vec = (int)(16 / es);
+    const int vec = SDE_SOA_VEC;
     if (dev) {
       a.npaths = npaths;
       a.out = out;

@@ -22,6 +22,7 @@ typedef long long int64_t;
 #endif
 #define SDE_TAB_DOUBLES 2304 /* FP64 transform tables in shared memory: 256 (log) + 2048 (rotation) */
 #define SDE_SIMREF_PW 1   /* paths per lane in the reference-layout trajectory kernels (2 measured slower: 128 registers) */
+#define SDE_SOA_VEC 4  /* consecutive paths per thread in the [time][D][path] trajectory kernel (8 measured no better in FP32) */
 #ifndef SDE_SIMW_ROWBYTES
 #define SDE_SIMW_ROWBYTES 128 /* contiguous bytes per path and tile in the Wiener-driven kernel */
 #define SDE_SIMW_MINBLOCKS 5

@@ -638,7 +638,7 @@ SDE_D void mlmc_body(const sde_args &a) {
 
 // ---------------------------------------------------------------------------------------------------
 // K2a full trajectories, device layout [time][D][path]:  simulate / simulate!   [simulation.jl:71-76,104-117]
-//     VEC consecutive paths per thread -> one 16-byte streaming store per (time, d) per thread.
+//     VEC = 4 consecutive paths per thread -> 16-byte streaming stores (one in FP32, two in FP64) per (time, d).
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int VEC> struct VecStore;
 template <> struct VecStore<double, 2> {
@@ -647,10 +647,22 @@ template <> struct VecStore<double, 2> {
 template <> struct VecStore<float, 4> {
   static SDE_D void st(float *p, const float *v) { __stcs((float4 *)p, make_float4(v[0], v[1], v[2], v[3])); }
 };
+template <> struct VecStore<double, 4> {  // two 16-byte stores
+  static SDE_D void st(double *p, const double *v) {
+    __stcs((double2 *)p, make_double2(v[0], v[1]));
+    __stcs((double2 *)p + 1, make_double2(v[2], v[3]));
+  }
+};
+template <> struct VecStore<float, 8> {
+  static SDE_D void st(float *p, const float *v) {
+    __stcs((float4 *)p, make_float4(v[0], v[1], v[2], v[3]));
+    __stcs((float4 *)p + 1, make_float4(v[4], v[5], v[6], v[7]));
+  }
+};
 
 template <class Model, typename T, int SCHEME>
 SDE_D void simulate_soa_body(const sde_args &a) {
-  constexpr int D = Model::D, M = Model::M, VEC = 16 / (int)sizeof(T);
+  constexpr int D = Model::D, M = Model::M, VEC = SDE_SOA_VEC;
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
   load_tables<T>(s_tab, a.noise_var);
@@ -668,7 +680,8 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   const int nlive = (int)((a.npaths - k0) < VEC ? (a.npaths - k0) : VEC);
   T *out = (T *)a.out;
   const int64_t ld = a.ld_paths, col = a.path_off + k0;
-  const bool vec_ok = nlive == VEC && ((ld % VEC) == 0) && ((col % VEC) == 0) &&
+  constexpr int ALN = 16 / (int)sizeof(T);  // 16-byte store alignment in elements
+  const bool vec_ok = nlive == VEC && ((ld % ALN) == 0) && ((col % ALN) == 0) &&
                       ((((uint64_t)out) & 15u) == 0);
   T x[VEC][SDE_MAXD];
 #pragma unroll
