@@ -98,6 +98,9 @@ int sdeb200_synchronize(void);
 double sdeb200_last_kernel_ms(void);       /* CUDA-event time of the path kernels of the last call */
 int64_t sdeb200_launch_count(void);        /* kernels launched by this library so far */
 int sdeb200_measure_peak(int precision, double *tflops, double *ms); /* FMA-chain micro-benchmark */
+int sdeb200_set_tma(int enabled);          /* tuning switch: 0 routes the trajectory kernels that have a TMA (tensor-tile)
+                                              form to their plain shared-memory-tile form; returns the previous value */
+int64_t sdeb200_tma_launch_count(void);    /* launches of TMA kernels so far (tests assert that the path was taken) */
 
 /* ---- models: what `@sde_model` produces (src/models/codegen.jl:87-159) ---- */
 /* Parse the equations, build drift / diffusion (correlation Cholesky folded in, codegen.jl:105-112) and emit

@@ -40,6 +40,15 @@ def launch_count():
     return _lib.lib().sdeb200_launch_count()
 
 
+def set_tma(enabled):
+    """Tuning switch: False routes trajectory kernels with a TMA (tensor-tile) form to the plain tile kernels."""
+    return bool(_lib.lib().sdeb200_set_tma(1 if enabled else 0))
+
+
+def tma_launch_count():
+    return _lib.lib().sdeb200_tma_launch_count()
+
+
 def set_stream(cuda_stream_ptr):
     _lib.check(_lib.lib().sdeb200_set_stream(cuda_stream_ptr))
 

@@ -43,7 +43,9 @@ template <int DIM> struct WienerN {
   T.simref[s][0] = (const void *)sdek_##TAG##_simref_##SNAME##_f64;                    \
   T.simref[s][1] = (const void *)sdek_##TAG##_simref_##SNAME##_f32;                    \
   T.simw[s][0] = (const void *)sdek_##TAG##_simw_##SNAME##_f64;                        \
-  T.simw[s][1] = (const void *)sdek_##TAG##_simw_##SNAME##_f32;
+  T.simw[s][1] = (const void *)sdek_##TAG##_simw_##SNAME##_f32;                        \
+  T.simwt[s][0] = (const void *)sdek_##TAG##_simwt_##SNAME##_f64;                      \
+  T.simwt[s][1] = (const void *)sdek_##TAG##_simwt_##SNAME##_f32;
 #define XCOEFFILL(T, TAG) XCOEFFILL2(T, TAG)
 #define XCOEFFILL2(T, TAG)                              \
   T.coef = (const void *)sdek_##TAG##_coef;             \

@@ -3,11 +3,13 @@
 // (AOT for the built-in functors, NVRTC for @sde_model-generated ones), the exact accumulator's host half,
 // and the NCCL communicator (one process per GPU).  No compute happens on the CPU: every driver launches
 // the kernels of sde_device.cuh and fails with SDEB200_E_CUDA when no device is available.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -452,6 +454,53 @@ static size_t simw_smem(int D, int M, int precision) {
   const int wld = (ts * mw) | 1, xld = (ts * D) | 1;
   return (size_t)(SDE_BLOCK / 32) * 32 * (wld + xld) * esize(precision);
 }
+static bool g_tma_enabled = getenv("SDEB200_NO_TMA") == nullptr;
+static int64_t g_tma_launches = 0;
+extern "C" int sdeb200_set_tma(int enabled) {
+  const int prev = g_tma_enabled ? 1 : 0;
+  g_tma_enabled = enabled != 0;
+  return prev;
+}
+extern "C" int64_t sdeb200_tma_launch_count(void) { return g_tma_launches; }
+
+// Wiener-driven kernel on TMA tensor tiles (simulate_wiener_tma_body): per warp a ring of SDE_SIMWT_STAGES 4 KB tiles
+static size_t simwt_smem() { return (size_t)(SDE_BLOCK / 32) * SDE_SIMWT_STAGES * (4096 + 8) + 1024; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int tmap_encoder(tmap_encode_fn *out) {
+  static tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    if (!p || qr != cudaDriverEntryPointSuccess) return fail(SDEB200_E_CUDA, "the driver has no cuTensorMapEncodeTiled");
+    fn = (tmap_encode_fn)p;
+  }
+  *out = fn;
+  return 0;
+}
+// Tensor map of a trajectory buffer in reference order [path][row][D]: g paths per map row (sde_args.h), boxes of
+// (32/g map rows) x (128 bytes), 128-byte shared-memory swizzle.  npaths must be a multiple of g.
+static_assert(sizeof(sde_tmap) == sizeof(CUtensorMap) && alignof(sde_tmap) == alignof(CUtensorMap), "sde_tmap mirrors CUtensorMap");
+static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, int64_t nrows, int64_t npaths, int g) {
+  tmap_encode_fn enc = nullptr;
+  int rc = tmap_encoder(&enc);
+  if (rc) return rc;
+  const size_t es = precision == SDEB200_F64 ? 8 : 4;
+  const cuuint64_t dims[2] = {(cuuint64_t)g * nrows * D, (cuuint64_t)(npaths / g)};
+  const cuuint64_t strides[1] = {(cuuint64_t)g * nrows * D * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)(32 / g)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap *)tm, precision == SDEB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SDEB200_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 static int64_t simref_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SIMREF_PW); }
 
 static bool is_device_ptr(const void *p) {
@@ -687,6 +736,41 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
 // ---------------------------------------------------------------------------------------------------
 // simulate! driven by a Wiener path
 // ---------------------------------------------------------------------------------------------------
+// One Wiener-driven launch over device buffers: the TMA kernel where its tiles apply (D == M, D*sizeof(T) | 128,
+// 16-byte aligned buffers, paths of at least two tiles), the plain tile kernel for everything else and for the
+// npaths % g leftover paths.  `a` carries everything but npaths / out / out2.
+static int launch_simw(const sde_ktable *kt, const sdeb200_model *m, const sdeb200_opts *o, sde_args a, int64_t nrows,
+                       int64_t npaths, const void *w, void *x, cudaStream_t st) {
+  const int MW = m->M > 0 ? m->M : 1, D = m->D;
+  const size_t es = esize(o->precision);
+  const int rowb = (int)(D * es);
+  const void *kt_tma = kt->simwt[o->scheme][o->precision], *k = kt->simw[o->scheme][o->precision];
+  int rc;
+  int64_t done = 0;
+  if (kt_tma && g_tma_enabled && D == MW && 128 % rowb == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)x % 16) == 0 &&
+      nrows >= 2 * (128 / rowb) + 4 && nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
+    const int g = sde_tma_group((int64_t)nrows * rowb);
+    const int64_t ncov = npaths - npaths % g;
+    if (ncov >= 32) {
+      a.npaths = ncov;
+      a.out = x;
+      a.out2 = (void *)w;
+      if ((rc = make_traj_tmap(&a.tm_w, w, o->precision, D, nrows, ncov, g))) return rc;
+      if ((rc = make_traj_tmap(&a.tm_x, x, o->precision, D, nrows, ncov, g))) return rc;
+      if ((rc = launch(kt_tma, cdiv(ncov, SDE_BLOCK), &a, st, simwt_smem()))) return rc;
+      g_tma_launches++;
+      done = ncov;
+    }
+  }
+  if (done < npaths) {
+    a.npaths = npaths - done;
+    a.out = (char *)x + (size_t)done * nrows * D * es;
+    a.out2 = (char *)w + (size_t)done * nrows * MW * es;
+    if ((rc = launch(k, cdiv(npaths - done, SDE_BLOCK), &a, st, simw_smem(m->D, m->M, o->precision)))) return rc;
+  }
+  return 0;
+}
+
 extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, const double *params,
                                        const double *x0, int64_t nrows, int64_t npaths, const void *w, void *x) {
   int rc = check_common(m, o, params, x0);
@@ -701,17 +785,13 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
   if (npaths == 0) return SDEB200_OK;
   cudaStream_t st = g.stream();
   const size_t es = esize(o->precision);
-  const void *k = kt->simw[o->scheme][o->precision];
   sde_args a;
   fill_args(&a, m, o, params, x0);
   a.nsteps = nrows - 1;
   const bool wdev = is_device_ptr(w), xdev = is_device_ptr(x);
   if ((rc = timed_begin())) return rc;
   if (wdev && xdev) {
-    a.npaths = npaths;
-    a.out = x;
-    a.out2 = (void *)w;
-    if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, simw_smem(m->D, m->M, o->precision)))) return rc;
+    if ((rc = launch_simw(kt, m, o, a, nrows, npaths, w, x, st))) return rc;
   } else {
     const size_t wb = (size_t)nrows * MW * es, xb = (size_t)nrows * m->D * es;
     int64_t slab = (int64_t)((size_t)(128u << 20) / std::max(wb, xb));
@@ -722,11 +802,7 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
       const int64_t n = std::min<int64_t>(slab, npaths - s0);
       const void *wsrc = (const char *)w + (size_t)s0 * wb;
       CU(cudaMemcpyAsync(g.win[0].p, wsrc, (size_t)n * wb, wdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-      sde_args b = a;
-      b.npaths = n;
-      b.out = g.slab[0].p;
-      b.out2 = g.win[0].p;
-      if ((rc = launch(k, cdiv(n, SDE_BLOCK), &b, st, simw_smem(m->D, m->M, o->precision)))) return rc;
+      if ((rc = launch_simw(kt, m, o, a, nrows, n, g.win[0].p, g.slab[0].p, st))) return rc;
       CU(cudaMemcpyAsync((char *)x + (size_t)s0 * xb, g.slab[0].p, (size_t)n * xb,
                          xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
@@ -1102,20 +1178,13 @@ extern "C" int sdeb200_mlmc_simulate_level(sdeb200_model *m, const sdeb200_opts 
   if ((rc = wiener_device(&of, m->D, nf, npaths, o->path_offset, dxf, st))) return rc;
   sde_launch_subsample(o->precision, dxf, dxc, npaths, nc, nf, substeps, m->D, st);
   g.launches++;
-  const void *k = kt->simw[o->scheme][o->precision];
   sde_args a;
   fill_args(&a, m, &of, params, x0);
-  a.npaths = npaths;
   a.nsteps = nf - 1;
-  a.out = dxf;
-  a.out2 = dxf;
-  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, simw_smem(m->D, m->M, o->precision)))) return rc;
+  if ((rc = launch_simw(kt, m, o, a, nf, npaths, dxf, dxf, st))) return rc;
   fill_args(&a, m, o, params, x0);
-  a.npaths = npaths;
   a.nsteps = nc - 1;
-  a.out = dxc;
-  a.out2 = dxc;
-  if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, simw_smem(m->D, m->M, o->precision)))) return rc;
+  if ((rc = launch_simw(kt, m, o, a, nc, npaths, dxc, dxc, st))) return rc;
   if (!fdev) CU(cudaMemcpyAsync(xf, dxf, fb, cudaMemcpyDeviceToHost, st));
   if (!cdev) CU(cudaMemcpyAsync(xc, dxc, cb, cudaMemcpyDeviceToHost, st));
   return timed_end();

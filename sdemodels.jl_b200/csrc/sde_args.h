@@ -40,6 +40,37 @@ typedef long long int64_t;
 #define SDE_LAYOUT_REFERENCE 0 /* [path][time][D]  == Julia Array{SVector{D}}(nsteps+1, npaths)   */
 #define SDE_LAYOUT_SOA 1       /* [time][D][path]  coalesced device layout */
 
+/* a CUtensorMap (TMA descriptor), opaque to device code; built by the host with cuTensorMapEncodeTiled */
+typedef struct {
+#if defined(__cplusplus)
+  alignas(64)
+#endif
+  unsigned long long v[16];
+} sde_tmap;
+
+/* Geometry of the TMA trajectory tiles (device: sde_device.cuh, host: the tensor maps in sde_api.cu).  A tensor
+ * map's strides must be multiples of 16 bytes but the path pitch nrows*D*sizeof(T) usually is not, so g = 1, 2 or 4
+ * consecutive paths form one row of the map; the box of sub-path j starts at the first time row h_j whose
+ * address is 16-byte aligned (TMA box starts must be). */
+#if defined(__CUDACC__)
+#define SDE_ARGS_HD __host__ __device__ static inline
+#else
+#define SDE_ARGS_HD static inline
+#endif
+SDE_ARGS_HD int sde_tma_group(int64_t pitch_bytes) {
+  int g = 1;
+  while ((g * pitch_bytes) % 16) g *= 2;
+  return g; /* the pitch is a multiple of sizeof(T) >= 4, hence g <= 4 */
+}
+SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb) {
+  int h = 0;
+  while (((int64_t)j * pitch_bytes + (int64_t)h * rowb) % 16) h++;
+  return h;
+}
+#ifndef SDE_SIMWT_STAGES
+#define SDE_SIMWT_STAGES 6 /* ring depth of the TMA Wiener-driven kernel: 4 KB per stage and warp */
+#endif
+
 typedef struct {
   double params[SDE_MAXP];
   double x0[SDE_MAXD];
@@ -62,6 +93,8 @@ typedef struct {
   unsigned long long *nonfinite; /* number of paths that ended non-finite (reference: DomainError) */
   int64_t ld_paths;  /* SoA layout: leading dimension (total paths of the buffer) */
   int64_t path_off;  /* SoA layout: column offset of this launch inside the buffer */
+  /* TMA trajectory kernels only: tensor maps of the w (input) and x (output) buffers in reference order */
+  sde_tmap tm_w, tm_x;
 } sde_args;
 
 #endif

@@ -921,6 +921,210 @@ SDE_D void simulate_wiener_body(const sde_args &a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// TMA / mbarrier primitives (inline PTX, sm_90+): tensor tiles global <-> shared, completion on an mbarrier
+// (loads) or a bulk async-group (stores).  SASS: UTMALDG / UTMASTG / SYNCS.
+// ---------------------------------------------------------------------------------------------------
+SDE_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SDE_D void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+SDE_D void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+SDE_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+SDE_D void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+}
+SDE_D void tma_load_2d(uint32_t dst, const sde_tmap *tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+SDE_D void tma_store_2d(const sde_tmap *tm, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+SDE_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> SDE_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+SDE_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Cooperative load / store of a warp's ragged tail tile [32 paths][ROW] (not unrolled: it runs once per warp).
+// The store writes row r only from column cstart[r % g] on: the columns before belong to time rows that were
+// already written by TMA stores.
+template <typename T, int ROW, int LD>
+SDE_D void tail_tile_load(T *tile, const T *g, int64_t gstride, int nlive, int ncols, int lane) {
+#pragma unroll 4
+  for (int k = 0; k < ROW; k++) {
+    const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW;
+    if (r < nlive && c < ncols) tile[r * LD + c] = __ldcs(g + r * gstride + c);
+  }
+}
+template <typename T, int ROW, int LD>
+SDE_D void tail_tile_store(const T *tile, T *g, int64_t gstride, int nlive, int ncols, int cs0, int cs1, int cs2, int cs3, int gm1,
+                           int lane) {
+#pragma unroll 4
+  for (int k = 0; k < ROW; k++) {
+    const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW, j = r & gm1;
+    const int cs = j == 0 ? cs0 : (j == 1 ? cs1 : (j == 2 ? cs2 : cs3));
+    if (r < nlive && c < ncols && c >= cs) __stcs(g + r * gstride + c, tile[r * LD + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3t Wiener-driven trajectories on TMA tensor tiles (the HBM-bound kernel of the path; same semantics as K3):
+//     a warp owns 32 paths; its lane 0 moves tiles of w global -> shared through a ring of SDE_SIMWT_STAGES stages
+//     (one mbarrier per stage, SDE_SIMWT_STAGES - 2 loads in flight), every lane integrates its own path IN PLACE in
+//     the swizzled tile (16-byte shared-memory accesses, conflict-free), lane 0 stores the tile to x.  A tile is
+//     complete in shared memory before any of it is stored => x === w is safe.  Rows before the first aligned row
+//     of a path (h_j <= 3) use plain accesses; the rows after the last full tile go through one cooperative
+//     shared-memory tile (tile_load / tile_store_from).  Needs D == M (eltype(x) == eltype(w)) and D*sizeof(T) | 128;
+//     the host routes everything else, unaligned buffers, short paths and the npaths % g leftover to K3.
+// ---------------------------------------------------------------------------------------------------
+template <class Model, typename T, int SCHEME>
+SDE_D void simulate_wiener_tma_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M, MW = (M > 0 ? M : 1);
+  constexpr int ROWB = D * (int)sizeof(T);
+  constexpr bool OK = (D == MW) && (128 % ROWB == 0);
+  if (!OK) return;
+  constexpr int NST = SDE_SIMWT_STAGES;
+  constexpr int TS = 128 / ROWB;                          // rows per tile
+  constexpr int GB = ROWB > 16 ? ROWB : 16;               // bytes per register group
+  constexpr int G = GB / ROWB > 0 ? GB / ROWB : 1, GQ = GB / 16, NG = 128 / GB;
+  constexpr int TILE = 32 * 128;
+  constexpr int HMAX = 16 / (int)sizeof(T) - 1;           // bound on the head rows h_j
+  constexpr int TROW = (TS + HMAX) * D, TLD = TROW | 1;   // the cooperative tail tile [32][TLD] (fits in two stages)
+  static_assert(!OK || 32 * TLD * (int)sizeof(T) <= 2 * TILE, "tail tile does not fit");
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);  // the swizzle is a function of the address
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *tiles = smem + (size_t)wid * (NST * TILE);
+  uint64_t *bars = (uint64_t *)(smem + (size_t)(SDE_BLOCK / 32) * (NST * TILE)) + wid * NST;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++) mbar_init(smem_u32(bars + s), 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const int64_t wbase = ((int64_t)blockIdx.x * (SDE_BLOCK / 32) + wid) * 32;   // a.npaths is a multiple of g
+  if (wbase >= a.npaths) return;
+  const int nrows = (int)(a.nsteps + 1);
+  const int64_t pitch = (int64_t)nrows * ROWB;
+  const int g = sde_tma_group(pitch), rpb = 32 / g;
+  // head rows of the g sub-paths (scalars, not an indexed array: no local memory)
+  const int h0 = 0, h1 = g > 1 ? sde_tma_head(1, pitch, ROWB) : 0, h2 = g > 2 ? sde_tma_head(2, pitch, ROWB) : 0,
+            h3 = g > 2 ? sde_tma_head(3, pitch, ROWB) : 0;
+  auto hh = [&](int j) { return j == 0 ? h0 : (j == 1 ? h1 : (j == 2 ? h2 : h3)); };
+  const int h12 = h1 > h2 ? h1 : h2, hmax = h12 > h3 ? h12 : h3;
+  const int ntile = nrows > hmax ? (nrows - hmax) / TS : 0;
+  const int r = (lane % rpb) * g + lane / rpb;        // lane <-> tile row `lane` <-> path wbase + r
+  const int h = hh(lane / rpb);
+  const int64_t p = wbase + r;
+  const bool live = p < a.npaths;
+  const int c1 = (int)(wbase / g);
+  const sde_tmap *tmw = &a.tm_w, *tmx = &a.tm_x;
+  auto issue_load = [&](int k) {  // lane 0
+    if (k < ntile) {
+      const int s = k % NST;
+      const uint32_t bar = smem_u32(bars + s);
+      mbar_expect_tx(bar, TILE);
+      for (int j = 0; j < g; j++)
+        tma_load_2d(smem_u32(tiles + s * TILE + j * rpb * 128), tmw, j * nrows * D + (hh(j) + k * TS) * D, c1, bar);
+    }
+  };
+  if (lane == 0)
+    for (int k = 0; k < NST - 2; k++) issue_load(k);
+
+  Consts<T> cst;
+  T prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
+  const T dt = (T)a.dt, t0 = (T)a.t0;
+  Model::prepare(prm, dt, cst.c);
+  const T *wp = (const T *)a.out2 + p * (int64_t)nrows * D;
+  T *xp = (T *)a.out + p * (int64_t)nrows * D;
+  T x[SDE_MAXD], wprev[D], dw[D];
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
+#pragma unroll
+  for (int d = 0; d < D; d++) wprev[d] = (T)0;
+  // one row of the path: v[] holds w[row] on entry and x[row] on exit
+  auto row_step = [&](int row, T *v) {
+    if (row == 0) {
+#pragma unroll
+      for (int d = 0; d < D; d++) wprev[d] = v[d];
+    } else {
+      const T t = t0 + (T)(row - 1) * dt;
+#pragma unroll
+      for (int d = 0; d < D; d++) { dw[d] = v[d] - wprev[d]; wprev[d] = v[d]; }
+      Model::template step<SCHEME>(cst.c, t, dt, dw, x);
+    }
+#pragma unroll
+    for (int d = 0; d < D; d++) v[d] = x[d];
+  };
+  if (live)
+    for (int row = 0; row < h && row < nrows; row++) {   // head rows before the first aligned row
+      T v[D];
+#pragma unroll
+      for (int d = 0; d < D; d++) v[d] = wp[(int64_t)row * D + d];
+      row_step(row, v);
+#pragma unroll
+      for (int d = 0; d < D; d++) xp[(int64_t)row * D + d] = v[d];
+    }
+  const int sw = lane & 7;
+  for (int k = 0; k < ntile; k++) {
+    if (lane == 0) {
+      bulk_wait_read<1>();  // the stage tile k + NST - 2 goes into was stored from at iteration k - 2
+      issue_load(k + NST - 2);
+    }
+    const int s = k % NST;
+    mbar_wait(smem_u32(bars + s), (uint32_t)((k / NST) & 1));
+    unsigned char *trow = tiles + s * TILE + lane * 128;
+    if (live) {
+      const int row0 = h + k * TS;
+#pragma unroll
+      for (int gi = 0; gi < NG; gi++) {
+        union { uint4 q[GQ]; T v[G * D]; } u;
+#pragma unroll
+        for (int c = 0; c < GQ; c++) u.q[c] = *(const uint4 *)(trow + (((gi * GQ + c) ^ sw) << 4));
+#pragma unroll
+        for (int i = 0; i < G; i++) row_step(row0 + gi * G + i, u.v + i * D);
+#pragma unroll
+        for (int c = 0; c < GQ; c++) *(uint4 *)(trow + (((gi * GQ + c) ^ sw) << 4)) = u.q[c];
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      for (int j = 0; j < g; j++)
+        tma_store_2d(tmx, j * nrows * D + (hh(j) + k * TS) * D, c1, smem_u32(tiles + s * TILE + j * rpb * 128));
+      bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();   // the ring is free again (and must outlive the stores' reads)
+  __syncwarp();
+  // rows past the last full tile: one cooperative tile over rows [T0, nrows) of the warp's paths (natural order)
+  const int T0 = ntile * TS, ncols = (nrows - T0) * D;
+  if (ncols > 0) {
+    const int64_t rem = a.npaths - wbase;
+    const int nlive = (int)(rem < 32 ? rem : 32);
+    T *tt = (T *)tiles;
+    tail_tile_load<T, TROW, TLD>(tt, (const T *)a.out2 + (wbase * nrows + T0) * D, (int64_t)nrows * D, nlive, ncols, lane);
+    __syncwarp();
+    if (live)
+      for (int row = T0 + h; row < nrows; row++) row_step(row, tt + r * TLD + (row - T0) * D);
+    __syncwarp();
+    tail_tile_store<T, TROW, TLD>(tt, (T *)a.out + (wbase * nrows + T0) * D, (int64_t)nrows * D, nlive, ncols, h0 * D, h1 * D, h2 * D,
+                                  h3 * D, g - 1, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K7  logtransition(model, ::EulerMaruyama, times, data)  [schemes.jl:64-76, euler_maruyama.jl:8-13]:
 //     Gaussian one-step log-densities along stored trajectories, x (a.out2) [path][row][D] -> a.out [path][row-1].
 //     Streaming and HBM-bound (D reads, 1 write per transition); same tile staging as K3.  The arithmetic is done
@@ -1067,7 +1271,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMW_MINBLOCKS) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }
+      const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simwt_##SNAME##_##PNAME(                 \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_tma_body<MODEL, T, SCH>(a); }
 
 // Exact one-step samplers exist for a few models only and have no Wiener-driven or coupled form
 // (src/simulation.jl:50-57,78-89): terminal and full-trajectory kernels, scheme id 3.

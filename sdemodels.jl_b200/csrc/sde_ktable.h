@@ -9,6 +9,7 @@ typedef struct {
   const void *simsoa[4][2];
   const void *simref[4][2];
   const void *simw[4][2];
+  const void *simwt[4][2]; /* Wiener-driven on TMA tensor tiles (null: not applicable) */
   const void *logt[2]; /* [precision] */
   const void *coef;
 } sde_ktable;

@@ -92,6 +92,58 @@ def test_wiener_driven_in_place(gpu, O):
     assert np.array_equal(buf, ref)
 
 
+TMA_SHAPES = [  # (model, npaths, nrows): ragged tails, head rows (odd pitch), leftover paths (npaths % g), partial warps
+    ("BlackScholes", 257, 513), ("BlackScholes", 1000, 253), ("BlackScholes", 64, 40), ("BlackScholes", 33, 512),
+    ("BlackScholes", 95, 37), ("Heston", 257, 129), ("Heston", 100, 41), ("Heston", 32, 24),
+]
+
+
+@pytest.mark.parametrize("name,npaths,nrows", TMA_SHAPES)
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_wiener_driven_tma_tiles(gpu, O, name, npaths, nrows, precision, inplace):
+    """The TMA tensor-tile form of simulate!(x, model, scheme, t0, x0, w) (K3t): STRICT FP64 bit-identical to the
+    oracle, every precision bit-identical to the plain tile kernel (K3) on the same input, device buffers inside
+    guard zones (no stray TMA stores), x === w and x !== w."""
+    import torch
+    params, x0 = (BS_P, 100.0) if name == "BlackScholes" else (HESTON_P, [100.0, 0.4])
+    D = 1 if name == "BlackScholes" else 2
+    nsteps = nrows - 1
+    dt = 1.0 / nsteps
+    w = wiener_paths(O, npaths, nsteps, D, dt, 11)
+    ref = O.simulate_wiener(name, EM, params, 0.0, dt, x0, w)
+    tdt = torch.float64 if precision == "f64" else torch.float32
+    G = 1024
+    shape = (npaths, nrows, D) if D > 1 else (npaths, nrows)
+    n = int(np.prod(shape))
+
+    def guarded():
+        full = torch.full((n + 2 * G,), -7.0, dtype=tdt, device="cuda")
+        return full[G:G + n].view(*shape), full
+
+    def run(tma):
+        gpu.set_tma(tma)
+        try:
+            wd, fw = guarded()
+            wd.copy_(torch.from_numpy(np.ascontiguousarray(w[..., 0] if D == 1 else w)).to(tdt))
+            xd, fx = (wd, fw) if inplace else guarded()
+            c0 = gpu.tma_launch_count()
+            gpu.simulate_(xd, _model(gpu, name, params), gpu.EulerMaruyama(dt), 0.0, x0, wd, math="strict")
+            torch.cuda.synchronize()
+            for f in (fw, fx):
+                assert bool((f[:G] == -7.0).all() and (f[-G:] == -7.0).all()), "guard zone overwritten"
+            return xd.cpu().numpy().reshape(npaths, nrows, D), gpu.tma_launch_count() - c0
+        finally:
+            gpu.set_tma(True)
+
+    x_tma, n_tma = run(True)
+    x_old, n_old = run(False)
+    assert n_old == 0 and n_tma == (1 if nrows >= 2 * (128 // (D * (8 if precision == "f64" else 4))) + 4 and npaths >= 32 else 0)
+    assert np.array_equal(x_tma, x_old)
+    if precision == "f64":
+        assert np.array_equal(x_tma, ref)
+
+
 @pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
 @pytest.mark.parametrize("math", ["fast", "strict"])
 def test_sample_matches_oracle_on_the_same_normal_stream(gpu, O, name, params, x0, sid, nsteps, math):
