@@ -14,9 +14,13 @@ namespace sdeb200 {
 template <int DIM> struct WienerN {
   static constexpr int D = DIM, M = DIM, NP = 0;
   template <typename T> SDE_HD static void prepare(const T *, T, T *) {}
-  template <int SCHEME, typename T> SDE_HD static void step(const T *, T, T, const T *dw, T *x) {
+  // w[i] = w[i-1] + sqrt(Δt)*z with the product and the sum rounded separately, as the reference does: the add is
+  // never contracted into the generator's last multiply, so every kernel form writes the same bits in FAST math too.
+  SDE_D static double add_rn(double a, double b) { return __dadd_rn(a, b); }
+  SDE_D static float add_rn(float a, float b) { return __fadd_rn(a, b); }
+  template <int SCHEME, typename T> SDE_D static void step(const T *, T, T, const T *dw, T *x) {
 #pragma unroll
-    for (int d = 0; d < DIM; d++) x[d] = x[d] + dw[d];
+    for (int d = 0; d < DIM; d++) x[d] = add_rn(x[d], dw[d]);
   }
 };
 }  // namespace sdeb200
@@ -42,6 +46,8 @@ template <int DIM> struct WienerN {
   T.simsoa[s][1] = (const void *)sdek_##TAG##_simsoa_##SNAME##_f32;                    \
   T.simref[s][0] = (const void *)sdek_##TAG##_simref_##SNAME##_f64;                    \
   T.simref[s][1] = (const void *)sdek_##TAG##_simref_##SNAME##_f32;                    \
+  T.simrt[s][0] = (const void *)sdek_##TAG##_simrt_##SNAME##_f64;                      \
+  T.simrt[s][1] = (const void *)sdek_##TAG##_simrt_##SNAME##_f32;                      \
   T.simw[s][0] = (const void *)sdek_##TAG##_simw_##SNAME##_f64;                        \
   T.simw[s][1] = (const void *)sdek_##TAG##_simw_##SNAME##_f32;                        \
   T.simwt[s][0] = (const void *)sdek_##TAG##_simwt_##SNAME##_f64;                      \
@@ -65,7 +71,9 @@ XCOEF(BlackScholes, TAGGED(bs))
   T.simsoa[3][0] = (const void *)sdek_##TAG##_simsoa_exact_f64;          \
   T.simsoa[3][1] = (const void *)sdek_##TAG##_simsoa_exact_f32;          \
   T.simref[3][0] = (const void *)sdek_##TAG##_simref_exact_f64;          \
-  T.simref[3][1] = (const void *)sdek_##TAG##_simref_exact_f32;
+  T.simref[3][1] = (const void *)sdek_##TAG##_simref_exact_f32;          \
+  T.simrt[3][0] = (const void *)sdek_##TAG##_simrt_exact_f64;            \
+  T.simrt[3][1] = (const void *)sdek_##TAG##_simrt_exact_f32;
 XEXACT(BlackScholes, TAGGED(bs))
 XSCHEME(OrnsteinUhlenbeck, TAGGED(ou), 0, em)
 XSCHEME(OrnsteinUhlenbeck, TAGGED(ou), 1, mil)
@@ -82,6 +90,12 @@ XCOEF(Heston, TAGGED(heston))
   }                                                                                                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_f32(const __grid_constant__ sde_args a) { \
     sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, float, 0>(a);                                          \
+  }                                                                                                          \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##t_f64(const __grid_constant__ sde_args a) { \
+    sdeb200::simulate_ref_tma_body<sdeb200::WienerN<DIM>, double, 0>(a);                                     \
+  }                                                                                                          \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##t_f32(const __grid_constant__ sde_args a) { \
+    sdeb200::simulate_ref_tma_body<sdeb200::WienerN<DIM>, float, 0>(a);                                      \
   }
 XWIENER(1, TAGGED(wiener1))
 XWIENER(2, TAGGED(wiener2))
@@ -119,7 +133,20 @@ extern "C" int SDE_AOT_TABLE(int model, sde_ktable *t) {
 // wiener kernels [dim-1][precision]
 #define XW(TAG, P) XW2(TAG, P)
 #define XW2(TAG, P) (const void *)sdek_##TAG##_##P
+#define XWT(TAG, P) XWT2(TAG, P)
+#define XWT2(TAG, P) (const void *)sdek_##TAG##t_##P
 extern "C" const void *SDE_AOT_WIENER(int dim, int precision) {
+  if (dim >= 16) {  // + 16: the TMA tensor-store form (dim 3 has none: 3*sizeof(T) does not divide 128)
+    switch ((dim - 16) * 2 + precision) {
+      case 2: return XWT(TAGGED(wiener1), f64);
+      case 3: return XWT(TAGGED(wiener1), f32);
+      case 4: return XWT(TAGGED(wiener2), f64);
+      case 5: return XWT(TAGGED(wiener2), f32);
+      case 8: return XWT(TAGGED(wiener4), f64);
+      case 9: return XWT(TAGGED(wiener4), f32);
+    }
+    return 0;
+  }
   switch (dim * 2 + precision) {
     case 2: return XW(TAGGED(wiener1), f64);
     case 3: return XW(TAGGED(wiener1), f32);

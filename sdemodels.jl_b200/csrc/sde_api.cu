@@ -501,6 +501,45 @@ static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, 
   return 0;
 }
 
+// reference-order trajectories with TMA tensor stores (simulate_ref_tma_body): per warp a ring of two 4 KB tiles
+static size_t simrt_smem() { return (size_t)(SDE_BLOCK / 32) * 2 * 4096 + 1024; }
+static int64_t simref_grid(int64_t npaths);
+static size_t simref_smem(int D, int precision);
+// One RNG-driven reference-order launch into a device buffer: the TMA-store kernel where its tiles apply
+// (D*sizeof(T) | 128, 16-byte aligned buffer, paths of at least two tiles), the shared-memory-tile kernel otherwise
+// and for the npaths % g leftover paths.  `a` carries everything but npaths / out (and path0 of the first path).
+static int launch_simref(const void *k, const void *k_tma, int D, int precision, sde_args a, int64_t npaths, void *out,
+                         cudaStream_t st) {
+  const size_t es = precision == SDEB200_F64 ? 8 : 4;
+  const int rowb = (int)(D * es);
+  const int64_t nrows = a.nsteps + 1;
+  int rc;
+  int64_t done = 0;
+  // measured (profiles/README.md): the tensor-store form wins for 8-byte rows (+5..19 %), the tile kernel for 4- and
+  // 16-byte rows (-3 %): route by row size
+  if (k_tma && g_tma_enabled && rowb == 8 && ((uintptr_t)out % 16) == 0 && nrows >= 2 * (128 / rowb) + 4 &&
+      nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
+    const int g = sde_tma_group(nrows * rowb);
+    const int64_t ncov = npaths - npaths % g;
+    if (ncov >= 32) {
+      sde_args b = a;
+      b.npaths = ncov;
+      b.out = out;
+      if ((rc = make_traj_tmap(&b.tm_x, out, precision, D, nrows, ncov, g))) return rc;
+      if ((rc = launch(k_tma, (ncov + SDE_BLOCK - 1) / SDE_BLOCK, &b, st, simrt_smem()))) return rc;
+      g_tma_launches++;
+      done = ncov;
+    }
+  }
+  if (done < npaths) {
+    a.npaths = npaths - done;
+    a.path0 += done;
+    a.out = (char *)out + (size_t)done * nrows * D * es;
+    if ((rc = launch(k, simref_grid(npaths - done), &a, st, simref_smem(D, precision)))) return rc;
+  }
+  return 0;
+}
+
 static int64_t simref_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SIMREF_PW); }
 
 static bool is_device_ptr(const void *p) {
@@ -682,19 +721,15 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
   const bool dev = is_device_ptr(out);
   if ((rc = timed_begin())) return rc;
   if (layout == SDEB200_LAYOUT_REFERENCE) {
-    const void *k = kt->simref[o->scheme][o->precision];
+    const void *k = kt->simref[o->scheme][o->precision], *k_tma = kt->simrt[o->scheme][o->precision];
     const size_t bpp = (size_t)nrows * m->D * es;
     if (dev) {
-      a.npaths = npaths;
-      a.out = out;
-      if ((rc = launch(k, simref_grid(npaths), &a, st, simref_smem(m->D, o->precision)))) return rc;
+      if ((rc = launch_simref(k, k_tma, m->D, o->precision, a, npaths, out, st))) return rc;
     } else {
       rc = run_slabs(npaths, bpp, out, [&](int64_t s0, int64_t n, void *d, cudaStream_t s) {
         sde_args b = a;
-        b.npaths = n;
         b.path0 = o->path_offset + s0;
-        b.out = d;
-        return launch(k, simref_grid(n), &b, s, simref_smem(m->D, o->precision));
+        return launch_simref(k, k_tma, m->D, o->precision, b, n, d, s);
       });
       if (rc) return rc;
     }
@@ -891,9 +926,9 @@ static int wiener_device(const sdeb200_opts *o, int dim, int64_t nrows, int64_t 
   a.stream = o->stream;
   a.path0 = path0;
   a.nsteps = nrows - 1;
-  a.npaths = npaths;
-  a.out = dev;
-  return launch(k, simref_grid(npaths), &a, st, simref_smem(dim, o->precision));
+  const void *k_tma = o->math == SDEB200_MATH_STRICT ? sde_aot_wiener_strict(16 + dim, o->precision)
+                                                     : sde_aot_wiener_fast(16 + dim, o->precision);
+  return launch_simref(k, k_tma, dim, o->precision, a, npaths, dev, st);
 }
 
 extern "C" int sdeb200_wiener(const sdeb200_opts *o, int dim, int64_t nrows, int64_t npaths, void *w) {

@@ -1125,6 +1125,184 @@ SDE_D void simulate_wiener_tma_body(const sde_args &a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2t full trajectories in the reference's order [path][time][D] with TMA tensor stores (same results as K2b):
+//     every lane owns a path and writes its rows into the 128-byte row of the warp's swizzled tile; when all lanes
+//     have filled tile k, lane 0 stores it with g tensor stores (geometry: sde_args.h) and the warp goes on
+//     filling the other stage — no cooperative store pass, no second trip through registers.  The box of sub-path
+//     j starts at time row h_j (first 16-byte aligned row), so lanes of different sub-paths are h_j rows out of
+//     phase inside the ring; rows before h_j and after the last full tile are plain (fire-and-forget) stores.
+//     Used by simulate (reference layout), the Exact samplers and wiener!.
+// ---------------------------------------------------------------------------------------------------
+#define SDE_SIMRT_STAGES 2
+// tile k of the warp is complete in shared memory: g tensor stores by lane 0 (rare: out of line)
+static __device__ __noinline__ void simrt_flush(const sde_tmap *tmx, uint32_t tiles_s, int g, int nrowsD, int tsD, int h1D, int h2D, int h3D,
+                                         int c1, int k) {
+  fence_async_smem();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t src = tiles_s + (uint32_t)(k % SDE_SIMRT_STAGES) * 4096u;
+    const int rpb128 = (32 / g) * 128;
+    for (int j = 0; j < g; j++) {
+      const int hD = j == 0 ? 0 : (j == 1 ? h1D : (j == 2 ? h2D : h3D));
+      tma_store_2d(tmx, j * nrowsD + hD + k * tsD, c1, src + (uint32_t)(j * rpb128));
+    }
+    bulk_commit();
+  }
+}
+// a lane is about to start writing a tile whose stage was used `SDE_SIMRT_STAGES` tiles ago: lane 0 waits until at
+// most `pending` tensor stores are still reading shared memory
+static __device__ __noinline__ void simrt_acquire(int pending) {
+  if ((threadIdx.x & 31) == 0) {
+    if (pending >= 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
+  }
+  __syncwarp();
+}
+
+template <class Model, typename T, int SCHEME>
+SDE_D void simulate_ref_tma_body(const sde_args &a) {
+  constexpr int D = Model::D, M = Model::M;
+  constexpr int ROWB = D * (int)sizeof(T);
+  constexpr bool OK = (128 % ROWB == 0);
+  constexpr int NSX = SDE_SIMRT_STAGES;
+  constexpr int TS = OK ? 128 / ROWB : 1;     // rows per tile (a power of two)
+  constexpr int TILE = 32 * 128;
+  static_assert(NSX == 2 && TILE == 4096, "ring arithmetic below assumes two 4 KB stages");
+  typedef Batch<T, M> B;
+  constexpr int U = B::U;
+  __shared__ double s_tab[TabSize<T>::value];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  load_tables<T>(s_tab, a.noise_var);
+  if (!OK) return;
+  unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *tiles = smem + (size_t)wid * (NSX * TILE);
+  PhiloxKeys ks;
+  philox_expand(a.seed_lo, a.seed_hi, ks);
+  Consts<T> cst;
+  T prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = i < Model::NP ? (T)a.params[i] : (T)0;
+  const T dt = (T)a.dt, t0 = (T)a.t0;
+  Model::prepare(prm, dt, cst.c);
+
+  const int64_t wbase = ((int64_t)blockIdx.x * (SDE_BLOCK / 32) + wid) * 32;   // a.npaths is a multiple of g
+  if (wbase >= a.npaths) return;
+  const int nrows = (int)(a.nsteps + 1);
+  const int64_t pitch = (int64_t)nrows * ROWB;
+  const int g = sde_tma_group(pitch), rpb = 32 / g;
+  const int h1 = g > 1 ? sde_tma_head(1, pitch, ROWB) : 0, h2 = g > 2 ? sde_tma_head(2, pitch, ROWB) : 0,
+            h3 = g > 2 ? sde_tma_head(3, pitch, ROWB) : 0;
+  const int h12 = h1 > h2 ? h1 : h2, hmax = h12 > h3 ? h12 : h3;
+  const int ntile = nrows > hmax ? (nrows - hmax) / TS : 0;
+  const int r = (lane % rpb) * g + lane / rpb;        // lane <-> tile row `lane` <-> path wbase + r
+  const int jl = lane / rpb;
+  const int h = jl == 0 ? 0 : (jl == 1 ? h1 : (jl == 2 ? h2 : h3));
+  const int64_t p = wbase + r;
+  const bool live = p < a.npaths;
+  const int c1 = (int)(wbase / g);
+  const sde_tmap *tmx = &a.tm_x;
+  T *xp = (T *)a.out + p * (int64_t)nrows * D;
+  const uint32_t swz = (uint32_t)(lane & 7) << 4;
+  unsigned char *trow = tiles + lane * 128;
+  const uint32_t tiles_s = smem_u32(tiles);
+  const int qend = ntile * TS;
+
+  T x[SDE_MAXD];
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
+
+  // warp-uniform ring state: tiles flushed so far, next tile a lane with h = 0 will start
+  int nflushed = 0, tbeg = 0;
+  // rows [i_first, i_last] are about to be written
+  auto begin_check = [&](int i_last) {
+    if (tbeg < ntile && tbeg * TS <= i_last) {
+      if (tbeg >= NSX) simrt_acquire(nflushed - (tbeg - NSX + 1));
+      tbeg++;
+    }
+  };
+  // rows up to i_last have been written
+  auto flush_check = [&](int i_last) {
+    if (nflushed < ntile && i_last >= (nflushed + 1) * TS - 1 + hmax) {
+      simrt_flush(tmx, tiles_s, g, nrows * D, TS * D, h1 * D, h2 * D, h3 * D, c1, nflushed);
+      nflushed++;
+    }
+  };
+  // store x as the row at byte offset `off` (0..255: stage bit 7, 128-byte swizzled row below) of this lane's ring
+  auto put = [&](uint32_t off) {
+    unsigned char *dst = trow + ((off & 128u) << 5);
+    const uint32_t o = (off & 127u) ^ swz;
+    if (ROWB % 16 == 0) {
+#pragma unroll
+      for (int c = 0; c < ROWB / 16; c++) {
+        union { uint4 q4; T v[16 / sizeof(T)]; } u;
+#pragma unroll
+        for (int e = 0; e < (int)(16 / sizeof(T)); e++) u.v[e] = x[c * (16 / sizeof(T)) + e];
+        *(uint4 *)(dst + (((off & 127u) + 16u * c) ^ swz)) = u.q4;
+      }
+    } else if (ROWB == 8) {
+      union { uint2 q2; T v[8 / sizeof(T)]; } u;
+#pragma unroll
+      for (int e = 0; e < (int)(8 / sizeof(T)); e++) u.v[e] = x[e];
+      *(uint2 *)(dst + o) = u.q2;
+    } else {
+      *(T *)(dst + o) = x[0];
+    }
+  };
+  // general row: ring, or plain store before the first aligned row / after the last full tile
+  auto emit_slow = [&](int i) {
+    begin_check(i);
+    const int q = i - h;
+    if (q >= 0 && q < qend) {
+      put((uint32_t)(q * ROWB) & 255u);
+    } else if (live) {
+#pragma unroll
+      for (int d = 0; d < D; d++) __stcs(xp + (int64_t)i * D + d, x[d]);
+    }
+    flush_check(i);
+  };
+
+  emit_slow(0);
+  const uint64_t gpath = (uint64_t)(a.path0 + p);
+  const int64_t nbatch = (a.nsteps + U - 1) / U;
+  auto slow_batch = [&](int64_t it) {
+    T dw[B::NZ];
+    gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int64_t i = it * U + u;
+      if (i < a.nsteps) {
+        const T t = t0 + (T)i * dt;
+        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x);
+        emit_slow((int)i + 1);
+      }
+    }
+  };
+  int64_t it = 0;
+  for (; it < nbatch && it * U + 1 < hmax; it++) slow_batch(it);          // until every lane is inside its ring
+  {
+    // steady state: all U rows of a batch go into the ring for every lane; bookkeeping once per batch
+    const int64_t it_end = (qend - 1) / U;                                  // rows (it+1)*U <= qend - 1
+    uint32_t off = (uint32_t)(((int)(it * U) + 1 - h) * ROWB) & 255u;
+    for (; it < it_end; it++) {
+      const int i_last = (int)(it * U) + U;
+      begin_check(i_last);
+      T dw[B::NZ];
+      gen_batch<T, M>(gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const T t = t0 + (T)(it * U + u) * dt;
+        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x);
+        put(off);
+        off = (off + ROWB) & 255u;
+      }
+      flush_check(i_last);
+    }
+  }
+  for (; it < nbatch; it++) slow_batch(it);                                 // rows after the last full tile
+  if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the stores' reads
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K7  logtransition(model, ::EulerMaruyama, times, data)  [schemes.jl:64-76, euler_maruyama.jl:8-13]:
 //     Gaussian one-step log-densities along stored trajectories, x (a.out2) [path][row][D] -> a.out [path][row-1].
 //     Streaming and HBM-bound (D reads, 1 write per transition); same tile staging as K3.  The arithmetic is done
@@ -1270,6 +1448,8 @@ SDE_D void coef_eval_body(const sde_args &a) {
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##_simrt_##SNAME##_##PNAME(                \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, SCH>(a); }                \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMW_MINBLOCKS) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }                  \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simwt_##SNAME##_##PNAME(                 \
@@ -1283,7 +1463,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_exact_##PNAME(                    \
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, 3>(a); }                      \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_exact_##PNAME(                 \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, 3>(a); }
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, 3>(a); }                      \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##_simrt_exact_##PNAME(                  \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, 3>(a); }
 
 #define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \
   SDE_KERNELS(MODEL, TAG, SCH, SNAME, double, f64)  \

@@ -8,6 +8,7 @@ typedef struct {
   const void *mlmc[4][2];
   const void *simsoa[4][2];
   const void *simref[4][2];
+  const void *simrt[4][2]; /* reference-order trajectories with TMA tensor stores */
   const void *simw[4][2];
   const void *simwt[4][2]; /* Wiener-driven on TMA tensor tiles (null: not applicable) */
   const void *logt[2]; /* [precision] */

@@ -144,6 +144,54 @@ def test_wiener_driven_tma_tiles(gpu, O, name, npaths, nrows, precision, inplace
         assert np.array_equal(x_tma, ref)
 
 
+@pytest.mark.parametrize("npaths,nrows", [(257, 513), (1000, 253), (64, 40), (33, 512), (95, 37), (4097, 65), (32, 300)])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_reference_order_trajectories_with_tma_stores(gpu, npaths, nrows, precision):
+    """simulate / wiener! / the Exact sampler in the reference's [path][time][D] order: the TMA tensor-store kernels
+    (K2t) write bit for bit what the shared-memory-tile kernels (K2b) write, inside guard zones, for ragged shapes."""
+    import torch
+    S = gpu
+    tdt = torch.float64 if precision == "f64" else torch.float32
+    G = 1024
+    nsteps = nrows - 1
+    dt = 1.0 / nsteps
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        full = torch.full((n + 2 * G,), -7.0, dtype=tdt, device="cuda")
+        return full[G:G + n].view(*shape), full
+
+    def intact(f):
+        return bool((f[:G] == -7.0).all() and (f[-G:] == -7.0).all())
+
+    he, bs = S.Heston(*HESTON_P), S.BlackScholes(*BS_P)
+    jobs = [
+        ("bs-milstein", 1, lambda v: S.simulate(bs, S.Milstein(dt), 0.0, 100.0, nsteps, npaths, seed=5, precision=precision, out=v, path_offset=3)),
+        ("heston-em", 2, lambda v: S.simulate(he, S.EulerMaruyama(dt), 0.0, [100.0, 0.4], nsteps, npaths, seed=6, precision=precision, out=v)),
+        ("bs-exact", 1, lambda v: S.simulate(bs, S.Exact(dt), 0.0, 100.0, nsteps, npaths, seed=7, precision=precision, out=v)),
+        ("wiener1", 1, lambda v: S.wiener_(v, dt, seed=8)),
+        ("wiener2", 2, lambda v: S.wiener_(v, dt, seed=9)),
+    ]
+    for tag, D, fn in jobs:
+        shape = (npaths, nrows, D) if D > 1 else (npaths, nrows)
+        res = []
+        for tma in (True, False):
+            S.set_tma(tma)
+            try:
+                v, f = guarded(shape)
+                c0 = S.tma_launch_count()
+                fn(v)
+                torch.cuda.synchronize()
+                assert intact(f), f"{tag}: guard zone overwritten (tma={tma})"
+                res.append((v.cpu().numpy().copy(), S.tma_launch_count() - c0))
+            finally:
+                S.set_tma(True)
+        rowb = D * (8 if precision == "f64" else 4)
+        assert res[1][1] == 0 and res[0][1] == (1 if rowb == 8 and nrows >= 2 * (128 // rowb) + 4 else 0), tag
+        assert np.array_equal(res[0][0], res[1][0]), tag
+        assert np.isfinite(res[0][0]).all(), tag
+
+
 @pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
 @pytest.mark.parametrize("math", ["fast", "strict"])
 def test_sample_matches_oracle_on_the_same_normal_stream(gpu, O, name, params, x0, sid, nsteps, math):
