@@ -100,6 +100,9 @@ int64_t sdeb200_launch_count(void);        /* kernels launched by this library s
 int sdeb200_measure_peak(int precision, double *tflops, double *ms); /* FMA-chain micro-benchmark */
 int sdeb200_set_tma(int enabled);          /* tuning switch: 0 routes the trajectory kernels that have a TMA (tensor-tile)
                                               form to their plain shared-memory-tile form; returns the previous value */
+int64_t sdeb200_set_sample1_max(int64_t npaths); /* tuning switch: terminal-value launches of at most this many paths use the
+                                              one-path-per-thread kernel form (default 262144; 0: never); returns the
+                                              previous value.  Results do not depend on it (bit-identical forms). */
 int64_t sdeb200_tma_launch_count(void);    /* launches of TMA kernels so far (tests assert that the path was taken) */
 
 /* ---- models: what `@sde_model` produces (src/models/codegen.jl:87-159) ---- */

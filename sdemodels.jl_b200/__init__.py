@@ -45,6 +45,11 @@ def set_tma(enabled):
     return bool(_lib.lib().sdeb200_set_tma(1 if enabled else 0))
 
 
+def set_sample1_max(npaths):
+    """Tuning switch: terminal-value launches of at most `npaths` paths use the one-path-per-thread kernel form."""
+    return _lib.lib().sdeb200_set_sample1_max(int(npaths))
+
+
 def tma_launch_count():
     return _lib.lib().sdeb200_tma_launch_count()
 

@@ -54,6 +54,7 @@ SYMBOLS = {
     "sdeb200_launch_count": (_I64, []),
     "sdeb200_set_tma": (_I, [_I]),
     "sdeb200_tma_launch_count": (_I64, []),
+    "sdeb200_set_sample1_max": (_I64, [_I64]),
     "sdeb200_measure_peak": (_I, [_I, _PD, _PD]),
     "sdeb200_model_create": (_I, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), _I, C.POINTER(_VP)]),
     "sdeb200_model_builtin": (_I, [C.c_char_p, C.POINTER(_VP)]),

@@ -40,6 +40,8 @@ template <int DIM> struct WienerN {
 #define XFILL2(T, TAG, s, SNAME)                                                      \
   T.sample[s][0] = (const void *)sdek_##TAG##_sample_##SNAME##_f64;                    \
   T.sample[s][1] = (const void *)sdek_##TAG##_sample_##SNAME##_f32;                    \
+  T.sample1[s][0] = (const void *)sdek_##TAG##_sample1_##SNAME##_f64;                  \
+  T.sample1[s][1] = (const void *)sdek_##TAG##_sample1_##SNAME##_f32;                  \
   T.mlmc[s][0] = (const void *)sdek_##TAG##_mlmc_##SNAME##_f64;                        \
   T.mlmc[s][1] = (const void *)sdek_##TAG##_mlmc_##SNAME##_f32;                        \
   T.simsoa[s][0] = (const void *)sdek_##TAG##_simsoa_##SNAME##_f64;                    \
@@ -68,6 +70,8 @@ XCOEF(BlackScholes, TAGGED(bs))
 #define XEXACTFILL2(T, TAG)                                              \
   T.sample[3][0] = (const void *)sdek_##TAG##_sample_exact_f64;          \
   T.sample[3][1] = (const void *)sdek_##TAG##_sample_exact_f32;          \
+  T.sample1[3][0] = (const void *)sdek_##TAG##_sample1_exact_f64;        \
+  T.sample1[3][1] = (const void *)sdek_##TAG##_sample1_exact_f32;        \
   T.simsoa[3][0] = (const void *)sdek_##TAG##_simsoa_exact_f64;          \
   T.simsoa[3][1] = (const void *)sdek_##TAG##_simsoa_exact_f32;          \
   T.simref[3][0] = (const void *)sdek_##TAG##_simref_exact_f64;          \

@@ -424,7 +424,7 @@ static int64_t capped(int64_t nchunks) { return std::min<int64_t>(nchunks, 148 *
 
 static inline size_t esize(int precision);
 static inline int64_t cdiv(int64_t a, int64_t b);
-static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t st, size_t smem = 0) {
+static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t st, size_t smem = 0, int block = SDE_BLOCK) {
   if (!k) return fail(SDEB200_E_UNSUPPORTED, "kernel not available for this model / scheme");
   if (grid <= 0) return 0;
   if (grid > 2147483647LL) return fail(SDEB200_E_ARG, "too many paths for one launch");
@@ -436,7 +436,7 @@ static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t s
     }
   }
   void *args[1] = {(void *)a};
-  CU(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(SDE_BLOCK), args, smem, st));
+  CU(cudaLaunchKernel(k, dim3((unsigned)grid), dim3((unsigned)block), args, smem, st));
   g.launches++;
   return 0;
 }
@@ -454,6 +454,7 @@ static size_t simw_smem(int D, int M, int precision) {
   const int wld = (ts * mw) | 1, xld = (ts * D) | 1;
   return (size_t)(SDE_BLOCK / 32) * 32 * (wld + xld) * esize(precision);
 }
+static int64_t g_sample1_max = getenv("SDEB200_SAMPLE1_MAX") ? atoll(getenv("SDEB200_SAMPLE1_MAX")) : 262144;
 static bool g_tma_enabled = getenv("SDEB200_NO_TMA") == nullptr;
 static int64_t g_tma_launches = 0;
 extern "C" int sdeb200_set_tma(int enabled) {
@@ -462,6 +463,11 @@ extern "C" int sdeb200_set_tma(int enabled) {
   return prev;
 }
 extern "C" int64_t sdeb200_tma_launch_count(void) { return g_tma_launches; }
+extern "C" int64_t sdeb200_set_sample1_max(int64_t npaths) {
+  const int64_t prev = g_sample1_max;
+  g_sample1_max = npaths;
+  return prev;
+}
 
 // Wiener-driven kernel on TMA tensor tiles (simulate_wiener_tma_body): per warp a ring of SDE_SIMWT_STAGES 4 KB tiles
 static size_t simwt_smem() { return (size_t)(SDE_BLOCK / 32) * SDE_SIMWT_STAGES * (4096 + 8) + 1024; }
@@ -655,6 +661,19 @@ extern "C" int sdeb200_model_coefficients(sdeb200_model *m, const double *params
 #define SDE_PPT 4
 #endif
 static int64_t sample_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SDE_PPT); }
+// Terminal-value launch: chunks of SDE_BLOCK*SDE_PPT = 512 paths either way; launches too small to fill the GPU with
+// SDE_PPT paths per thread (148 SMs x ~32 warps x 32 lanes x 4 paths ~ 600 k) use the one-path-per-thread form,
+// which has the same per-path arithmetic and the same summation tree (bit-identical outputs and partials).
+// Bit-identical means: STRICT math (no FMA contraction anywhere) or a built-in functor (FAST forms written with
+// explicit FMAs only); generated functors in FAST math leave contraction to the compiler, which may choose
+// differently in the two instantiations, so they always take the SDE_PPT form and stay shard-invariant.
+static int launch_sample(const sdeb200_model *m, const sde_ktable *kt, const sdeb200_opts *o, const sde_args *a, cudaStream_t st) {
+  const void *k1 = kt->sample1[o->scheme][o->precision];
+  const int64_t grid = capped(sample_grid(a->npaths));
+  const bool invariant = o->math == SDEB200_MATH_STRICT || m->builtin >= 0;
+  if (k1 && invariant && a->npaths <= g_sample1_max) return launch(k1, grid, a, st, 0, SDE_BLOCK * SDE_PPT);
+  return launch(kt->sample[o->scheme][o->precision], grid, a, st);
+}
 
 extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
                               int64_t nsteps, int64_t npaths, void *out) {
@@ -669,7 +688,6 @@ extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const dou
   cudaStream_t st = g.stream();
   unsigned long long *d_bad = (unsigned long long *)g.red.p;
   CU(cudaMemsetAsync(d_bad, 0, 8, st));
-  const void *k = kt->sample[o->scheme][o->precision];
   sde_args a;
   fill_args(&a, m, o, params, x0);
   a.nsteps = nsteps;
@@ -679,14 +697,14 @@ extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const dou
   if (is_device_ptr(out)) {
     a.npaths = npaths;
     a.out = out;
-    if ((rc = launch(k, capped(sample_grid(npaths)), &a, st))) return rc;
+    if ((rc = launch_sample(m, kt, o, &a, st))) return rc;
   } else {
     rc = run_slabs(npaths, bpp, out, [&](int64_t s0, int64_t n, void *dev, cudaStream_t s) {
       sde_args b = a;
       b.npaths = n;
       b.path0 = o->path_offset + s0;
       b.out = dev;
-      return launch(k, capped(sample_grid(n)), &b, s);
+      return launch_sample(m, kt, o, &b, s);
     });
     if (rc) return rc;
   }
@@ -1115,7 +1133,7 @@ extern "C" int sdeb200_estimate(sdeb200_model *m, const sdeb200_opts *o, const d
     a.payoff_comp = payoff->comp;
     a.payoff_k = payoff->strike;
     a.payoff_disc = payoff->discount;
-    if ((rc = launch(kt->sample[o->scheme][o->precision], capped(grid), &a, st))) return rc;
+    if ((rc = launch_sample(m, kt, o, &a, st))) return rc;
     sde_launch_accumulate((const double *)g.partials[0].p, grid, 2 * SDE_MAXF, nq, r.bins, r.ovf, st);
     g.launches++;
   }
@@ -1255,7 +1273,7 @@ static int queue_level(sdeb200_model *m, const sde_ktable *kt, const sdeb200_opt
     a.nsteps = ncoarse;
     a.npaths = npaths;
     grid = sample_grid(npaths);
-    k = kt->sample[o->scheme][o->precision];
+    k = nullptr;   // launch_sample picks the form
   }
   if ((rc = g.partials[slot].ensure((size_t)grid * 2 * SDE_MAXF * 8))) return rc;
   a.partials = (double *)g.partials[slot].p;
@@ -1264,7 +1282,7 @@ static int queue_level(sdeb200_model *m, const sde_ktable *kt, const sdeb200_opt
   a.payoff_comp = payoff->comp;
   a.payoff_k = payoff->strike;
   a.payoff_disc = payoff->discount;
-  if ((rc = launch(k, capped(grid), &a, st))) return rc;
+  if ((rc = k ? launch(k, capped(grid), &a, st) : launch_sample(m, kt, o, &a, st))) return rc;
   sde_launch_accumulate((const double *)g.partials[slot].p, grid, 2 * SDE_MAXF, coupled ? 6 : 2, r.bins, r.ovf, st);
   g.launches++;
   return 0;

@@ -423,7 +423,9 @@ SDE_D void sample_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   typedef Batch<T, M> B;
   __shared__ double s_tab[TabSize<T>::value];
-  __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
+  __shared__ double s_red[(SDE_BLOCK * SDE_PPT / PPT / 32) * 2 * SDE_MAXF];
+  __shared__ double s_stage[PPT == SDE_PPT ? 1 : SDE_MAXF * SDE_BLOCK * SDE_PPT];   // features of a chunk (PPT < SDE_PPT forms)
+  __shared__ unsigned char s_ok[PPT == SDE_PPT ? 1 : SDE_BLOCK * SDE_PPT];
   load_tables<T>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
@@ -493,29 +495,67 @@ SDE_D void sample_body(const sde_args &a) {
     }
   }
   if (a.partials) {
+    // per-chunk partial sums.  The summation tree is a function of the chunk alone (512 consecutive paths: path
+    // i = p*128 + t is added p = 0..3 in order for each t < 128, then lanes, then the four warps), NOT of how many
+    // paths a thread carries: the PPT = 1 form (512 threads, small launches) stages its features in shared memory
+    // and lets threads t < 128 run the same loop, so both forms write bit-identical partials.
     double acc[2 * SDE_MAXF];
 #pragma unroll
     for (int q = 0; q < 2 * SDE_MAXF; q++) acc[q] = 0.0;
     unsigned bad = 0;
     int nf = 1;
+    if (PPT == SDE_PPT) {
 #pragma unroll
-    for (int p = 0; p < PPT; p++) {
-      double xd[SDE_MAXD], f[SDE_MAXF];
+      for (int p = 0; p < PPT; p++) {
+        double xd[SDE_MAXD], f[SDE_MAXF];
 #pragma unroll
-      for (int d = 0; d < SDE_MAXD; d++) xd[d] = (double)x[p][d];
-      nf = payoff_features(a, D, xd, f);
-      if (live[p]) {
-        if (all_finite(xd, D)) {
+        for (int d = 0; d < SDE_MAXD; d++) xd[d] = (double)x[p][d];
+        nf = payoff_features(a, D, xd, f);
+        if (live[p]) {
+          if (all_finite(xd, D)) {
 #pragma unroll
-          for (int q = 0; q < SDE_MAXF; q++)
-            if (q < nf) { acc[2 * q] += f[q]; acc[2 * q + 1] += f[q] * f[q]; }
-        } else {
-          bad++;
+            for (int q = 0; q < SDE_MAXF; q++)
+              if (q < nf) { acc[2 * q] += f[q]; acc[2 * q + 1] = fma(f[q], f[q], acc[2 * q + 1]); }
+          } else {
+            bad++;
+          }
+        }
+      }
+    } else {
+      constexpr int NT = SDE_BLOCK * SDE_PPT / PPT;   // threads of this form
+#pragma unroll
+      for (int p = 0; p < PPT; p++) {
+        double xd[SDE_MAXD], f[SDE_MAXF];
+#pragma unroll
+        for (int d = 0; d < SDE_MAXD; d++) xd[d] = (double)x[p][d];
+        nf = payoff_features(a, D, xd, f);
+        const bool ok = live[p] && all_finite(xd, D);
+        if (live[p] && !ok) bad++;
+        const int i = p * NT + threadIdx.x;           // path index inside the chunk
+        s_ok[i] = ok ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < SDE_MAXF; q++)
+          if (q < nf) s_stage[q * (SDE_BLOCK * SDE_PPT) + i] = f[q];
+      }
+      __syncthreads();
+      if (threadIdx.x < SDE_BLOCK) {
+#pragma unroll
+        for (int p = 0; p < SDE_PPT; p++) {
+          const int i = p * SDE_BLOCK + threadIdx.x;
+          if (s_ok[i]) {
+#pragma unroll
+            for (int q = 0; q < SDE_MAXF; q++)
+              if (q < nf) {
+                const double fq = s_stage[q * (SDE_BLOCK * SDE_PPT) + i];
+                acc[2 * q] += fq;
+                acc[2 * q + 1] = fma(fq, fq, acc[2 * q + 1]);
+              }
+          }
         }
       }
     }
     block_reduce_store<2 * SDE_MAXF>(acc, 2 * nf, s_red, a.partials + chunk * (2 * SDE_MAXF));
-    __syncthreads();  // s_red is reused by the next chunk
+    __syncthreads();  // s_red / s_stage are reused by the next chunk
     bad = __reduce_add_sync(0xffffffffu, bad);
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
   } else if (a.nonfinite) {
@@ -1442,6 +1482,8 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #define SDE_KERNELS(MODEL, TAG, SCH, SNAME, T, PNAME)                                                            \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT>(a); }                       \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT) sdek_##TAG##_sample1_##SNAME##_##PNAME(      \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 1>(a); }                        \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_mlmc_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, T, SCH>(a); }                            \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_##SNAME##_##PNAME(                \
@@ -1460,6 +1502,8 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #define SDE_KERNELS_EXACT(MODEL, TAG, T, PNAME)                                                                  \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_exact_##PNAME(                    \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, 3, SDE_PPT>(a); }                   \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT) sdek_##TAG##_sample1_exact_##PNAME(         \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, 3, 1>(a); }                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_exact_##PNAME(                    \
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, 3>(a); }                      \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_exact_##PNAME(                 \

@@ -5,6 +5,7 @@
 #define SDE_KTABLE_H
 typedef struct {
   const void *sample[4][2];
+  const void *sample1[4][2]; /* one path per thread, 512-thread CTAs: launches too small to fill the GPU with SDE_PPT paths per thread */
   const void *mlmc[4][2];
   const void *simsoa[4][2];
   const void *simref[4][2];

@@ -45,7 +45,11 @@ struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
     (void)t;
     const T S = x[0], w = dw[0];
     if (SCHEME == 3) {  // rand(LogNormal(log(x0) + (r-σ²/2)Δt, sqrt(Δt)σ)) = exp(randn()*d + μ); dw is a plain N(0,1) here
+#if SDE_STRICT
       x[0] = sde_exp(w * c[6] + (sde_log(S) + c[5]));
+#else
+      x[0] = sde_exp(sde_fma(w, c[6], sde_log(S) + c[5]));
+#endif
       return;
     }
 #if SDE_STRICT
@@ -83,10 +87,15 @@ struct OrnsteinUhlenbeck {  // dx = θ*(μ-x)*dt + σ*dW, params (θ, μ, σ)   
     c[3] = sde_exp(-p[0] * dt);
     c[4] = p[1] * ((T)1 - sde_exp(-p[0] * dt));
     c[5] = sde_sqrt((T)1 - sde_exp((T)-2 * p[0] * dt)) * p[2] / sde_sqrt((T)2 * p[0]);
+#if !SDE_STRICT
+    c[6] = (T)1 - p[0] * dt;   // 1 - θΔt
+    c[7] = p[0] * p[1] * dt;   // θμΔt
+#endif
   }
   template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
     (void)t;
     const T X = x[0], w = dw[0];
+#if SDE_STRICT
     if (SCHEME == 3) {  // rand(Normal(m, d)) = m + d*randn(); dw is a plain N(0,1) here
       x[0] = (X * c[3] + c[4]) + c[5] * w;
       return;
@@ -97,6 +106,13 @@ struct OrnsteinUhlenbeck {  // dx = θ*(μ-x)*dt + σ*dW, params (θ, μ, σ)   
     if (SCHEME == 1) y = y + (((T)0 * c[2]) * (w * w - dt)) / (T)2;
     if (SCHEME == 2) y = y + ((c[2] - c[2]) * (w * w - dt)) / ((T)2 * sde_sqrt(dt));
     x[0] = y;
+#else
+    // FAST forms are written with explicit FMAs only (like BlackScholes and Heston): the compiler has no contraction
+    // left to choose, so every kernel form produces the same bits
+    (void)dt;
+    if (SCHEME == 3) x[0] = sde_fma(c[5], w, sde_fma(X, c[3], c[4]));
+    else x[0] = sde_fma(c[2], w, sde_fma(X, c[6], c[7]));   // the Milstein / RungeKutta corrections are exactly 0
+#endif
   }
   SDE_HD static void coefficients(const double *p, double t, const double *x, double *mu, double *sig) {
     (void)t;

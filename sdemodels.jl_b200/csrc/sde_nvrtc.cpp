@@ -123,7 +123,7 @@ int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precisio
   const char *sn[3] = {"em", "mil", "rk"};
   for (int s = 0; s < nsch; s++) {
     const std::string suf = std::string("_") + sn[s] + "_" + P;
-    if (!get("sdek_gen_sample" + suf, &kt->sample[s][precision]) || !get("sdek_gen_mlmc" + suf, &kt->mlmc[s][precision]) ||
+    if (!get("sdek_gen_sample" + suf, &kt->sample[s][precision]) || !get("sdek_gen_sample1" + suf, &kt->sample1[s][precision]) || !get("sdek_gen_mlmc" + suf, &kt->mlmc[s][precision]) ||
         !get("sdek_gen_simsoa" + suf, &kt->simsoa[s][precision]) || !get("sdek_gen_simref" + suf, &kt->simref[s][precision]) ||
         !get("sdek_gen_simw" + suf, &kt->simw[s][precision]) || !get("sdek_gen_simwt" + suf, &kt->simwt[s][precision]) ||
         !get("sdek_gen_simrt" + suf, &kt->simrt[s][precision])) {

@@ -267,6 +267,47 @@ def test_sharded_paths_reproduce_the_single_launch(gpu):
     assert np.array_equal(full, np.concatenate([lo, hi]))
 
 
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("npaths", [1, 31, 1000, 4097, 70000])
+def test_small_launch_kernel_form_is_bit_identical(gpu, precision, npaths):
+    """Launches too small to fill the GPU use one path per thread (512-thread CTAs) instead of four: same per-path
+    arithmetic, same summation tree per 512-path chunk => terminal states, exact sums and non-finite counts agree
+    bit for bit with the four-paths-per-thread form (so sharding over GPUs cannot change a result through it)."""
+    import torch
+    S = gpu
+    he, bs = S.Heston(*HESTON_P), S.BlackScholes(*BS_P)
+    tdt = torch.float64 if precision == "f64" else torch.float32
+    jobs = [(he, S.EulerMaruyama(1 / 64), [100.0, 0.4], S.Moments(), 2), (bs, S.Milstein(1 / 64), 100.0, S.Call(100.0, 0.99), 1),
+            (S.Heston(0.01, 10.0, 0.3, 3.0, 0.4), S.EulerMaruyama(0.25), [100.0, 0.05], S.Moments(), 2)]  # goes non-finite
+    for m, sch, x0, pay, D in jobs:
+        res = []
+        for cap in (1 << 40, 0):
+            prev = S.set_sample1_max(cap)
+            try:
+                x = torch.zeros((npaths, D) if D > 1 else (npaths,), dtype=tdt, device="cuda")
+                term = torch.zeros_like(x)
+                sums, msg = None, ""
+                try:
+                    S.sample(m, sch, 0.0, x0, 16, npaths, seed=3, precision=precision, path_offset=5, out=x)
+                    e = S.estimate(m, sch, pay, 0.0, x0, 16, npaths, seed=3, precision=precision, path_offset=5, terminal=term)
+                    sums = np.asarray(e.sums).copy()
+                except S.DomainError as err:
+                    msg = str(err)
+                    try:
+                        S.estimate(m, sch, pay, 0.0, x0, 16, npaths, seed=3, precision=precision, path_offset=5, terminal=term)
+                    except S.DomainError as err2:
+                        msg += str(err2)
+                torch.cuda.synchronize()
+                res.append((x.cpu().numpy(), term.cpu().numpy(), sums, msg))
+            finally:
+                S.set_sample1_max(prev)
+        assert np.array_equal(res[0][0], res[1][0], equal_nan=True) and np.array_equal(res[0][1], res[1][1], equal_nan=True)
+        assert np.array_equal(res[0][0], res[0][1], equal_nan=True)
+        assert res[0][3] == res[1][3]   # same non-finite counts in the messages
+        if res[0][2] is not None:
+            assert np.array_equal(res[0][2], res[1][2])
+
+
 @pytest.mark.parametrize("substeps,ncoarse", [(2, 16), (4, 10)])
 def test_coupled_level_matches_oracle(gpu, O, substeps, ncoarse):
     """_multilevel_sample (multilevel.jl:65-89): same increments drive fine and coarse paths."""
