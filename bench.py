@@ -71,8 +71,18 @@ def clocks_summary(proc):
             "power_w_max": max(power), "samples": len(sm)}
 
 
+def host_threads():
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not
+    inherit that (it would time the reference on one core and call it the host), so the count is passed explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(O, nsteps, seconds, threads=0):
     """path-steps/s of the CPU restatement on a bounded sample sized for ~`seconds` of work."""
+    threads = threads or host_threads()
     dt = 1.0 / nsteps
     t = time.perf_counter()
     O.sample_rng("Heston", 0, HESTON, 0.0, dt, X0, nsteps, 20000, 0, threads)
