@@ -1,3 +1,5 @@
+"""Kernel time of small terminal-value launches (Heston EM, 1024 steps): the one-path-per-thread form against the
+four-paths-per-thread form (SDEB200_SAMPLE1_MAX=0 python tools/small_launch_timing.py forces the latter)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg
