@@ -265,6 +265,36 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
+        if world == 1:
+            # the HBM-bound kernel of the path, measured live for its own roofline line: Wiener-driven trajectories
+            # simulate!(x, model, scheme, t0, x0, w) with x === w on TMA tensor tiles (2e6 paths x 513 rows, 8.2 GB)
+            try:
+                nw, rw = 2_000_000, 513
+                wbuf = torch.empty((nw, rw), dtype=torch.float64, device="cuda")
+                bsm = S.BlackScholes(0.01, 0.3)
+                best = None
+                for rep in range(4):
+                    S.wiener_(wbuf, 1.0 / (rw - 1), seed=rep)
+                    S.simulate_(wbuf, bsm, S.EulerMaruyama(1.0 / (rw - 1)), 0.0, 100.0, wbuf)
+                    t = S.last_kernel_ms()
+                    best = t if best is None or (rep > 0 and t < best) else best
+                nbytes = 2 * wbuf.numel() * wbuf.element_size()
+                hbm_peak = 6547.8
+                try:
+                    hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                    src = "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
+                except (OSError, KeyError):
+                    src = "fallback"
+                line["roofline_hbm_kernel"] = {
+                    "kernel": "sdek_bs_f_simwt_em_f64", "bound": "hbm", "achieved": nbytes / best / 1e6, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": nbytes / best / 1e6 / hbm_peak, "peak_source": src, "kernel_ms": best,
+                    "algorithmic_bytes": nbytes, "traffic": 16611395000,
+                    "traffic_note": "ncu --set full of the same launch shape: 8.394 GB read + 8.217 GB written "
+                                    "(profiles/r01d_tma_kernels_ncu_summary.csv); algorithmic 8.208 + 8.208 GB",
+                    "workload": "BlackScholes EM FP64, simulate!(x, model, scheme, t0, x0, w) in place, 2e6 paths x 513 rows"}
+                del wbuf
+            except Exception as err:  # the headline line must not depend on this extra
+                line["roofline_hbm_kernel"] = {"error": str(err)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             import oracle as O
             O.build()
