@@ -1259,20 +1259,26 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
 #pragma unroll
   for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
 
-  // warp-uniform ring state: tiles flushed so far, next tile a lane with h = 0 will start
+  // warp-uniform ring state: tiles flushed so far, next tile a lane with h = 0 will start, and the rows at which the
+  // next of each happens (one compare per batch on the common path)
+  constexpr int NEVER = 0x7fffffff;
   int nflushed = 0, tbeg = 0;
-  // rows [i_first, i_last] are about to be written
+  int begin_row = ntile > 0 ? 0 : NEVER;                     // tbeg * TS
+  int flush_row = ntile > 0 ? TS - 1 + hmax : NEVER;         // (nflushed + 1) * TS - 1 + hmax
+  // rows up to i_last are about to be written
   auto begin_check = [&](int i_last) {
-    if (tbeg < ntile && tbeg * TS <= i_last) {
+    if (i_last >= begin_row) {
       if (tbeg >= NSX) simrt_acquire(nflushed - (tbeg - NSX + 1));
       tbeg++;
+      begin_row = tbeg < ntile ? begin_row + TS : NEVER;
     }
   };
   // rows up to i_last have been written
   auto flush_check = [&](int i_last) {
-    if (nflushed < ntile && i_last >= (nflushed + 1) * TS - 1 + hmax) {
+    if (i_last >= flush_row) {
       simrt_flush(tmx, tiles_s, g, nrows * D, TS * D, h1 * D, h2 * D, h3 * D, c1, nflushed);
       nflushed++;
+      flush_row = nflushed < ntile ? flush_row + TS : NEVER;
     }
   };
   // store x as the row at byte offset `off` (0..255: stage bit 7, 128-byte swizzled row below) of this lane's ring
