@@ -1014,7 +1014,7 @@ SDE_D void tail_tile_store(const T *tile, T *g, int64_t gstride, int nlive, int 
 //     the swizzled tile (16-byte shared-memory accesses, conflict-free), lane 0 stores the tile to x.  A tile is
 //     complete in shared memory before any of it is stored => x === w is safe.  Rows before the first aligned row
 //     of a path (h_j <= 3) use plain accesses; the rows after the last full tile go through one cooperative
-//     shared-memory tile (tile_load / tile_store_from).  Needs D == M (eltype(x) == eltype(w)) and D*sizeof(T) | 128;
+//     shared-memory tile (loads via registers, tail_tile_store).  Needs D == M (eltype(x) == eltype(w)) and D*sizeof(T) | 128;
 //     the host routes everything else, unaligned buffers, short paths and the npaths % g leftover to K3.
 // ---------------------------------------------------------------------------------------------------
 template <class Model, typename T, int SCHEME>

@@ -42,3 +42,6 @@ extern "C" void h_pair_from_bits(const uint32_t *r4, double scale2, double *z) {
   make_log_consts(scale2, lk);
   normal_pair_f64(r, tab, lk, z[0], z[1]);
 }
+// geometry of the TMA trajectory tiles (sde_args.h): paths per tensor-map row and the first aligned row of a sub-path
+extern "C" int h_tma_group(int64_t pitch_bytes) { return sde_tma_group(pitch_bytes); }
+extern "C" int h_tma_head(int j, int64_t pitch_bytes, int rowb) { return sde_tma_head(j, pitch_bytes, rowb); }

@@ -71,3 +71,23 @@ def test_fp32_normal_transform_matches_the_specification(H, O):
     ref = O.normals(9, 2, 4, 0, n, "f32")
     assert np.max(np.abs(out - ref)) < 2e-5
     assert np.all(np.isfinite(out))
+
+
+def test_tma_tile_geometry(H):
+    """sde_tma_group / sde_tma_head (sde_args.h): g consecutive paths make the tensor map's row stride a multiple of
+    16 bytes (TMA requirement), and the box of sub-path j starts at the first 16-byte-aligned time row."""
+    H.h_tma_group.argtypes = [C.c_int64]
+    H.h_tma_head.argtypes = [C.c_int, C.c_int64, C.c_int]
+    for es in (4, 8):
+        for D in (1, 2, 4):
+            rowb = D * es
+            for nrows in list(range(1, 70)) + [252, 253, 512, 513, 1024, 1025, 4097]:
+                pitch = nrows * rowb
+                g = H.h_tma_group(pitch)
+                assert g in (1, 2, 4) and (g * pitch) % 16 == 0 and (g == 1 or ((g // 2) * pitch) % 16 != 0)
+                heads = [H.h_tma_head(j, pitch, rowb) for j in range(g)]
+                assert heads[0] == 0
+                for j, h in enumerate(heads):
+                    assert (j * pitch + h * rowb) % 16 == 0                       # aligned box start
+                    assert all((j * pitch + k * rowb) % 16 != 0 for k in range(h))  # and the first such row
+                    assert h <= (0 if rowb % 16 == 0 else (1 if rowb % 8 == 0 else 3))  # HMAX of the kernels
