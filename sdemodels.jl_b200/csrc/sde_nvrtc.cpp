@@ -3,7 +3,11 @@
 // C-ABI library itself has no link-time dependency on it.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -55,6 +59,66 @@ static bool nvrtc_load(std::string *log) {
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// On-disk cache of compiled cubins: a generated model costs 2-12 s of NVRTC per (precision, math) on first use; a
+// later process with the same equations, library build and options loads the cubin back instead.
+// Directory: $SDEB200_CACHE_DIR (empty string: caching off), else $XDG_CACHE_HOME/sdeb200, else $HOME/.cache/sdeb200.
+// Key: two independent 64-bit FNV-1a hashes over the translation unit, the embedded headers and the options.
+// ---------------------------------------------------------------------------------------------------
+static uint64_t fnv1a(uint64_t h, const char *p, size_t n) {
+  for (size_t i = 0; i < n; i++) { h ^= (unsigned char)p[i]; h *= 0x100000001b3ULL; }
+  return h;
+}
+static std::string cache_dir() {
+  const char *d = getenv("SDEB200_CACHE_DIR");
+  if (d) return std::string(d);   // may be empty: off
+  const char *x = getenv("XDG_CACHE_HOME");
+  if (x && *x) return std::string(x) + "/sdeb200";
+  const char *h = getenv("HOME");
+  if (h && *h) return std::string(h) + "/.cache/sdeb200";
+  return std::string();
+}
+static std::string cache_path(const std::string &src, const std::vector<const char *> &opts) {
+  const std::string dir = cache_dir();
+  if (dir.empty()) return std::string();
+  uint64_t a = 0xcbf29ce484222325ULL, b = 0x84222325cbf29ce4ULL;
+  const char *parts[] = {src.c_str(), sde_embedded_device_cuh, sde_embedded_args_h, sde_embedded_coeffs_inc};
+  for (const char *q : parts) { a = fnv1a(a, q, strlen(q)); b = fnv1a(b ^ 0x9e3779b97f4a7c15ULL, q, strlen(q)); }
+  for (const char *o : opts) { a = fnv1a(a, o, strlen(o) + 1); b = fnv1a(b, o, strlen(o) + 1); }
+  char name[64];
+  snprintf(name, sizeof name, "/%016llx%016llx.cubin", (unsigned long long)a, (unsigned long long)b);
+  return dir + name;
+}
+static bool cache_read(const std::string &path, std::vector<char> *cubin) {
+  if (path.empty()) return false;
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 64;
+  if (ok) {
+    cubin->resize((size_t)n);
+    ok = fread(cubin->data(), 1, (size_t)n, f) == (size_t)n && memcmp(cubin->data(), "\x7f" "ELF", 4) == 0;
+  }
+  fclose(f);
+  return ok;
+}
+static void cache_write(const std::string &path, const std::vector<char> &cubin) {
+  if (path.empty()) return;
+  const std::string dir = path.substr(0, path.rfind('/'));
+  for (size_t i = 1; i <= dir.size(); i++)   // mkdir -p
+    if (i == dir.size() || dir[i] == '/') mkdir(dir.substr(0, i).c_str(), 0700);
+  char tmp[32];
+  snprintf(tmp, sizeof tmp, ".tmp%ld", (long)getpid());
+  const std::string t = path + tmp;
+  FILE *f = fopen(t.c_str(), "wb");
+  if (!f) return;   // a read-only or missing cache directory only costs the next compile
+  const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  fclose(f);
+  if (!ok || rename(t.c_str(), path.c_str()) != 0) unlink(t.c_str());
+}
+
 // Compile only (no device needed): used by the CPU test-suite to check that generated functors build.
 int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision, int math, std::vector<char> *cubin,
                            std::string *log) {
@@ -69,12 +133,14 @@ int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision,
   src += std::string("SDE_KERNELS_LOGT(sdeb200::GenModel, gen, ") + T + ", " + P + ")\n";
   const char *hdr_src[] = {sde_embedded_device_cuh, sde_embedded_args_h, sde_embedded_coeffs_inc};
   const char *hdr_name[] = {"sde_device.cuh", "sde_args.h", "sde_coeffs.inc"};
-  nvrtcProgram prog = nullptr;
-  int r = nv.CreateProgram(&prog, src.c_str(), "sde_generated_model.cu", 3, hdr_src, hdr_name);
-  if (r) { *log = std::string("nvrtcCreateProgram: ") + nv.GetErrorString(r); return SDEB200_E_NVRTC; }
   std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
                                     math ? "-DSDE_STRICT=1" : "-DSDE_STRICT=0"};
   if (math) opts.push_back("--fmad=false");
+  const std::string cpath = cache_path(src, opts);
+  if (cache_read(cpath, cubin)) return 0;
+  nvrtcProgram prog = nullptr;
+  int r = nv.CreateProgram(&prog, src.c_str(), "sde_generated_model.cu", 3, hdr_src, hdr_name);
+  if (r) { *log = std::string("nvrtcCreateProgram: ") + nv.GetErrorString(r); return SDEB200_E_NVRTC; }
   r = nv.CompileProgram(prog, (int)opts.size(), opts.data());
   size_t ls = 0;
   nv.GetProgramLogSize(prog, &ls);
@@ -93,6 +159,7 @@ int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision,
   cubin->resize(cs);
   nv.GetCUBIN(prog, cubin->data());
   nv.DestroyProgram(&prog);
+  cache_write(cpath, *cubin);
   return 0;
 }
 

@@ -6,6 +6,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+# the library's cubin cache (NVRTC-compiled generated models) stays inside the repository during the tests
+os.environ.setdefault("SDEB200_CACHE_DIR", os.path.join(ROOT, ".pytest_cache", "sdeb200_cubins"))
 
 
 def pytest_configure(config):

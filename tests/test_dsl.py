@@ -211,3 +211,30 @@ def test_generated_functor_compiles_for_sm100a(S, name):
     for prec, math_ in variants:
         rc = fn(src, cls._M, prec, math_, log, len(log))
         assert rc > 1000, log.value.decode()
+
+
+def test_cubin_cache_round_trip(S, tmp_path, monkeypatch):
+    """A generated model's cubin is written to $SDEB200_CACHE_DIR and loaded back by the next compile of the same
+    source / options; an empty variable turns the cache off; a corrupt entry is ignored."""
+    import time
+    L = S._lib.lib()
+    cls = S.sde_model("CacheProbe", "dX = a*(b - X)*dt + c*X*dW1; dY = e*Y*dt + f*dW2")   # M = 2: one scheme to compile
+    L.sdeb200_model_cuda_source.restype = C.c_char_p
+    src = L.sdeb200_model_cuda_source(cls._handle)
+    fn = L.sdeb200_debug_nvrtc_check
+    fn.restype = C.c_int
+    log = C.create_string_buffer(1 << 16)
+    monkeypatch.setenv("SDEB200_CACHE_DIR", str(tmp_path / "cubins"))
+    t = time.perf_counter()
+    n1 = fn(src, 2, 1, 0, log, len(log))
+    cold = time.perf_counter() - t
+    files = list((tmp_path / "cubins").glob("*.cubin"))
+    assert n1 > 1000 and len(files) == 1 and files[0].stat().st_size == n1
+    t = time.perf_counter()
+    n2 = fn(src, 2, 1, 0, log, len(log))
+    warm = time.perf_counter() - t
+    assert n2 == n1 and warm < 0.5 * cold
+    files[0].write_bytes(b"not a cubin" * 10)                 # corrupt entry: recompiled and replaced
+    assert fn(src, 2, 1, 0, log, len(log)) == n1 and files[0].stat().st_size == n1
+    monkeypatch.setenv("SDEB200_CACHE_DIR", "")               # off
+    assert fn(src, 2, 1, 1, log, len(log)) > 1000 and len(list((tmp_path / "cubins").glob("*.cubin"))) == 1
