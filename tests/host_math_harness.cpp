@@ -45,3 +45,13 @@ extern "C" void h_pair_from_bits(const uint32_t *r4, double scale2, double *z) {
 // geometry of the TMA trajectory tiles (sde_args.h): paths per tensor-map row and the first aligned row of a sub-path
 extern "C" int h_tma_group(int64_t pitch_bytes) { return sde_tma_group(pitch_bytes); }
 extern "C" int h_tma_head(int j, int64_t pitch_bytes, int rowb) { return sde_tma_head(j, pitch_bytes, rowb); }
+// the per-path form of the block function (round 0/1 invariants hoisted) must equal the plain one
+extern "C" void h_philox_path(uint64_t path, uint32_t stream, uint32_t blk, const uint32_t *key, uint32_t *out) {
+  PhiloxKeys ks;
+  philox_expand(key[0], key[1], ks);
+  PhiloxPath pp;
+  philox_path_init(path, stream, ks, pp);
+  uint32_t r[4];
+  philox4x32_10(pp, blk, ks, r);
+  for (int i = 0; i < 4; i++) out[i] = r[i];
+}

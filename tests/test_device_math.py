@@ -91,3 +91,16 @@ def test_tma_tile_geometry(H):
                     assert (j * pitch + h * rowb) % 16 == 0                       # aligned box start
                     assert all((j * pitch + k * rowb) % 16 != 0 for k in range(h))  # and the first such row
                     assert h <= (0 if rowb % 16 == 0 else (1 if rowb % 8 == 0 else 3))  # HMAX of the kernels
+
+
+def test_per_path_philox_form_is_bit_identical(H, O):
+    """philox4x32_10(PhiloxPath, blk): rounds 0 and 1 partly hoisted per path — same 128 bits as the plain block function."""
+    rng = np.random.default_rng(3)
+    H.h_philox_path.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    for _ in range(200):
+        path = int(rng.integers(0, 2 ** 63)) if rng.random() < 0.5 else int(rng.integers(0, 2 ** 20))
+        stream, blk = int(rng.integers(0, 2 ** 32)), int(rng.integers(0, 2 ** 32))
+        key = [int(rng.integers(0, 2 ** 32)), int(rng.integers(0, 2 ** 32))]
+        out = (C.c_uint32 * 4)()
+        H.h_philox_path(path, stream, blk, (C.c_uint32 * 2)(*key), out)
+        assert list(out) == O.philox4x32_10([path & 0xffffffff, path >> 32, blk, stream], key)
