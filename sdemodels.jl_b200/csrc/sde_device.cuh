@@ -30,6 +30,9 @@
 #ifndef SDE_PHILOX_ROUNDS
 #define SDE_PHILOX_ROUNDS 10 /* Philox4x32-10, the Random123 / cuRAND default; other values are tuning experiments only */
 #endif
+#ifndef SDE_SOA_PP
+#define SDE_SOA_PP 0 /* [time][D][path] trajectory kernel: per-path Philox form (1: measured 2.5 % slower, 16 more registers) or the plain block function (0) */
+#endif
 #ifndef SDE_STRICT
 #define SDE_STRICT 0 /* 1: reference evaluation order, translation unit compiled with -fmad=false */
 #endif
@@ -208,7 +211,7 @@ SDE_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, co
 struct PhiloxPath {
   uint32_t a, b, c, e;   // path_hi ^ k0;  hi(Q) ^ k2;  lo(Q);  lo(M0*path_lo) ^ k3   with Q = M1 * n2(round 0)
 };
-SDE_HD void philox_path_init(uint64_t path, uint32_t stream, const PhiloxKeys &ks, PhiloxPath &pp) {
+SDE_HD void philox_path_init(uint64_t path, uint32_t stream, const PhiloxKeys &ks, PhiloxPath &pp, bool used = true) {
   const uint64_t p0 = (uint64_t)0xD2511F53u * (uint32_t)path;
   const uint32_t n2 = (uint32_t)(p0 >> 32) ^ stream ^ ks.k[1];
   const uint64_t q = (uint64_t)0xCD9E8D57u * n2;
@@ -217,7 +220,7 @@ SDE_HD void philox_path_init(uint64_t path, uint32_t stream, const PhiloxKeys &k
   pp.c = (uint32_t)q;
   pp.e = (uint32_t)p0 ^ ks.k[3];
 #if defined(__CUDA_ARCH__)
-  asm volatile("" : "+r"(pp.a), "+r"(pp.b), "+r"(pp.c), "+r"(pp.e));  // keep them, do not rematerialise
+  if (used) asm volatile("" : "+r"(pp.a), "+r"(pp.b), "+r"(pp.c), "+r"(pp.e));  // keep them, do not rematerialise (FP32: dead)
 #endif
 }
 SDE_HD void philox4x32_10(const PhiloxPath &pp, uint32_t blk, const PhiloxKeys &ks, uint32_t (&r)[4]) {
@@ -410,7 +413,7 @@ template <typename T, int M> struct Batch {
 
 template <typename T, int M>
 SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const PhiloxKeys &ks, const double *s_tab,
-                     const double *lk, T scale2, T *dw) {
+                     const double *lk, T scale2, T *dw, const double *kr = nullptr) {
   typedef Batch<T, M> B;
   if (M == 0) {
     dw[0] = (T)0;
@@ -420,7 +423,7 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const Philox
   for (int b = 0; b < B::NB; b++) {
     uint32_t r[4];
     philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, ks, r);
-    normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB);
+    normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
   }
 }
 
@@ -429,11 +432,11 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const Philox
 // from where every use as a DFMA multiplicand costs two moves (measured: +1.3 % on the headline kernel).
 struct PinnedCoef {
   double v[3];
-  SDE_D explicit PinnedCoef(const double *lk) {
+  SDE_D PinnedCoef(const double *lk, bool fp64) {
     v[0] = lk[3];
     v[1] = SDE_K(SDE_ROT_S2);
     v[2] = SDE_K(SDE_ROT_C2);
-    asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]) : "r"(threadIdx.x));
+    if (fp64) asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]) : "r"(threadIdx.x));   // FP32 kernels: dead code
   }
 };
 
@@ -547,8 +550,8 @@ SDE_D void sample_body(const sde_args &a) {
   const int rem = (int)(a.nsteps - nbatch * B::U);
   PhiloxPath pp[PPT];
 #pragma unroll
-  for (int p = 0; p < PPT; p++) philox_path_init(gpath0 + (uint64_t)(p * (int)blockDim.x), a.stream, ks, pp[p]);
-  PinnedCoef pc(a.lk);
+  for (int p = 0; p < PPT; p++) philox_path_init(gpath0 + (uint64_t)(p * (int)blockDim.x), a.stream, ks, pp[p], sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8);
   const double *kr = pc.v;
 
   for (int64_t it = 0; it < nbatch; it++) {
@@ -689,7 +692,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   const T dtf = (T)a.dt, dtc = (T)a.dt_coarse, t0 = (T)a.t0;
   Model::prepare(prm, dtf, cf.c);
   Model::prepare(prm, dtc, cc.c);
-  PinnedCoef pc(a.lk);
+  PinnedCoef pc(a.lk, sizeof(T) == 8);
 
   const int64_t nchunks = (a.npaths + blockDim.x - 1) / blockDim.x;
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -697,7 +700,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   const bool live = k < a.npaths;
   const uint64_t gpath = (uint64_t)(a.path0 + k);
   PhiloxPath pp;
-  philox_path_init(gpath, a.stream, ks, pp);
+  philox_path_init(gpath, a.stream, ks, pp, sizeof(T) == 8);
   T xf[SDE_MAXD], xc[SDE_MAXD], DW[M > 0 ? M : 1];
 #pragma unroll
   for (int d = 0; d < SDE_MAXD; d++) xf[d] = xc[d] = d < D ? (T)a.x0[d] : (T)0;
@@ -850,14 +853,19 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   const uint64_t gpath = (uint64_t)(a.path0 + k0);
   PhiloxPath pp[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; v++) philox_path_init(gpath + (uint64_t)v, a.stream, ks, pp[v]);
-  PinnedCoef pc(a.lk);
+  for (int v = 0; v < VEC; v++) philox_path_init(gpath + (uint64_t)v, a.stream, ks, pp[v], sizeof(T) == 8 && SDE_SOA_PP);
+  PinnedCoef pc(a.lk, sizeof(T) == 8);
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[VEC][B::NZ];
 #pragma unroll
     for (int v = 0; v < VEC; v++)
+#if SDE_SOA_PP
       gen_batch<T, M>(pp[v], gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v], pc.v);
+#else
+      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v],
+                      sizeof(T) == 8 ? pc.v : nullptr);
+#endif
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;
@@ -977,8 +985,8 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   const uint64_t gpath = (uint64_t)(a.path0 + wbase + lane);
   PhiloxPath pp[PW];
 #pragma unroll
-  for (int p = 0; p < PW; p++) philox_path_init(gpath + (uint64_t)(32 * p), a.stream, ks, pp[p]);
-  PinnedCoef pc(a.lk);
+  for (int p = 0; p < PW; p++) philox_path_init(gpath + (uint64_t)(32 * p), a.stream, ks, pp[p], sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8);
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[PW][B::NZ];
@@ -1428,8 +1436,8 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
   emit_slow(0);
   const uint64_t gpath = (uint64_t)(a.path0 + p);
   PhiloxPath pp;
-  philox_path_init(gpath, a.stream, ks, pp);
-  PinnedCoef pc(a.lk);
+  philox_path_init(gpath, a.stream, ks, pp, sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8);
   const int64_t nbatch = (a.nsteps + U - 1) / U;
   auto slow_batch = [&](int64_t it) {
     T dw[B::NZ];
@@ -1603,20 +1611,30 @@ SDE_D void coef_eval_body(const sde_args &a) {
 
 #define SDE_EM 0
 #define SDE_MILSTEIN 1
+// Resident CTAs per SM the FP64 terminal-value kernel is compiled for.  1 = "no occupancy target": ptxas then spends
+// registers on scheduling (154 for Heston) and the kernel runs 12 warps per SM — measured FASTER (2.20e11 vs 2.10e11
+// path-steps/s at 64 registers / 30 warps): the loop is dispatch-bound, not latency-bound.  The FP32 kernel keeps the
+// default heuristics (0 = unspecified; with 1 it took 124 registers and lost 2 %).
 #ifndef SDE_SAMPLE_MINB
-#define SDE_SAMPLE_MINB 1 /* resident CTAs per SM the terminal-value kernel is compiled for (register cap) */
+#define SDE_SAMPLE_MINB 1
+#endif
+#ifndef SDE_F64_MINB
+#define SDE_F64_MINB 1 /* the same switch for the FP64 coupled-level and [time][D][path] kernels (+0.6 % / +1.1 %) */
 #endif
 
 // Kernel entry points for one model type, scheme and precision.  TAG makes the symbols unique.  The
 // reference defines Milstein for M == 1 models only (milstein.jl:4): instantiate SCH = 1 only there.
 #define SDE_KERNELS(MODEL, TAG, SCH, SNAME, T, PNAME)                                                            \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SAMPLE_MINB) sdek_##TAG##_sample_##SNAME##_##PNAME( \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_SAMPLE_MINB : 0)                   \
+      sdek_##TAG##_sample_##SNAME##_##PNAME(                                                                     \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT>(a); }                       \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT) sdek_##TAG##_sample1_##SNAME##_##PNAME(      \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 1>(a); }                        \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_mlmc_##SNAME##_##PNAME(                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_F64_MINB : 0)                      \
+      sdek_##TAG##_mlmc_##SNAME##_##PNAME(                                                                       \
       const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, T, SCH>(a); }                            \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_##SNAME##_##PNAME(                \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_F64_MINB : 0)                      \
+      sdek_##TAG##_simsoa_##SNAME##_##PNAME(                                                                     \
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
