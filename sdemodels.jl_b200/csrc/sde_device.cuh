@@ -1618,6 +1618,15 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #ifndef SDE_SAMPLE_MINB
 #define SDE_SAMPLE_MINB 1
 #endif
+#ifndef SDE_SAMPLE_MINB_F32
+#define SDE_SAMPLE_MINB_F32 0
+#endif
+#ifndef SDE_SIMRT_MINB
+#define SDE_SIMRT_MINB 4
+#endif
+#ifndef SDE_SIMREF_MINB
+#define SDE_SIMREF_MINB 5
+#endif
 #ifndef SDE_F64_MINB
 #define SDE_F64_MINB 1 /* the same switch for the FP64 coupled-level and [time][D][path] kernels (+0.6 % / +1.1 %) */
 #endif
@@ -1625,7 +1634,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
 // Kernel entry points for one model type, scheme and precision.  TAG makes the symbols unique.  The
 // reference defines Milstein for M == 1 models only (milstein.jl:4): instantiate SCH = 1 only there.
 #define SDE_KERNELS(MODEL, TAG, SCH, SNAME, T, PNAME)                                                            \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_SAMPLE_MINB : 0)                   \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_SAMPLE_MINB : SDE_SAMPLE_MINB_F32) \
       sdek_##TAG##_sample_##SNAME##_##PNAME(                                                                     \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT>(a); }                       \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT) sdek_##TAG##_sample1_##SNAME##_##PNAME(      \
@@ -1636,9 +1645,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_F64_MINB : 0)                      \
       sdek_##TAG##_simsoa_##SNAME##_##PNAME(                                                                     \
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##_simrt_##SNAME##_##PNAME(                \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_##SNAME##_##PNAME(                \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, SCH>(a); }                \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMW_MINBLOCKS) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }                  \
@@ -1654,9 +1663,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, 3, 1>(a); }                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_exact_##PNAME(                    \
       const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, 3>(a); }                      \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_simref_exact_##PNAME(                 \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_exact_##PNAME(                 \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, 3>(a); }                      \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##_simrt_exact_##PNAME(                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_exact_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, 3>(a); }
 
 #define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \
