@@ -711,7 +711,35 @@ SDE_D void mlmc_body(const sde_args &a) {
   const int substeps = (int)a.substeps;
   int sub = 0;          // fine steps taken inside the current coarse step
   int64_t ncoarse = 0;  // coarse steps completed
-  for (int64_t it = 0; it < nbatch; it++) {
+  int64_t it = 0;
+  if (substeps == 2) {
+    // the usual refinement factor, unrolled over groups of G = lcm(U, 2) fine steps: the position inside the coarse
+    // step is a compile-time constant, no counters, no branch.  Same operations in the same order as the general loop
+    // below (which finishes what is left when nsteps is not a multiple of G).
+    constexpr int G = (B::U % 2 == 0) ? B::U : 2 * B::U, NBG = G / B::U;
+    const int64_t ngroups = a.nsteps / G;
+    for (int64_t gi = 0; gi < ngroups; gi++) {
+      T dw[NBG][B::NZ];
+#pragma unroll
+      for (int b = 0; b < NBG; b++)
+        gen_batch<T, M>(pp, gpath, (uint32_t)((gi * NBG + b) * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[b], pc.v);
+#pragma unroll
+      for (int j = 0; j < G; j++) {
+        const T tc = t0 + (T)(gi * (G / 2) + j / 2) * dtc;
+        const T tf = tc + (T)(j & 1) * dtf;
+        const T *dwu = dw[j / B::U] + (j % B::U) * (M > 0 ? M : 0);
+#pragma unroll
+        for (int q = 0; q < M; q++) DW[q] = ((j & 1) ? DW[q] : (T)0) + dwu[q];
+        Model::template step<SCHEME>(cf.c, tf, dtf, dwu, xf);
+        if (j & 1) Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
+      }
+    }
+    it = ngroups * NBG;
+    ncoarse = ngroups * (G / 2);
+#pragma unroll
+    for (int q = 0; q < (M > 0 ? M : 1); q++) DW[q] = (T)0;
+  }
+  for (; it < nbatch; it++) {
     T dw[B::NZ];
     gen_batch<T, M>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
 #pragma unroll

@@ -19,7 +19,7 @@ KERNELS = {
     "bs_sample_em_f64": ("sdek_bs_f_sample_em_f64", PPT * 2, "D"),
     "bs_simsoa_mil_f64": ("sdek_bs_f_simsoa_mil_f64", 4 * 2, "D"),
     "bs_simsoa_mil_f32": ("sdek_bs_f_simsoa_mil_f32", 4 * 4, "F"),
-    "heston_mlmc_em_f64": ("sdek_heston_f_mlmc_em_f64", 1, "D"),
+    "heston_mlmc_em_f64": ("sdek_heston_f_mlmc_em_f64", 2, "D"),  # substeps == 2 path: two fine steps per iteration
 }
 
 
