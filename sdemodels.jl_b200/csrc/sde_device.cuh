@@ -1646,6 +1646,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #ifndef SDE_SAMPLE_MINB
 #define SDE_SAMPLE_MINB 1
 #endif
+#ifndef SDE_SAMPLE1_MINB
+#define SDE_SAMPLE1_MINB 0
+#endif
 #ifndef SDE_SAMPLE_MINB_F32
 #define SDE_SAMPLE_MINB_F32 0
 #endif
@@ -1665,7 +1668,8 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_SAMPLE_MINB : SDE_SAMPLE_MINB_F32) \
       sdek_##TAG##_sample_##SNAME##_##PNAME(                                                                     \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT>(a); }                       \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT) sdek_##TAG##_sample1_##SNAME##_##PNAME(      \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT, sizeof(T) == 8 ? SDE_SAMPLE1_MINB : 0)        \
+      sdek_##TAG##_sample1_##SNAME##_##PNAME(                                                                    \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 1>(a); }                        \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_F64_MINB : 0)                      \
       sdek_##TAG##_mlmc_##SNAME##_##PNAME(                                                                       \
