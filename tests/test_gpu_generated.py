@@ -185,3 +185,36 @@ def test_logtransition_matches_oracle(gpu, O, name, params, x, t, precision):
         assert np.array_equal(dev.cpu().numpy(), got)
     one = S.logtransition(m, S.EulerMaruyama(dt), t, data[0])
     assert one.shape == (nsteps,) and np.array_equal(one, got[0])
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("npaths,nrows", [(70, 41), (257, 130)])
+def test_four_dimensional_model_on_tma_tiles(gpu, precision, npaths, nrows):
+    """D = M = 4 (32-byte rows in FP64: a row spans two 16-byte chunks of the swizzled tile; 16-byte rows in FP32): the
+    TMA form of simulate!(x, model, scheme, t0, x0, w) equals the plain tile kernel bit for bit, in place and not."""
+    import torch
+    S = gpu
+    cls = S.sde_model("Four_g", "dA = a*A*dt + s*A*dW1\ndB = b*(A - B)*dt + s*dW2\ndC = -c*C*dt + s*B*dW3\ndE = 0.001*A*C*dt + s*dW4")
+    assert (cls._D, cls._M) == (4, 4)
+    m = cls(0.05, 1.5, 0.7, 0.2)   # fields (a, b, c, s): drift symbols first, then diffusion, in order of appearance
+    dt = 1.0 / (nrows - 1)
+    tdt = torch.float64 if precision == "f64" else torch.float32
+    rng = np.random.default_rng(21)
+    w = np.cumsum(np.concatenate([np.zeros((npaths, 1, 4)), rng.standard_normal((npaths, nrows - 1, 4)) * math.sqrt(dt)], axis=1), axis=1)
+    res = []
+    for tma in (True, False):
+        S.set_tma(tma)
+        try:
+            wd = torch.from_numpy(w).to(tdt).cuda()
+            xd = torch.empty_like(wd)
+            c0 = S.tma_launch_count()
+            S.simulate_(xd, m, S.EulerMaruyama(dt), 0.0, [1.0, 0.5, 0.25, 0.0], wd, math="strict")
+            S.simulate_(wd, m, S.EulerMaruyama(dt), 0.0, [1.0, 0.5, 0.25, 0.0], wd, math="strict")   # x === w
+            torch.cuda.synchronize()
+            res.append((xd.cpu().numpy(), wd.cpu().numpy(), S.tma_launch_count() - c0))
+        finally:
+            S.set_tma(True)
+    assert res[0][2] == 2 and res[1][2] == 0
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][0], res[0][1]) and np.isfinite(res[0][0]).all()
+    assert np.all(res[0][0][:, 0] == np.array([1.0, 0.5, 0.25, 0.0], dtype=res[0][0].dtype))
