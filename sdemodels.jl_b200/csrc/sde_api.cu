@@ -849,17 +849,30 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
     const size_t wb = (size_t)nrows * MW * es, xb = (size_t)nrows * m->D * es;
     int64_t slab = (int64_t)((size_t)(128u << 20) / std::max(wb, xb));
     slab = std::max<int64_t>(32, std::min<int64_t>(slab, npaths));
-    if ((rc = g.win[0].ensure((size_t)slab * wb))) return rc;
-    if ((rc = g.slab[0].ensure((size_t)slab * xb))) return rc;
-    for (int64_t s0 = 0; s0 < npaths; s0 += slab) {
+    // two slabs in flight: host -> device copy and kernel of slab i + 1 (compute stream) overlap the device -> host
+    // copy of slab i (copy stream); PCIe is full duplex, so host-resident simulate!(x, ..., w) moves both ways at once
+    const int nb = npaths > slab ? 2 : 1;
+    for (int b = 0; b < nb; b++) {
+      if ((rc = g.win[b].ensure((size_t)slab * wb))) return rc;
+      if ((rc = g.slab[b].ensure((size_t)slab * xb))) return rc;
+    }
+    bool used[2] = {false, false};
+    int b = 0;
+    for (int64_t s0 = 0; s0 < npaths; s0 += slab, b ^= 1) {
       const int64_t n = std::min<int64_t>(slab, npaths - s0);
       const void *wsrc = (const char *)w + (size_t)s0 * wb;
-      CU(cudaMemcpyAsync(g.win[0].p, wsrc, (size_t)n * wb, wdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-      if ((rc = launch_simw(kt, m, o, a, nrows, n, g.win[0].p, g.slab[0].p, st))) return rc;
-      CU(cudaMemcpyAsync((char *)x + (size_t)s0 * xb, g.slab[0].p, (size_t)n * xb,
-                         xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
+      if (used[b]) CU(cudaStreamWaitEvent(st, g.cdone[b], 0));   // slab[b] was read by the copy of slab i - 2
+      CU(cudaMemcpyAsync(g.win[b].p, wsrc, (size_t)n * wb, wdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+      if ((rc = launch_simw(kt, m, o, a, nrows, n, g.win[b].p, g.slab[b].p, st))) return rc;
+      CU(cudaEventRecord(g.kdone[b], st));
+      CU(cudaStreamWaitEvent(g.copy, g.kdone[b], 0));
+      CU(cudaMemcpyAsync((char *)x + (size_t)s0 * xb, g.slab[b].p, (size_t)n * xb,
+                         xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, g.copy));
+      CU(cudaEventRecord(g.cdone[b], g.copy));
+      used[b] = true;
     }
+    CU(cudaStreamSynchronize(g.copy));
+    CU(cudaStreamSynchronize(st));
   }
   if ((rc = timed_end())) return rc;
   return SDEB200_OK;
