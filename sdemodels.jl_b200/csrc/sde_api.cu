@@ -921,21 +921,33 @@ extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, co
   } else {
     int64_t slab = (int64_t)((size_t)(128u << 20) / xb);
     slab = std::max<int64_t>(32, std::min<int64_t>(slab, npaths));
-    if ((rc = g.win[0].ensure((size_t)slab * xb))) return rc;
-    if ((rc = g.slab[0].ensure((size_t)slab * ob))) return rc;
-    for (int64_t s0 = 0; s0 < npaths; s0 += slab) {
+    // two slabs in flight, like the host path of simulate!(x, ..., w): the copy back of slab i overlaps slab i + 1
+    const int nb = npaths > slab ? 2 : 1;
+    for (int i = 0; i < nb; i++) {
+      if ((rc = g.win[i].ensure((size_t)slab * xb))) return rc;
+      if ((rc = g.slab[i].ensure((size_t)slab * ob))) return rc;
+    }
+    bool used[2] = {false, false};
+    int bi = 0;
+    for (int64_t s0 = 0; s0 < npaths; s0 += slab, bi ^= 1) {
       const int64_t n = std::min<int64_t>(slab, npaths - s0);
-      CU(cudaMemcpyAsync(g.win[0].p, (const char *)x + (size_t)s0 * xb, (size_t)n * xb,
+      if (used[bi]) CU(cudaStreamWaitEvent(st, g.cdone[bi], 0));
+      CU(cudaMemcpyAsync(g.win[bi].p, (const char *)x + (size_t)s0 * xb, (size_t)n * xb,
                          xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
       sde_args b = a;
       b.npaths = n;
-      b.out = g.slab[0].p;
-      b.out2 = g.win[0].p;
+      b.out = g.slab[bi].p;
+      b.out2 = g.win[bi].p;
       if ((rc = launch(k, cdiv(n, SDE_BLOCK), &b, st, smem))) return rc;
-      CU(cudaMemcpyAsync((char *)out + (size_t)s0 * ob, g.slab[0].p, (size_t)n * ob,
-                         odev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
+      CU(cudaEventRecord(g.kdone[bi], st));
+      CU(cudaStreamWaitEvent(g.copy, g.kdone[bi], 0));
+      CU(cudaMemcpyAsync((char *)out + (size_t)s0 * ob, g.slab[bi].p, (size_t)n * ob,
+                         odev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, g.copy));
+      CU(cudaEventRecord(g.cdone[bi], g.copy));
+      used[bi] = true;
     }
+    CU(cudaStreamSynchronize(g.copy));
+    CU(cudaStreamSynchronize(st));
   }
   return timed_end();
 }
