@@ -56,6 +56,13 @@ extern "C" {
  * without FMA contraction (bit-identical to a CPU evaluation of the Julia expressions) */
 #define SDEB200_MATH_FAST 0
 #define SDEB200_MATH_STRICT 1
+/* Normal stream versions.  Both are counter-based Philox4x32-10 streams keyed by (seed, stream, global
+ * path index, step); they differ in how many Philox bits a pair of FP64 normals consumes: v1 128 (64-bit uniform + 64-bit
+ * angle, two normals per block), v2 96 (64-bit uniform + 32-bit angle, eight normals per three blocks: -25 % generator
+ * work).  FP32 runs use the same stream under both.  A given (seed, ...) produces DIFFERENT numbers under v1 and v2. */
+#define SDEB200_RNG_DEFAULT 0
+#define SDEB200_RNG_V1 1
+#define SDEB200_RNG_V2 2
 /* full-trajectory layouts */
 #define SDEB200_LAYOUT_REFERENCE 0 /* [path][time][D] — what simulate returns (simulation.jl:71-76) */
 #define SDEB200_LAYOUT_SOA 1       /* [time][D][path] — coalesced device layout */
@@ -72,7 +79,7 @@ typedef struct {
   int32_t scheme;      /* SDEB200_EULER_MARUYAMA | SDEB200_MILSTEIN | SDEB200_RUNGE_KUTTA | SDEB200_EXACT */
   int32_t precision;   /* SDEB200_F64 | SDEB200_F32 */
   int32_t math;        /* SDEB200_MATH_FAST | SDEB200_MATH_STRICT */
-  int32_t reserved;
+  int32_t rng;         /* SDEB200_RNG_DEFAULT (= v1) | SDEB200_RNG_V1 | SDEB200_RNG_V2: version of the normal stream */
   double t0;           /* start time (argument t0 of sample/simulate) */
   double dt;           /* scheme.Δt (src/schemes/schemes.jl:5-7) */
   uint64_t seed;       /* Philox key — replaces Random.seed! on the process-global RNG */

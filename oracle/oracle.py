@@ -44,7 +44,8 @@ def lib():
         L.oracle_cost.restype = None
         L.oracle_normals_f64.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int64, _dp]
         L.oracle_normals_f32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int64, _dp]
-        L.oracle_normals_f64.restype = L.oracle_normals_f32.restype = None
+        L.oracle_normals_f64_v2.argtypes = L.oracle_normals_f64.argtypes
+        L.oracle_normals_f64.restype = L.oracle_normals_f32.restype = L.oracle_normals_f64_v2.restype = None
         _lib = L
     return _lib
 
@@ -92,51 +93,74 @@ def diffusion(model, params, t, x):
     return out
 
 
-def sample_z(model, scheme, params, t0, dt, x0, z):
+def _rt(precision):
+    """(numpy dtype, symbol prefix) of the arithmetic the loops run in: the reference's Float64, or float — the same
+    loops restated in FP32 (oracle_f32_*), the bit-exact model of the STRICT FP32 kernels."""
+    return (np.float32, "oracle_f32_") if precision in ("f32", "float32") else (np.float64, "oracle_")
+
+
+def step(model, scheme, params, dt, t, x0, dw, precision="f64"):
+    """step(model, scheme, t0, x0, Δw): src/schemes/euler_maruyama.jl:1-6, milstein.jl:4-10, runge_kutta.jl:4-11."""
+    D, M, _ = dims(model)
+    rt, pre = _rt(precision)
+    p, xx = _pv(params), _vec(x0)
+    dww = np.ascontiguousarray(np.atleast_1d(np.asarray(dw, dtype=rt)))
+    out = np.zeros(D, dtype=rt)
+    rc = getattr(lib(), pre + "step")(model_id(model), scheme, _ptr(p), C.c_double(dt), C.c_double(t), _ptr(xx), _ptr(dww), _ptr(out))
+    if rc:
+        raise RuntimeError(f"oracle_step rc={rc}")
+    return out
+
+
+def sample_z(model, scheme, params, t0, dt, x0, z, precision="f64"):
     """simulation.jl:39-48,59-67 with supplied normals z[npaths, nsteps, max(M,1)] -> [npaths, D]."""
     D, M, _ = dims(model)
-    z = np.ascontiguousarray(z, dtype=np.float64)
+    rt, pre = _rt(precision)
+    z = np.ascontiguousarray(z, dtype=rt)
     npaths, nsteps = z.shape[0], z.shape[1]
-    out = np.zeros((npaths, D))
+    out = np.zeros((npaths, D), dtype=rt)
     p, xx = _pv(params), _vec(x0)
-    rc = lib().oracle_sample_z(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt), _ptr(xx),
+    rc = getattr(lib(), pre + "sample_z")(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt), _ptr(xx),
                                C.c_int64(nsteps), C.c_int64(npaths), _ptr(z), _ptr(out))
     if rc:
         raise RuntimeError(f"oracle_sample_z rc={rc}")
     return out
 
 
-def wiener_z(dt, z):
+def wiener_z(dt, z, precision="f64"):
     """wiener! (simulation.jl:22-35): z[npaths, nrows-1, dim] -> w[npaths, nrows, dim]."""
-    z = np.ascontiguousarray(z, dtype=np.float64)
+    rt, pre = _rt(precision)
+    z = np.ascontiguousarray(z, dtype=rt)
     npaths, nm1, dim = z.shape
-    w = np.zeros((npaths, nm1 + 1, dim))
-    lib().oracle_wiener_z(C.c_double(dt), C.c_int64(nm1 + 1), C.c_int64(npaths), C.c_int(dim), _ptr(z), _ptr(w))
+    w = np.zeros((npaths, nm1 + 1, dim), dtype=rt)
+    getattr(lib(), pre + "wiener_z")(C.c_double(dt), C.c_int64(nm1 + 1), C.c_int64(npaths), C.c_int(dim), _ptr(z), _ptr(w))
     return w
 
 
-def simulate_z(model, scheme, params, t0, dt, x0, z):
+def simulate_z(model, scheme, params, t0, dt, x0, z, precision="f64"):
     """simulate! (simulation.jl:104-117): z[npaths, nsteps, max(M,1)] -> x[npaths, nsteps+1, D]."""
     D, M, _ = dims(model)
-    z = np.ascontiguousarray(z, dtype=np.float64)
+    rt, pre = _rt(precision)
+    z = np.ascontiguousarray(z, dtype=rt)
     npaths, nsteps = z.shape[0], z.shape[1]
-    x = np.zeros((npaths, nsteps + 1, D))
+    x = np.zeros((npaths, nsteps + 1, D), dtype=rt)
     p, xx = _pv(params), _vec(x0)
-    rc = lib().oracle_simulate_z(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt), _ptr(xx),
+    rc = getattr(lib(), pre + "simulate_z")(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt), _ptr(xx),
                                  C.c_int64(nsteps + 1), C.c_int64(npaths), _ptr(z), _ptr(x))
     if rc:
         raise RuntimeError(f"oracle_simulate_z rc={rc}")
     return x
 
 
-def simulate_wiener(model, scheme, params, t0, dt, x0, w, inplace=False):
+def simulate_wiener(model, scheme, params, t0, dt, x0, w, inplace=False, precision="f64"):
     """simulate!(x, model, scheme, t0, x0, w) (simulation.jl:119-134): w[npaths, nrows, M] -> x[npaths, nrows, D]."""
     D, M, _ = dims(model)
-    w = np.ascontiguousarray(w, dtype=np.float64)
+    rt, pre = _rt(precision)
+    w = np.ascontiguousarray(w, dtype=rt)
     npaths, nrows = w.shape[0], w.shape[1]
-    x = w if inplace else np.zeros((npaths, nrows, D))
+    x = w if inplace else np.zeros((npaths, nrows, D), dtype=rt)
     p, xx = _pv(params), _vec(x0)
-    rc = lib().oracle_simulate_wiener(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt), _ptr(xx),
+    rc = getattr(lib(), pre + "simulate_wiener")(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt), _ptr(xx),
                                       C.c_int64(nrows), C.c_int64(npaths), _ptr(w), _ptr(x))
     if rc:
         raise RuntimeError(f"oracle_simulate_wiener rc={rc}")
@@ -173,15 +197,16 @@ def cost(substeps, level_lo, level_hi, n):
     return out
 
 
-def multilevel_sample_z(model, scheme, params, t0, dt_coarse, dt_fine, substeps, x0, z):
+def multilevel_sample_z(model, scheme, params, t0, dt_coarse, dt_fine, substeps, x0, z, precision="f64"):
     """_multilevel_sample (multilevel.jl:65-89): z[npaths, ncoarse*substeps, M] -> (xc, xf) each [npaths, D]."""
     D, M, _ = dims(model)
-    z = np.ascontiguousarray(z, dtype=np.float64)
+    rt, pre = _rt(precision)
+    z = np.ascontiguousarray(z, dtype=rt)
     npaths, nfine = z.shape[0], z.shape[1]
     assert nfine % substeps == 0
-    xc, xf = np.zeros((npaths, D)), np.zeros((npaths, D))
+    xc, xf = np.zeros((npaths, D), dtype=rt), np.zeros((npaths, D), dtype=rt)
     p, xx = _pv(params), _vec(x0)
-    rc = lib().oracle_multilevel_sample_z(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt_coarse),
+    rc = getattr(lib(), pre + "multilevel_sample_z")(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt_coarse),
                                           C.c_double(dt_fine), C.c_int64(substeps), _ptr(xx),
                                           C.c_int64(nfine // substeps), C.c_int64(npaths), _ptr(z), _ptr(xc), _ptr(xf))
     if rc:
@@ -189,15 +214,16 @@ def multilevel_sample_z(model, scheme, params, t0, dt_coarse, dt_fine, substeps,
     return xc, xf
 
 
-def multilevel_simulate_z(model, scheme, params, t0, dt_coarse, dt_fine, substeps, x0, z):
+def multilevel_simulate_z(model, scheme, params, t0, dt_coarse, dt_fine, substeps, x0, z, precision="f64"):
     """_multilevel_simulate (multilevel.jl:91-100): z[npaths, ncoarse*substeps, D] -> (xc, xf) full paths."""
     D, M, _ = dims(model)
-    z = np.ascontiguousarray(z, dtype=np.float64)
+    rt, pre = _rt(precision)
+    z = np.ascontiguousarray(z, dtype=rt)
     npaths, nfine = z.shape[0], z.shape[1]
     nsteps = nfine // substeps
-    xc, xf = np.zeros((npaths, nsteps + 1, D)), np.zeros((npaths, nfine + 1, D))
+    xc, xf = np.zeros((npaths, nsteps + 1, D), dtype=rt), np.zeros((npaths, nfine + 1, D), dtype=rt)
     p, xx = _pv(params), _vec(x0)
-    rc = lib().oracle_multilevel_simulate_z(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt_coarse),
+    rc = getattr(lib(), pre + "multilevel_simulate_z")(model_id(model), scheme, _ptr(p), C.c_double(t0), C.c_double(dt_coarse),
                                             C.c_double(dt_fine), C.c_int64(substeps), _ptr(xx), C.c_int64(nsteps),
                                             C.c_int64(npaths), _ptr(z), _ptr(xc), _ptr(xf))
     if rc:
@@ -213,20 +239,22 @@ def philox4x32_10(ctr, key):
     return [int(v) for v in o]
 
 
-def normals(seed, stream, path, q0, n, precision="f64"):
-    """The sdeb200 normal stream v1: normals q0..q0+n-1 of one path's sub-stream."""
+def normals(seed, stream, path, q0, n, precision="f64", rng=1):
+    """The sdeb200 normal stream: normals q0..q0+n-1 of one path's sub-stream.  rng = 1 | 2 selects the
+    stream version (FP64 only; the FP32 stream is the same in both)."""
     out = np.zeros(n)
-    fn = lib().oracle_normals_f64 if precision == "f64" else lib().oracle_normals_f32
+    L = lib()
+    fn = (L.oracle_normals_f64_v2 if rng == 2 else L.oracle_normals_f64) if precision == "f64" else L.oracle_normals_f32
     fn(C.c_uint64(seed), C.c_uint32(stream), C.c_uint64(path), C.c_uint64(q0), C.c_int64(n), out)
     return out
 
 
-def normals_paths(seed, stream, path0, npaths, nsteps, M, precision="f64"):
+def normals_paths(seed, stream, path0, npaths, nsteps, M, precision="f64", rng=1):
     """z[npaths, nsteps, M] as the RNG-driven kernels consume them (flat index q = step*M + j)."""
     z = np.zeros((npaths, nsteps, max(M, 1)))
     if M > 0:
         for k in range(npaths):
-            z[k] = normals(seed, stream, path0 + k, 0, nsteps * M, precision).reshape(nsteps, M)
+            z[k] = normals(seed, stream, path0 + k, 0, nsteps * M, precision, rng).reshape(nsteps, M)
     return z
 
 

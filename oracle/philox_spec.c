@@ -93,3 +93,41 @@ void oracle_normals_f32(uint64_t seed, uint32_t stream, uint64_t path, uint64_t 
     out[i] = z[q & 3];
   }
 }
+
+/* "sdeb200 normal stream v2" (FP64; opt-in, sdeb200_opts.rng = 2): the path's Philox output is a stream of 32-bit words,
+ * word W = lane W % 4 of block W / 4 (counter (path_lo, path_hi, W / 4, stream)); pair P reads words 3P, 3P+1, 3P+2:
+ * X1 = w[3P+1]:w[3P] gives u1 exactly as in v1, c = w[3P+2] is the angle in units of 2^-32 turns.  Normal q of the
+ * path is element q % 2 of pair q / 2 (even -> cos, odd -> sin). */
+static uint32_t stream_word(uint64_t seed, uint32_t stream, uint64_t path, uint64_t W) {
+  uint32_t ctr[4] = {(uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(W >> 2), stream};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, r[4];
+  oracle_philox4x32_10(ctr, key, r);
+  return r[W & 3];
+}
+
+static void pair_f64_v2(uint64_t seed, uint32_t stream, uint64_t path, uint64_t P, double z[2]) {
+  const uint32_t a = stream_word(seed, stream, path, 3 * P), b = stream_word(seed, stream, path, 3 * P + 1),
+                 c = stream_word(seed, stream, path, 3 * P + 2);
+  const uint64_t X1 = ((uint64_t)b << 32) | a;
+  long double w;
+  if (X1 == 0) {
+    w = 2.0L * 1087.0L * 0.693147180559945309417232121458176568L;
+  } else {
+    double d1 = (double)X1; /* round-to-nearest conversion, as cvt.rn.f64.u64 */
+    w = -2.0L * logl((long double)d1 * 0x1.0p-64L);
+  }
+  w += 0x1.0p-50L;
+  const long double phi = TWO_PI_L * ((long double)c * 0x1.0p-32L);
+  const long double rad = sqrtl(w);
+  z[0] = (double)(rad * cosl(phi));
+  z[1] = (double)(rad * sinl(phi));
+}
+
+void oracle_normals_f64_v2(uint64_t seed, uint32_t stream, uint64_t path, uint64_t q0, int64_t n, double *out) {
+  for (int64_t i = 0; i < n; i++) {
+    uint64_t q = q0 + (uint64_t)i;
+    double z[2];
+    pair_f64_v2(seed, stream, path, q >> 1, z);
+    out[i] = z[q & 1];
+  }
+}

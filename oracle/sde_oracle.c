@@ -31,6 +31,27 @@
 #define MAXD 4
 #define MAXM 4
 
+/* Arithmetic type of the restated loops.  The reference is Float64 only; the FP32 variants of the CUDA kernels
+ * are a new-framework addition.  Compiling this file a second time with -DORACLE_REAL_FLOAT restates the SAME loops in
+ * float (state, increments, parameters, Δt and times all rounded to float first, every operation a float operation,
+ * -ffp-contract=off) and exports them as oracle_f32_*: the STRICT FP32 kernels must equal that bit for bit, which separates
+ * kernel errors from the conditioning of FP32 arithmetic itself.  API: parameters / t0 / Δt / x0 arrive as double and are
+ * rounded once, arrays are `real`. */
+#ifdef ORACLE_REAL_FLOAT
+typedef float real;
+#define FN(name) oracle_f32_##name
+#define R_SQRT sqrtf
+#define R_EXP expf
+#define R_LOG logf
+#else
+typedef double real;
+#define FN(name) oracle_##name
+#define R_SQRT sqrt
+#define R_EXP exp
+#define R_LOG log
+#endif
+#define MAXP 16
+
 /* ------------------------------------------------------------------------------------------
  * Model functors: what `@sde_model` generates (src/models/codegen.jl:57-75,105-112) for the
  * registry models (src/models/models.jl:39-54, black_scholes.jl:1, cox_ingersoll_ross.jl:1,
@@ -38,11 +59,11 @@
  * diffusion is D x M, stored sig[i*MAXM + j]; correlation Cholesky already folded in
  * (codegen.jl:112).  dsig[i*MAXD + k] = d sigma_i / d x_k for M == 1 models (milstein.jl:1-2).
  * ------------------------------------------------------------------------------------------ */
-typedef void (*coef_fn)(const double *p, double t, const double *x, double *out);
+typedef void (*coef_fn)(const real *p, real t, const real *x, real *out);
 
 /* Exact one-step sampler given the standard normal the distribution's rand() would draw
  * (Distributions 0.21: rand(LogNormal(μ,σ)) = exp(randn()*σ + μ), rand(Normal(μ,σ)) = μ + σ*randn()). */
-typedef void (*exact_fn)(const double *p, double dt, const double *x0, double z, double *x1);
+typedef void (*exact_fn)(const real *p, real dt, const real *x0, real z, real *x1);
 
 typedef struct {
   const char *name;
@@ -52,111 +73,111 @@ typedef struct {
 } model_def;
 
 /* BlackScholes: dS = r*S*dt + σ*S*dW            params (r, σ)   black_scholes.jl:1 */
-static void bs_drift(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[0] * x[0]; }
-static void bs_diff(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[1] * x[0]; }
-static void bs_ddiff(const double *p, double t, const double *x, double *o) { (void)t; (void)x; o[0] = p[1]; }
+static void bs_drift(const real *p, real t, const real *x, real *o) { (void)t; o[0] = p[0] * x[0]; }
+static void bs_diff(const real *p, real t, const real *x, real *o) { (void)t; o[0] = p[1] * x[0]; }
+static void bs_ddiff(const real *p, real t, const real *x, real *o) { (void)t; (void)x; o[0] = p[1]; }
 
 /* sample(model::BlackScholes, scheme::Exact, t0, x0): black_scholes.jl:3-13 */
-static void bs_exact(const double *p, double dt, const double *x0, double z, double *x1) {
-  double mu = log(x0[0]) + (p[0] - 0.5 * (p[1] * p[1])) * dt;
-  double d = sqrt(dt) * p[1];
-  x1[0] = exp(z * d + mu);
+static void bs_exact(const real *p, real dt, const real *x0, real z, real *x1) {
+  real mu = R_LOG(x0[0]) + (p[0] - (real)0.5 * (p[1] * p[1])) * dt;
+  real d = R_SQRT(dt) * p[1];
+  x1[0] = R_EXP(z * d + mu);
 }
 
-/* Heston: models.jl:44-48, params (r, κ, θ, σ, ρ); generated form README.md:42-59 / SURVEY §3.5 */
-static void heston_drift(const double *p, double t, const double *x, double *o) {
+/* Heston: models.jl:44-48, params (r, κ, θ, σ, ρ); generated form README.md:42-59 / SURVEY §(real)3.5 */
+static void heston_drift(const real *p, real t, const real *x, real *o) {
   (void)t;
   o[0] = p[0] * x[0];
   o[1] = p[1] * (p[2] - x[1]);
 }
-static void heston_diff(const double *p, double t, const double *x, double *o) {
+static void heston_diff(const real *p, real t, const real *x, real *o) {
   (void)t;
-  double sv = sqrt(x[1]);
+  real sv = R_SQRT(x[1]);
   o[0 * MAXM + 0] = sv * x[0];
-  o[0 * MAXM + 1] = 0.0;
+  o[0 * MAXM + 1] = (real)0.0;
   o[1 * MAXM + 0] = (p[3] * sv) * p[4];
-  o[1 * MAXM + 1] = (p[3] * sv) * sqrt(1.0 - p[4] * p[4]);
+  o[1 * MAXM + 1] = (p[3] * sv) * R_SQRT((real)1.0 - p[4] * p[4]);
 }
 
 /* Deterministic: dX = X*dt (runtests.jl:24), D=1, M=0 */
-static void det_drift(const double *p, double t, const double *x, double *o) { (void)p; (void)t; o[0] = x[0]; }
-static void zero_diff(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; o[0] = 0.0; }
+static void det_drift(const real *p, real t, const real *x, real *o) { (void)p; (void)t; o[0] = x[0]; }
+static void zero_diff(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; o[0] = (real)0.0; }
 
 /* Wiener: dX = dW (runtests.jl:23) */
-static void wien_drift(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; o[0] = 0.0; }
-static void wien_diff(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; o[0] = 1.0; }
-static void wien_ddiff(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; o[0] = 0.0; }
+static void wien_drift(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; o[0] = (real)0.0; }
+static void wien_diff(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; o[0] = (real)1.0; }
+static void wien_ddiff(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; o[0] = (real)0.0; }
 
 /* TimeDependent: dX = t*a*X*dt + b*X*dW (runtests.jl:25), params (a, b) */
-static void td_drift(const double *p, double t, const double *x, double *o) { o[0] = (t * p[0]) * x[0]; }
-static void td_diff(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[1] * x[0]; }
-static void td_ddiff(const double *p, double t, const double *x, double *o) { (void)t; (void)x; o[0] = p[1]; }
+static void td_drift(const real *p, real t, const real *x, real *o) { o[0] = (t * p[0]) * x[0]; }
+static void td_diff(const real *p, real t, const real *x, real *o) { (void)t; o[0] = p[1] * x[0]; }
+static void td_ddiff(const real *p, real t, const real *x, real *o) { (void)t; (void)x; o[0] = p[1]; }
 
 /* TestModel (runtests.jl:17-21), params (a, c, e, b, d, f), D=3, M=4 */
-static void tm_drift(const double *p, double t, const double *x, double *o) {
+static void tm_drift(const real *p, real t, const real *x, real *o) {
   (void)t;
   o[0] = x[1] * p[0];
   o[1] = x[2] * p[1];
   o[2] = x[0] * p[2];
 }
-static void tm_diff(const double *p, double t, const double *x, double *o) {
+static void tm_diff(const real *p, real t, const real *x, real *o) {
   (void)t; (void)x;
-  for (int i = 0; i < 3 * MAXM; i++) o[i] = 0.0;
+  for (int i = 0; i < 3 * MAXM; i++) o[i] = (real)0.0;
   o[0 * MAXM + 0] = p[3]; o[0 * MAXM + 1] = p[4];
-  o[1 * MAXM + 1] = 1.0;  o[1 * MAXM + 2] = 1.0;
-  o[2 * MAXM + 2] = p[5]; o[2 * MAXM + 3] = -1.0;
+  o[1 * MAXM + 1] = (real)1.0;  o[1 * MAXM + 2] = (real)1.0;
+  o[2 * MAXM + 2] = p[5]; o[2 * MAXM + 3] = -(real)1.0;
 }
 
 /* SpecialCaseModel1-3 (runtests.jl:28-41) */
-static void zero_drift3(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; o[0] = o[1] = o[2] = 0.0; }
-static void sc1_diff(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; o[0] = 1.0; o[1] = 1.0; }
-static void sc2_diff(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; o[0 * MAXM] = 1.0; o[1 * MAXM] = 1.0; }
-static void sc2_ddiff(const double *p, double t, const double *x, double *o) { (void)p; (void)t; (void)x; for (int i = 0; i < MAXD * MAXD; i++) o[i] = 0.0; }
-static void sc3_diff(const double *p, double t, const double *x, double *o) {
+static void zero_drift3(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; o[0] = o[1] = o[2] = (real)0.0; }
+static void sc1_diff(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; o[0] = (real)1.0; o[1] = (real)1.0; }
+static void sc2_diff(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; o[0 * MAXM] = (real)1.0; o[1 * MAXM] = (real)1.0; }
+static void sc2_ddiff(const real *p, real t, const real *x, real *o) { (void)p; (void)t; (void)x; for (int i = 0; i < MAXD * MAXD; i++) o[i] = (real)0.0; }
+static void sc3_diff(const real *p, real t, const real *x, real *o) {
   (void)p; (void)t; (void)x;
-  o[0 * MAXM + 0] = 1.0; o[0 * MAXM + 1] = 0.0;
-  o[1 * MAXM + 0] = 1.0; o[1 * MAXM + 1] = 1.0;
-  o[2 * MAXM + 0] = 0.0; o[2 * MAXM + 1] = 1.0;
+  o[0 * MAXM + 0] = (real)1.0; o[0 * MAXM + 1] = (real)0.0;
+  o[1 * MAXM + 0] = (real)1.0; o[1 * MAXM + 1] = (real)1.0;
+  o[2 * MAXM + 0] = (real)0.0; o[2 * MAXM + 1] = (real)1.0;
 }
 
-/* CoxIngersollRoss: dr = κ*(θ-r)*dt + σ*sqrt(r)*dW (cox_ingersoll_ross.jl:1), params (κ, θ, σ) */
-static void cir_drift(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[0] * (p[1] - x[0]); }
-static void cir_diff(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[2] * sqrt(x[0]); }
-static void cir_ddiff(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[2] * (0.5 / sqrt(x[0])); }
+/* CoxIngersollRoss: dr = κ*(θ-r)*dt + σ*R_SQRT(r)*dW (cox_ingersoll_ross.jl:1), params (κ, θ, σ) */
+static void cir_drift(const real *p, real t, const real *x, real *o) { (void)t; o[0] = p[0] * (p[1] - x[0]); }
+static void cir_diff(const real *p, real t, const real *x, real *o) { (void)t; o[0] = p[2] * R_SQRT(x[0]); }
+static void cir_ddiff(const real *p, real t, const real *x, real *o) { (void)t; o[0] = p[2] * ((real)0.5 / R_SQRT(x[0])); }
 
 /* OrnsteinUhlenbeck: dx = θ*(μ-x)*dt + σ*dW (ornstein_uhlenbeck.jl:1), params (θ, μ, σ) */
-static void ou_drift(const double *p, double t, const double *x, double *o) { (void)t; o[0] = p[0] * (p[1] - x[0]); }
-static void ou_diff(const double *p, double t, const double *x, double *o) { (void)t; (void)x; o[0] = p[2]; }
+static void ou_drift(const real *p, real t, const real *x, real *o) { (void)t; o[0] = p[0] * (p[1] - x[0]); }
+static void ou_diff(const real *p, real t, const real *x, real *o) { (void)t; (void)x; o[0] = p[2]; }
 
 /* sample(model::OrnsteinUhlenbeck, scheme::Exact, t0, x0): ornstein_uhlenbeck.jl:3-13 */
-static void ou_exact(const double *p, double dt, const double *x0, double z, double *x1) {
-  double m = x0[0] * exp(-p[0] * dt) + p[1] * (1.0 - exp(-p[0] * dt));
-  double d = sqrt(1.0 - exp(-2.0 * p[0] * dt)) * p[2] / sqrt(2.0 * p[0]);
+static void ou_exact(const real *p, real dt, const real *x0, real z, real *x1) {
+  real m = x0[0] * R_EXP(-p[0] * dt) + p[1] * ((real)1.0 - R_EXP(-p[0] * dt));
+  real d = R_SQRT((real)1.0 - R_EXP(-(real)2.0 * p[0] * dt)) * p[2] / R_SQRT((real)2.0 * p[0]);
   x1[0] = m + d * z;
 }
 
 /* FitzHughNagumo (models.jl:39-42), params (ɛ, s, γ, β, σ1, σ2), D=2, M=2 */
-static void fhn_drift(const double *p, double t, const double *x, double *o) {
+static void fhn_drift(const real *p, real t, const real *x, real *o) {
   (void)t;
   o[0] = p[0] * (((x[0] - x[0] * x[0] * x[0]) - x[1]) + p[1]);
   o[1] = ((p[2] * x[0]) - x[1]) + p[3];
 }
-static void fhn_diff(const double *p, double t, const double *x, double *o) {
+static void fhn_diff(const real *p, real t, const real *x, real *o) {
   (void)t; (void)x;
-  o[0 * MAXM + 0] = p[4]; o[0 * MAXM + 1] = 0.0;
-  o[1 * MAXM + 0] = 0.0;  o[1 * MAXM + 1] = p[5];
+  o[0 * MAXM + 0] = p[4]; o[0 * MAXM + 1] = (real)0.0;
+  o[1 * MAXM + 0] = (real)0.0;  o[1 * MAXM + 1] = p[5];
 }
 
 /* Lorenz (models.jl:50-54), params (σ, ρ, β, σ1, σ2, σ3), D=3, M=3 */
-static void lor_drift(const double *p, double t, const double *x, double *o) {
+static void lor_drift(const real *p, real t, const real *x, real *o) {
   (void)t;
   o[0] = p[0] * (x[1] - x[0]);
   o[1] = x[0] * (p[1] - x[2]) - x[1];
   o[2] = x[0] * x[1] - p[2] * x[2];
 }
-static void lor_diff(const double *p, double t, const double *x, double *o) {
+static void lor_diff(const real *p, real t, const real *x, real *o) {
   (void)t; (void)x;
-  for (int i = 0; i < 3 * MAXM; i++) o[i] = 0.0;
+  for (int i = 0; i < 3 * MAXM; i++) o[i] = (real)0.0;
   o[0 * MAXM + 0] = p[3]; o[1 * MAXM + 1] = p[4]; o[2 * MAXM + 2] = p[5];
 }
 
@@ -181,6 +202,7 @@ static const model_def MODELS[M_COUNT] = {
   {"Lorenz", 3, 3, 6, lor_drift, lor_diff, 0, 0},
 };
 
+#ifndef ORACLE_REAL_FLOAT
 int oracle_model_count(void) { return M_COUNT; }
 const char *oracle_model_name(int id) { return (id >= 0 && id < M_COUNT) ? MODELS[id].name : 0; }
 int oracle_model_dims(int id, int *D, int *M, int *np) {
@@ -189,24 +211,33 @@ int oracle_model_dims(int id, int *D, int *M, int *np) {
   return 0;
 }
 /* dense (unpadded) outputs: mu[D]; sig[D*M] row-major */
-int oracle_drift(int id, const double *p, double t, const double *x, double *mu) {
+int oracle_drift(int id, const real *p, real t, const real *x, real *mu) {
   if (id < 0 || id >= M_COUNT) return -1;
-  double o[MAXD];
+  real o[MAXD];
   MODELS[id].drift(p, t, x, o);
   for (int i = 0; i < MODELS[id].D; i++) mu[i] = o[i];
   return 0;
 }
-int oracle_diffusion(int id, const double *p, double t, const double *x, double *sig) {
+int oracle_diffusion(int id, const real *p, real t, const real *x, real *sig) {
   if (id < 0 || id >= M_COUNT) return -1;
   const model_def *m = &MODELS[id];
-  double o[MAXD * MAXM];
+  real o[MAXD * MAXM];
   memset(o, 0, sizeof o);
   m->diffusion(p, t, x, o);
-  if (m->M == 0) { sig[0] = 0.0; return 0; } /* `diffusion = 0` for M == 0, codegen.jl:112 */
+  if (m->M == 0) { sig[0] = (real)0.0; return 0; } /* `diffusion = 0` for M == 0, codegen.jl:112 */
   for (int i = 0; i < m->D; i++)
     for (int j = 0; j < m->M; j++) sig[i * m->M + j] = o[i * MAXM + j];
   return 0;
 }
+
+#endif /* !ORACLE_REAL_FLOAT */
+
+/* API boundary: double arguments are rounded to `real` once (identity in the Float64 build), as the kernels do with
+ * their argument block ((T)a.params[i], (T)a.dt, (T)a.t0, (T)a.x0[d]: sde_device.cuh). */
+#define CONV_ARGS(m)                                                           \
+  real p[MAXP], x0[MAXD];                                                      \
+  for (int i_ = 0; i_ < MAXP; i_++) p[i_] = i_ < (m)->nparams ? (real)p_in[i_] : (real)0; \
+  for (int i_ = 0; i_ < (m)->D; i_++) x0[i_] = (real)x0_in[i_];
 
 /* ------------------------------------------------------------------------------------------
  * step: src/schemes/euler_maruyama.jl:1-6 and src/schemes/milstein.jl:4-10.
@@ -215,26 +246,26 @@ int oracle_diffusion(int id, const double *p, double t, const double *x, double 
  * scheme: 0 = EulerMaruyama, 1 = Milstein, 2 = RungeKutta (src/schemes/runge_kutta.jl:4-11, the derivative-free
  * Milstein); 1 and 2 for M == 1 only, as in the reference.
  * ------------------------------------------------------------------------------------------ */
-static int step(const model_def *m, int scheme, const double *p, double dt, double t, const double *x0,
-                const double *dw, double *x1) {
+static int step(const model_def *m, int scheme, const real *p, real dt, real t, const real *x0,
+                const real *dw, real *x1) {
   if (scheme == 3) { /* Exact: `dw` carries the plain standard normal (src/simulation.jl:50-57 calls sample(model, Exact, t, x)) */
     if (!m->exact) return -2;
     m->exact(p, dt, x0, dw[0], x1);
     return 0;
   }
-  double mu[MAXD], sig[MAXD * MAXM];
+  real mu[MAXD], sig[MAXD * MAXM];
   memset(sig, 0, sizeof sig);
   m->drift(p, t, x0, mu);
   m->diffusion(p, t, x0, sig);
   if (scheme == 0) {
     for (int i = 0; i < m->D; i++) {
-      double a = x0[i] + mu[i] * dt;
+      real a = x0[i] + mu[i] * dt;
       if (m->M > 0) {
-        double s = sig[i * MAXM] * dw[0];
+        real s = sig[i * MAXM] * dw[0];
         for (int j = 1; j < m->M; j++) s = s + sig[i * MAXM + j] * dw[j];
         a = a + s;
       } else {
-        a = a + 0.0 * dw[0]; /* σ == 0.0, Δw == 0.0 for AbstractSDE{1,0} (simulation.jl:6) */
+        a = a + (real)0.0 * dw[0]; /* σ == (real)0.0, Δw == (real)0.0 for AbstractSDE{1,0} (simulation.jl:6) */
       }
       x1[i] = a;
     }
@@ -242,30 +273,30 @@ static int step(const model_def *m, int scheme, const double *p, double dt, doub
   }
   if (scheme == 1) {
     if (m->M != 1 || !m->ddiffusion) return -2; /* no Milstein method for M != 1 (milstein.jl:4) */
-    double ds[MAXD * MAXD];
+    real ds[MAXD * MAXD];
     m->ddiffusion(p, t, x0, ds);
-    double c = dw[0] * dw[0] - dt; /* Δw.^2 - Δt */
+    real c = dw[0] * dw[0] - dt; /* Δw.^2 - Δt */
     for (int i = 0; i < m->D; i++) {
-      double js; /* (∂σ*σ)[i] */
+      real js; /* (∂σ*σ)[i] */
       if (m->D == 1) js = ds[0] * sig[0];
       else {
         js = ds[i * MAXD] * sig[0];
         for (int k = 1; k < m->D; k++) js = js + ds[i * MAXD + k] * sig[k * MAXM];
       }
-      x1[i] = ((x0[i] + mu[i] * dt) + sig[i * MAXM] * dw[0]) + (js * c) / 2.0;
+      x1[i] = ((x0[i] + mu[i] * dt) + sig[i * MAXM] * dw[0]) + (js * c) / (real)2.0;
     }
     return 0;
   }
   if (scheme == 2) {
-    /* x0hat = x0 + μ*Δt + vec(σ)*sqrt(Δt); σpred = diffusion(model, t0, x0hat);
-     * x = x0 + μ*Δt + σ*Δw + (σpred - σ)*(Δw.^2 - Δt)/(2*sqrt(Δt))          runge_kutta.jl:7-9 */
+    /* x0hat = x0 + μ*Δt + vec(σ)*R_SQRT(Δt); σpred = diffusion(model, t0, x0hat);
+     * x = x0 + μ*Δt + σ*Δw + (σpred - σ)*(Δw.^2 - Δt)/(2*R_SQRT(Δt))          runge_kutta.jl:7-9 */
     if (m->M != 1) return -2;
-    double xh[MAXD], sp[MAXD * MAXM];
-    const double sq = sqrt(dt);
+    real xh[MAXD], sp[MAXD * MAXM];
+    const real sq = R_SQRT(dt);
     memset(sp, 0, sizeof sp);
     for (int i = 0; i < m->D; i++) xh[i] = (x0[i] + mu[i] * dt) + sig[i * MAXM] * sq;
     m->diffusion(p, t, xh, sp);
-    const double c = dw[0] * dw[0] - dt, den = 2.0 * sq;
+    const real c = dw[0] * dw[0] - dt, den = (real)2.0 * sq;
     for (int i = 0; i < m->D; i++)
       x1[i] = ((x0[i] + mu[i] * dt) + sig[i * MAXM] * dw[0]) + ((sp[i * MAXM] - sig[i * MAXM]) * c) / den;
     return 0;
@@ -273,10 +304,10 @@ static int step(const model_def *m, int scheme, const double *p, double dt, doub
   return -3;
 }
 
-int oracle_step(int id, int scheme, const double *p, double dt, double t, const double *x0, const double *dw,
-                double *x1) {
+int FN(step)(int id, int scheme, const double *p_in, double dt, double t, const double *x0_in, const real *dw, real *x1) {
   if (id < 0 || id >= M_COUNT) return -1;
-  return step(&MODELS[id], scheme, p, dt, t, x0, dw, x1);
+  CONV_ARGS(&MODELS[id])
+  return step(&MODELS[id], scheme, p, (real)dt, (real)t, x0, dw, x1);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -285,19 +316,21 @@ int oracle_step(int id, int scheme, const double *p, double dt, double t, const 
  * in the reference's draw order (path outer, step inner, M draws left to right).
  * out[npaths][D].
  * ------------------------------------------------------------------------------------------ */
-int oracle_sample_z(int id, int scheme, const double *p, double t0, double dt, const double *x0, int64_t nsteps,
-                    int64_t npaths, const double *z, double *out) {
+int FN(sample_z)(int id, int scheme, const double *p_in, double t0_in, double dt_in, const double *x0_in, int64_t nsteps,
+                 int64_t npaths, const real *z, real *out) {
   if (id < 0 || id >= M_COUNT) return -1;
   const model_def *m = &MODELS[id];
+  CONV_ARGS(m)
+  const real t0 = (real)t0_in, dt = (real)dt_in;
   const int M = m->M > 0 ? m->M : 1;
-  const double sdt = sqrt(dt);
+  const real sdt = R_SQRT(dt);
   int rc = 0;
   for (int64_t k = 0; k < npaths; k++) {
-    double x[MAXD], xn[MAXD], dw[MAXM];
+    real x[MAXD], xn[MAXD], dw[MAXM];
     for (int i = 0; i < m->D; i++) x[i] = x0[i];
     for (int64_t i = 1; i <= nsteps; i++) {
-      double ti = t0 + (double)(i - 1) * dt;
-      for (int j = 0; j < M; j++) dw[j] = (scheme == 3 ? 1.0 : sdt) * (m->M > 0 ? z[(k * nsteps + (i - 1)) * M + j] : 0.0);
+      real ti = t0 + (real)(i - 1) * dt;
+      for (int j = 0; j < M; j++) dw[j] = (scheme == 3 ? (real)1.0 : sdt) * (m->M > 0 ? z[(k * nsteps + (i - 1)) * M + j] : (real)0.0);
       rc |= step(m, scheme, p, dt, ti, x, dw, xn);
       for (int d = 0; d < m->D; d++) x[d] = xn[d];
     }
@@ -307,11 +340,12 @@ int oracle_sample_z(int id, int scheme, const double *p, double t0, double dt, c
 }
 
 /* wiener!: src/simulation.jl:22-35.  w[npaths][nrows][dim]; z[npaths][nrows-1][dim]. */
-void oracle_wiener_z(double dt, int64_t nrows, int64_t npaths, int dim, const double *z, double *w) {
-  const double s = sqrt(dt);
+void FN(wiener_z)(double dt_in, int64_t nrows, int64_t npaths, int dim, const real *z, real *w) {
+  const real dt = (real)dt_in;
+  const real s = R_SQRT(dt);
   for (int64_t k = 0; k < npaths; k++) {
-    double sum[MAXM > MAXD ? MAXM : MAXD];
-    for (int j = 0; j < dim; j++) { sum[j] = 0.0; w[(k * nrows) * dim + j] = 0.0; }
+    real sum[MAXM > MAXD ? MAXM : MAXD];
+    for (int j = 0; j < dim; j++) { sum[j] = (real)0.0; w[(k * nrows) * dim + j] = (real)0.0; }
     for (int64_t i = 1; i < nrows; i++)
       for (int j = 0; j < dim; j++) {
         sum[j] = sum[j] + s * z[(k * (nrows - 1) + (i - 1)) * dim + j];
@@ -321,19 +355,21 @@ void oracle_wiener_z(double dt, int64_t nrows, int64_t npaths, int dim, const do
 }
 
 /* simulate! driven by standard normals: src/simulation.jl:104-117.  x[npaths][nrows][D]. */
-int oracle_simulate_z(int id, int scheme, const double *p, double t0, double dt, const double *x0, int64_t nrows,
-                      int64_t npaths, const double *z, double *x) {
+int FN(simulate_z)(int id, int scheme, const double *p_in, double t0_in, double dt_in, const double *x0_in, int64_t nrows,
+                   int64_t npaths, const real *z, real *x) {
   if (id < 0 || id >= M_COUNT) return -1;
   const model_def *m = &MODELS[id];
+  CONV_ARGS(m)
+  const real t0 = (real)t0_in, dt = (real)dt_in;
   const int M = m->M > 0 ? m->M : 1, D = m->D;
-  const double sdt = sqrt(dt);
+  const real sdt = R_SQRT(dt);
   int rc = 0;
   for (int64_t k = 0; k < npaths; k++) {
-    double *xk = x + k * nrows * D;
+    real *xk = x + k * nrows * D;
     for (int d = 0; d < D; d++) xk[d] = x0[d];
     for (int64_t i = 2; i <= nrows; i++) {
-      double t = t0 + (double)(i - 2) * dt, dw[MAXM];
-      for (int j = 0; j < M; j++) dw[j] = (scheme == 3 ? 1.0 : sdt) * (m->M > 0 ? z[(k * (nrows - 1) + (i - 2)) * M + j] : 0.0);
+      real t = t0 + (real)(i - 2) * dt, dw[MAXM];
+      for (int j = 0; j < M; j++) dw[j] = (scheme == 3 ? (real)1.0 : sdt) * (m->M > 0 ? z[(k * (nrows - 1) + (i - 2)) * M + j] : (real)0.0);
       rc |= step(m, scheme, p, dt, t, xk + (i - 2) * D, dw, xk + (i - 1) * D);
     }
   }
@@ -342,20 +378,22 @@ int oracle_simulate_z(int id, int scheme, const double *p, double t0, double dt,
 
 /* simulate! driven by a cumulative Wiener path, x === w allowed: src/simulation.jl:119-134.
  * w[npaths][nrows][M], x[npaths][nrows][D] (D == M when aliased). */
-int oracle_simulate_wiener(int id, int scheme, const double *p, double t0, double dt, const double *x0,
-                           int64_t nrows, int64_t npaths, const double *w, double *x) {
+int FN(simulate_wiener)(int id, int scheme, const double *p_in, double t0_in, double dt_in, const double *x0_in,
+                        int64_t nrows, int64_t npaths, const real *w, real *x) {
   if (id < 0 || id >= M_COUNT) return -1;
   const model_def *m = &MODELS[id];
+  CONV_ARGS(m)
+  const real t0 = (real)t0_in, dt = (real)dt_in;
   const int M = m->M > 0 ? m->M : 1, D = m->D;
   int rc = 0;
   for (int64_t k = 0; k < npaths; k++) {
-    const double *wk = w + k * nrows * M;
-    double *xk = x + k * nrows * D;
-    double wprev[MAXM], wnext[MAXM], dw[MAXM], xprev[MAXD], xn[MAXD];
+    const real *wk = w + k * nrows * M;
+    real *xk = x + k * nrows * D;
+    real wprev[MAXM], wnext[MAXM], dw[MAXM], xprev[MAXD], xn[MAXD];
     for (int j = 0; j < M; j++) wprev[j] = wk[j];
     for (int d = 0; d < D; d++) { xk[d] = x0[d]; xprev[d] = x0[d]; }
     for (int64_t i = 2; i <= nrows; i++) {
-      double t = t0 + (double)(i - 2) * dt;
+      real t = t0 + (real)(i - 2) * dt;
       for (int j = 0; j < M; j++) { wnext[j] = wk[(i - 1) * M + j]; dw[j] = wnext[j] - wprev[j]; }
       rc |= step(m, scheme, p, dt, t, xprev, dw, xn);
       for (int d = 0; d < D; d++) { xk[(i - 1) * D + d] = xn[d]; xprev[d] = xn[d]; }
@@ -365,6 +403,7 @@ int oracle_simulate_wiener(int id, int scheme, const double *p, double t0, doubl
   return rc;
 }
 
+#ifndef ORACLE_REAL_FLOAT
 /* ------------------------------------------------------------------------------------------
  * logtransition(model, ::EulerMaruyama, times, data): src/schemes/schemes.jl:64-76 with
  * _normal_transition_params of euler_maruyama.jl:8-13 — Gaussian one-step log-densities along
@@ -467,28 +506,32 @@ void oracle_cost(int64_t substeps, int64_t level_lo, int64_t level_hi, const int
   for (int64_t l = level_lo; l <= level_hi; l++) cost[l - level_lo] = ipow(substeps, l) * npaths[l - level_lo];
 }
 
+#endif /* !ORACLE_REAL_FLOAT */
+
 /* _multilevel_sample, one coupled level pair: multilevel.jl:65-89.
  * z[npaths][nsteps*substeps][M] fine-step normals; nsteps = number of COARSE steps.
  * xc[npaths][D], xf[npaths][D].  Requires D == M (or scalar), as the reference does (Δw = zero(T2)). */
-int oracle_multilevel_sample_z(int id, int scheme, const double *p, double t0, double dt_coarse, double dt_fine,
-                               int64_t substeps, const double *x0, int64_t nsteps, int64_t npaths,
-                               const double *z, double *xc_out, double *xf_out) {
+int FN(multilevel_sample_z)(int id, int scheme, const double *p_in, double t0_in, double dtc_in, double dtf_in,
+                            int64_t substeps, const double *x0_in, int64_t nsteps, int64_t npaths,
+                            const real *z, real *xc_out, real *xf_out) {
   if (id < 0 || id >= M_COUNT) return -1;
   const model_def *m = &MODELS[id];
+  CONV_ARGS(m)
+  const real t0 = (real)t0_in, dt_coarse = (real)dtc_in, dt_fine = (real)dtf_in;
   const int M = m->M > 0 ? m->M : 1, D = m->D;
-  const double s = sqrt(dt_fine);
+  const real s = R_SQRT(dt_fine);
   int rc = 0;
   for (int64_t k = 0; k < npaths; k++) {
-    double xc[MAXD], xf[MAXD], xn[MAXD], DW[MAXM], dw[MAXM];
+    real xc[MAXD], xf[MAXD], xn[MAXD], DW[MAXM], dw[MAXM];
     for (int d = 0; d < D; d++) { xc[d] = x0[d]; xf[d] = x0[d]; }
-    const double *zk = z + k * nsteps * substeps * M;
+    const real *zk = z + k * nsteps * substeps * M;
     for (int64_t n = 1; n <= nsteps; n++) {
-      for (int j = 0; j < M; j++) DW[j] = 0.0;
-      double tc = t0 + (double)(n - 1) * dt_coarse;
+      for (int j = 0; j < M; j++) DW[j] = (real)0.0;
+      real tc = t0 + (real)(n - 1) * dt_coarse;
       for (int64_t i = 1; i <= substeps; i++) {
-        double tf = tc + (double)(i - 1) * dt_fine;
+        real tf = tc + (real)(i - 1) * dt_fine;
         for (int j = 0; j < M; j++) {
-          dw[j] = s * (m->M > 0 ? zk[((n - 1) * substeps + (i - 1)) * M + j] : 0.0);
+          dw[j] = s * (m->M > 0 ? zk[((n - 1) * substeps + (i - 1)) * M + j] : (real)0.0);
           DW[j] = DW[j] + dw[j];
         }
         rc |= step(m, scheme, p, dt_fine, tf, xf, dw, xn);
@@ -505,23 +548,24 @@ int oracle_multilevel_sample_z(int id, int scheme, const double *p, double t0, d
 /* _multilevel_simulate: multilevel.jl:91-100.  wiener!(xf) draws eltype(xf)==D normals per row
  * (simulation.jl:12-18,30), xc = xf[1:substeps:end,:] then both integrated in place.
  * z[npaths][nsteps*substeps][D]; xf[npaths][nsteps*substeps+1][D]; xc[npaths][nsteps+1][D]. */
-int oracle_multilevel_simulate_z(int id, int scheme, const double *p, double t0, double dt_coarse, double dt_fine,
-                                 int64_t substeps, const double *x0, int64_t nsteps, int64_t npaths,
-                                 const double *z, double *xc, double *xf) {
+int FN(multilevel_simulate_z)(int id, int scheme, const double *p, double t0, double dt_coarse, double dt_fine,
+                              int64_t substeps, const double *x0, int64_t nsteps, int64_t npaths,
+                              const real *z, real *xc, real *xf) {
   if (id < 0 || id >= M_COUNT) return -1;
   const model_def *m = &MODELS[id];
   const int D = m->D;
   if (m->M != D) return -4;
   const int64_t nf = nsteps * substeps + 1, nc = nsteps + 1;
-  oracle_wiener_z(dt_fine, nf, npaths, D, z, xf);
+  FN(wiener_z)(dt_fine, nf, npaths, D, z, xf);
   for (int64_t k = 0; k < npaths; k++)
     for (int64_t i = 0; i < nc; i++)
       for (int d = 0; d < D; d++) xc[(k * nc + i) * D + d] = xf[(k * nf + i * substeps) * D + d];
-  int rc = oracle_simulate_wiener(id, scheme, p, t0, dt_fine, x0, nf, npaths, xf, xf);
-  rc |= oracle_simulate_wiener(id, scheme, p, t0, dt_coarse, x0, nc, npaths, xc, xc);
+  int rc = FN(simulate_wiener)(id, scheme, p, t0, dt_fine, x0, nf, npaths, xf, xf);
+  rc |= FN(simulate_wiener)(id, scheme, p, t0, dt_coarse, x0, nc, npaths, xc, xc);
   return rc;
 }
 
+#ifndef ORACLE_REAL_FLOAT
 /* ------------------------------------------------------------------------------------------
  * CPU baseline: the reference's execution model (scalar per path, simulation.jl:59-67 calling
  * :39-48) with a generator in the same cost class as Julia's randn() (ziggurat over a
@@ -710,3 +754,5 @@ int oracle_multilevel_rng(int id, int scheme, const double *p, double t0, double
   }
   return used;
 }
+
+#endif /* !ORACLE_REAL_FLOAT */

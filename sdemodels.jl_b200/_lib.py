@@ -14,6 +14,7 @@ EULER_MARUYAMA, MILSTEIN, RUNGE_KUTTA, EXACT = 0, 1, 2, 3
 F64, F32 = 0, 1
 MATH_FAST, MATH_STRICT = 0, 1
 LAYOUT_REFERENCE, LAYOUT_SOA = 0, 1
+RNG_DEFAULT, RNG_V1, RNG_V2 = 0, 1, 2
 PAYOFF_MOMENTS, PAYOFF_CALL, PAYOFF_PUT, PAYOFF_COMPONENT = 0, 1, 2, 3
 NBINS = 68
 SHARD_ALIGN = 1024
@@ -30,7 +31,7 @@ class DomainError(SDEB200Error, ArithmeticError):
 
 
 class Opts(C.Structure):
-    _fields_ = [("scheme", C.c_int32), ("precision", C.c_int32), ("math", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("scheme", C.c_int32), ("precision", C.c_int32), ("math", C.c_int32), ("rng", C.c_int32),
                 ("t0", C.c_double), ("dt", C.c_double), ("seed", C.c_uint64), ("stream", C.c_uint32),
                 ("reserved2", C.c_uint32), ("path_offset", C.c_int64)]
 

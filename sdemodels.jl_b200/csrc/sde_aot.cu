@@ -53,7 +53,15 @@ template <int DIM> struct WienerN {
   T.simw[s][0] = (const void *)sdek_##TAG##_simw_##SNAME##_f64;                        \
   T.simw[s][1] = (const void *)sdek_##TAG##_simw_##SNAME##_f32;                        \
   T.simwt[s][0] = (const void *)sdek_##TAG##_simwt_##SNAME##_f64;                      \
-  T.simwt[s][1] = (const void *)sdek_##TAG##_simwt_##SNAME##_f32;
+  T.simwt[s][1] = (const void *)sdek_##TAG##_simwt_##SNAME##_f32;                      \
+  T.sample[s][2] = (const void *)sdek_##TAG##_sample_##SNAME##_f64v2;                  \
+  T.sample1[s][2] = (const void *)sdek_##TAG##_sample1_##SNAME##_f64v2;                \
+  T.mlmc[s][2] = (const void *)sdek_##TAG##_mlmc_##SNAME##_f64v2;                      \
+  T.simsoa[s][2] = (const void *)sdek_##TAG##_simsoa_##SNAME##_f64v2;                  \
+  T.simref[s][2] = (const void *)sdek_##TAG##_simref_##SNAME##_f64v2;                  \
+  T.simrt[s][2] = (const void *)sdek_##TAG##_simrt_##SNAME##_f64v2;                    \
+  T.simw[s][2] = T.simw[s][0];                                                         \
+  T.simwt[s][2] = T.simwt[s][0];
 #define XCOEFFILL(T, TAG) XCOEFFILL2(T, TAG)
 #define XCOEFFILL2(T, TAG)                              \
   T.coef = (const void *)sdek_##TAG##_coef;             \
@@ -65,7 +73,7 @@ XSCHEME(BlackScholes, TAGGED(bs), 1, mil)
 XSCHEME(BlackScholes, TAGGED(bs), 2, rk)
 XCOEF(BlackScholes, TAGGED(bs))
 #define XEXACT(MODEL, TAG) XEXACT2(MODEL, TAG)
-#define XEXACT2(MODEL, TAG) SDE_KERNELS_EXACT(MODEL, TAG, double, f64) SDE_KERNELS_EXACT(MODEL, TAG, float, f32)
+#define XEXACT2(MODEL, TAG) SDE_KERNELS_EXACT(MODEL, TAG, double, f64) SDE_KERNELS_EXACT(MODEL, TAG, float, f32) SDE_KERNELS_EXACT_V2(MODEL, TAG)
 #define XEXACTFILL(T, TAG) XEXACTFILL2(T, TAG)
 #define XEXACTFILL2(T, TAG)                                              \
   T.sample[3][0] = (const void *)sdek_##TAG##_sample_exact_f64;          \
@@ -77,7 +85,12 @@ XCOEF(BlackScholes, TAGGED(bs))
   T.simref[3][0] = (const void *)sdek_##TAG##_simref_exact_f64;          \
   T.simref[3][1] = (const void *)sdek_##TAG##_simref_exact_f32;          \
   T.simrt[3][0] = (const void *)sdek_##TAG##_simrt_exact_f64;            \
-  T.simrt[3][1] = (const void *)sdek_##TAG##_simrt_exact_f32;
+  T.simrt[3][1] = (const void *)sdek_##TAG##_simrt_exact_f32;            \
+  T.sample[3][2] = (const void *)sdek_##TAG##_sample_exact_f64v2;        \
+  T.sample1[3][2] = (const void *)sdek_##TAG##_sample1_exact_f64v2;      \
+  T.simsoa[3][2] = (const void *)sdek_##TAG##_simsoa_exact_f64v2;        \
+  T.simref[3][2] = (const void *)sdek_##TAG##_simref_exact_f64v2;        \
+  T.simrt[3][2] = (const void *)sdek_##TAG##_simrt_exact_f64v2;
 XEXACT(BlackScholes, TAGGED(bs))
 XSCHEME(OrnsteinUhlenbeck, TAGGED(ou), 0, em)
 XSCHEME(OrnsteinUhlenbeck, TAGGED(ou), 1, mil)
@@ -100,6 +113,12 @@ XCOEF(Heston, TAGGED(heston))
   }                                                                                                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##t_f32(const __grid_constant__ sde_args a) { \
     sdeb200::simulate_ref_tma_body<sdeb200::WienerN<DIM>, float, 0>(a);                                      \
+  }                                                                                                          \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_f64v2(const __grid_constant__ sde_args a) { \
+    sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, double, 0, 2>(a);                                      \
+  }                                                                                                          \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##t_f64v2(const __grid_constant__ sde_args a) { \
+    sdeb200::simulate_ref_tma_body<sdeb200::WienerN<DIM>, double, 0, 2>(a);                                  \
   }
 XWIENER(1, TAGGED(wiener1))
 XWIENER(2, TAGGED(wiener2))
@@ -134,32 +153,41 @@ extern "C" int SDE_AOT_TABLE(int model, sde_ktable *t) {
   return -1;
 }
 
-// wiener kernels [dim-1][precision]
+// wiener kernels: dim 1..4 (+16: the TMA tensor-store form; dim 3 has none: 3*sizeof(T) does not divide 128),
+// slot 0 = f64 stream v1, 1 = f32, 2 = f64 stream v2
 #define XW(TAG, P) XW2(TAG, P)
 #define XW2(TAG, P) (const void *)sdek_##TAG##_##P
 #define XWT(TAG, P) XWT2(TAG, P)
 #define XWT2(TAG, P) (const void *)sdek_##TAG##t_##P
-extern "C" const void *SDE_AOT_WIENER(int dim, int precision) {
-  if (dim >= 16) {  // + 16: the TMA tensor-store form (dim 3 has none: 3*sizeof(T) does not divide 128)
-    switch ((dim - 16) * 2 + precision) {
-      case 2: return XWT(TAGGED(wiener1), f64);
-      case 3: return XWT(TAGGED(wiener1), f32);
-      case 4: return XWT(TAGGED(wiener2), f64);
-      case 5: return XWT(TAGGED(wiener2), f32);
-      case 8: return XWT(TAGGED(wiener4), f64);
-      case 9: return XWT(TAGGED(wiener4), f32);
+extern "C" const void *SDE_AOT_WIENER(int dim, int slot) {
+  if (slot < 0 || slot > 2) return 0;
+  if (dim >= 16) {
+    switch ((dim - 16) * 3 + slot) {
+      case 3: return XWT(TAGGED(wiener1), f64);
+      case 4: return XWT(TAGGED(wiener1), f32);
+      case 5: return XWT(TAGGED(wiener1), f64v2);
+      case 6: return XWT(TAGGED(wiener2), f64);
+      case 7: return XWT(TAGGED(wiener2), f32);
+      case 8: return XWT(TAGGED(wiener2), f64v2);
+      case 12: return XWT(TAGGED(wiener4), f64);
+      case 13: return XWT(TAGGED(wiener4), f32);
+      case 14: return XWT(TAGGED(wiener4), f64v2);
     }
     return 0;
   }
-  switch (dim * 2 + precision) {
-    case 2: return XW(TAGGED(wiener1), f64);
-    case 3: return XW(TAGGED(wiener1), f32);
-    case 4: return XW(TAGGED(wiener2), f64);
-    case 5: return XW(TAGGED(wiener2), f32);
-    case 6: return XW(TAGGED(wiener3), f64);
-    case 7: return XW(TAGGED(wiener3), f32);
-    case 8: return XW(TAGGED(wiener4), f64);
-    case 9: return XW(TAGGED(wiener4), f32);
+  switch (dim * 3 + slot) {
+    case 3: return XW(TAGGED(wiener1), f64);
+    case 4: return XW(TAGGED(wiener1), f32);
+    case 5: return XW(TAGGED(wiener1), f64v2);
+    case 6: return XW(TAGGED(wiener2), f64);
+    case 7: return XW(TAGGED(wiener2), f32);
+    case 8: return XW(TAGGED(wiener2), f64v2);
+    case 9: return XW(TAGGED(wiener3), f64);
+    case 10: return XW(TAGGED(wiener3), f32);
+    case 11: return XW(TAGGED(wiener3), f64v2);
+    case 12: return XW(TAGGED(wiener4), f64);
+    case 13: return XW(TAGGED(wiener4), f32);
+    case 14: return XW(TAGGED(wiener4), f64v2);
   }
   return 0;
 }

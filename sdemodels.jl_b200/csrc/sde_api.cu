@@ -24,8 +24,8 @@
 
 extern "C" int sde_aot_table_fast(int model, sde_ktable *t);
 extern "C" int sde_aot_table_strict(int model, sde_ktable *t);
-extern "C" const void *sde_aot_wiener_fast(int dim, int precision);
-extern "C" const void *sde_aot_wiener_strict(int dim, int precision);
+extern "C" const void *sde_aot_wiener_fast(int dim, int slot);
+extern "C" const void *sde_aot_wiener_strict(int dim, int slot);
 extern "C" void sde_launch_accumulate(const double *partials, int64_t nchunks, int stride, int nq,
                                       unsigned long long *bins, unsigned long long *overflow, cudaStream_t st);
 extern "C" void sde_launch_subsample(int precision, const void *src, void *dst, int64_t npaths, int64_t nrows_dst,
@@ -373,6 +373,9 @@ extern "C" int sdeb200_model_compile(sdeb200_model *m, int precision, int math) 
 // ---------------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------------
+// kernel-table slot of a run: 0 = f64 on normal stream v1, 1 = f32 (one stream definition), 2 = f64 on normal stream v2
+static inline int kslot(const sdeb200_opts *o) { return o->precision == SDEB200_F32 ? 1 : (o->rng == SDEB200_RNG_V2 ? 2 : 0); }
+
 static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0) {
   if (!m || !o || !x0) return fail(SDEB200_E_ARG, "null argument");
   if (!params && !m->params.empty()) return fail(SDEB200_E_ARG, "params is NULL but the model has %zu", m->params.size());
@@ -388,20 +391,29 @@ static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const dou
                 "(src/schemes/milstein.jl:4, runge_kutta.jl:4); '%s' has M == %d",
                 o->scheme == SDEB200_MILSTEIN ? "Milstein" : "RungeKutta", m->name.c_str(), m->M);
   if (o->precision < 0 || o->precision > 1 || o->math < 0 || o->math > 1) return fail(SDEB200_E_ARG, "bad precision/math");
+  if (o->rng < 0 || o->rng > SDEB200_RNG_V2) return fail(SDEB200_E_ARG, "unknown normal stream version %d", o->rng);
   if (!(o->dt > 0.0) || !isfinite(o->dt)) return fail(SDEB200_E_ARG, "scheme Δt must be positive and finite");
   return 0;
 }
 
-// a->dt and the dt-scaled constants of the FP64 normal transform (sde_device.cuh: make_log_consts)
-static void set_dt(sde_args *a, double dt, int scheme = SDEB200_EULER_MARUYAMA) {
+// a->dt and the dt-scaled constants of the FP64 normal transform (sde_device.cuh: make_log_consts / make_log_consts_v2)
+static void set_dt(sde_args *a, double dt, int scheme = SDEB200_EULER_MARUYAMA, int rng = SDEB200_RNG_V1) {
   a->dt = dt;
   const double v = scheme == SDEB200_EXACT ? 1.0 : dt;  // Exact samplers draw plain N(0,1) (rand(LogNormal / Normal))
   a->noise_var = v;
-  a->lk[0] = SDE_LOG_C1_V * v;
-  a->lk[1] = SDE_LOG_C2_V * v;
-  a->lk[2] = SDE_LOG_C3_V * v;
-  a->lk[3] = SDE_LOG_C4_V * v;
-  a->lk[4] = -2.0 * v;
+  if (rng == SDEB200_RNG_V2 && SDE_V2_FINE) {
+    a->lk[0] = SDE_LOG2_C0_V * v;
+    a->lk[1] = SDE_LOG2_C1_V * v;
+    a->lk[2] = SDE_LOG2_C2_V * v;
+    a->lk[3] = SDE_LOG2_C3_V * v;
+    a->lk[4] = 0.0;
+  } else {
+    a->lk[0] = SDE_LOG_C1_V * v;
+    a->lk[1] = SDE_LOG_C2_V * v;
+    a->lk[2] = SDE_LOG_C3_V * v;
+    a->lk[3] = SDE_LOG_C4_V * v;
+    a->lk[4] = -2.0 * v;
+  }
   a->lk[5] = SDE_TWO_LN2_V * v;
 }
 
@@ -416,7 +428,7 @@ static void fill_args(sde_args *a, const sdeb200_model *m, const sdeb200_opts *o
   a->seed_hi = (uint32_t)(o->seed >> 32);
   a->stream = o->stream;
   a->path0 = o->path_offset;
-  set_dt(a, o->dt, o->scheme);
+  set_dt(a, o->dt, o->scheme, o->rng);
 }
 
 // sample / mlmc kernels walk over chunks grid-stride: cap the grid so each CTA stages its tables once for many chunks
@@ -668,11 +680,13 @@ static int64_t sample_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BL
 // explicit FMAs only); generated functors in FAST math leave contraction to the compiler, which may choose
 // differently in the two instantiations, so they always take the SDE_PPT form and stay shard-invariant.
 static int launch_sample(const sdeb200_model *m, const sde_ktable *kt, const sdeb200_opts *o, const sde_args *a, cudaStream_t st) {
-  const void *k1 = kt->sample1[o->scheme][o->precision];
+  const void *k1 = kt->sample1[o->scheme][kslot(o)];
   const int64_t grid = capped(sample_grid(a->npaths));
   const bool invariant = o->math == SDEB200_MATH_STRICT || m->builtin >= 0;
-  if (k1 && invariant && a->npaths <= g_sample1_max) return launch(k1, grid, a, st, 0, SDE_BLOCK * SDE_PPT);
-  return launch(kt->sample[o->scheme][o->precision], grid, a, st);
+  // stream v2's fine transform tables live in dynamic shared memory (sample_body)
+  const size_t smem = (kslot(o) == 2 && SDE_V2_FINE) ? (size_t)SDE_TAB2_DOUBLES * 8 : 0;
+  if (k1 && invariant && a->npaths <= g_sample1_max) return launch(k1, grid, a, st, smem, SDE_BLOCK * SDE_PPT);
+  return launch(kt->sample[o->scheme][kslot(o)], grid, a, st, smem);
 }
 
 extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
@@ -739,7 +753,7 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
   const bool dev = is_device_ptr(out);
   if ((rc = timed_begin())) return rc;
   if (layout == SDEB200_LAYOUT_REFERENCE) {
-    const void *k = kt->simref[o->scheme][o->precision], *k_tma = kt->simrt[o->scheme][o->precision];
+    const void *k = kt->simref[o->scheme][kslot(o)], *k_tma = kt->simrt[o->scheme][kslot(o)];
     const size_t bpp = (size_t)nrows * m->D * es;
     if (dev) {
       if ((rc = launch_simref(k, k_tma, m->D, o->precision, a, npaths, out, st))) return rc;
@@ -752,7 +766,7 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
       if (rc) return rc;
     }
   } else {
-    const void *k = kt->simsoa[o->scheme][o->precision];
+    const void *k = kt->simsoa[o->scheme][kslot(o)];
     const int vec = SDE_SOA_VEC;
     if (dev) {
       a.npaths = npaths;
@@ -797,7 +811,7 @@ static int launch_simw(const sde_ktable *kt, const sdeb200_model *m, const sdeb2
   const int MW = m->M > 0 ? m->M : 1, D = m->D;
   const size_t es = esize(o->precision);
   const int rowb = (int)(D * es);
-  const void *kt_tma = kt->simwt[o->scheme][o->precision], *k = kt->simw[o->scheme][o->precision];
+  const void *kt_tma = kt->simwt[o->scheme][kslot(o)], *k = kt->simw[o->scheme][kslot(o)];
   int rc;
   int64_t done = 0;
   if (kt_tma && g_tma_enabled && D == MW && 128 % rowb == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)x % 16) == 0 &&
@@ -957,20 +971,19 @@ extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, co
 // ---------------------------------------------------------------------------------------------------
 static int wiener_device(const sdeb200_opts *o, int dim, int64_t nrows, int64_t npaths, int64_t path0, void *dev,
                          cudaStream_t st) {
-  const void *k = o->math == SDEB200_MATH_STRICT ? sde_aot_wiener_strict(dim, o->precision)
-                                                 : sde_aot_wiener_fast(dim, o->precision);
+  const int slot = kslot(o);
+  const void *k = o->math == SDEB200_MATH_STRICT ? sde_aot_wiener_strict(dim, slot) : sde_aot_wiener_fast(dim, slot);
   if (!k) return fail(SDEB200_E_ARG, "wiener!: dim must be 1..4");
   sde_args a;
   memset(&a, 0, sizeof a);
   a.t0 = o->t0;
-  set_dt(&a, o->dt);
+  set_dt(&a, o->dt, SDEB200_EULER_MARUYAMA, o->rng);
   a.seed_lo = (uint32_t)o->seed;
   a.seed_hi = (uint32_t)(o->seed >> 32);
   a.stream = o->stream;
   a.path0 = path0;
   a.nsteps = nrows - 1;
-  const void *k_tma = o->math == SDEB200_MATH_STRICT ? sde_aot_wiener_strict(16 + dim, o->precision)
-                                                     : sde_aot_wiener_fast(16 + dim, o->precision);
+  const void *k_tma = o->math == SDEB200_MATH_STRICT ? sde_aot_wiener_strict(16 + dim, slot) : sde_aot_wiener_fast(16 + dim, slot);
   return launch_simref(k, k_tma, dim, o->precision, a, npaths, dev, st);
 }
 
@@ -1182,7 +1195,7 @@ static int mlmc_args(sde_args *a, sdeb200_model *m, const sdeb200_opts *o, const
                 "the coupled level sampler needs D == M (Δw = zero(typeof(x0)) in src/multilevel.jl:79); "
                 "'%s' has D=%d, M=%d", m->name.c_str(), m->D, m->M);
   fill_args(a, m, o, params, x0);
-  set_dt(a, dt_fine);
+  set_dt(a, dt_fine, o->scheme, o->rng);
   a->dt_coarse = o->dt;
   a->substeps = substeps;
   a->nsteps = ncoarse * substeps;
@@ -1217,7 +1230,7 @@ extern "C" int sdeb200_mlmc_sample_level(sdeb200_model *m, const sdeb200_opts *o
     else { if ((rc = g.slab[1].ensure(bytes))) return rc; a.out2 = g.slab[1].p; }
   }
   if ((rc = timed_begin())) return rc;
-  if ((rc = launch(kt->mlmc[o->scheme][o->precision], capped(cdiv(npaths, SDE_BLOCK)), &a, st))) return rc;
+  if ((rc = launch(kt->mlmc[o->scheme][kslot(o)], capped(cdiv(npaths, SDE_BLOCK)), &a, st))) return rc;
   if (xf && !fdev) CU(cudaMemcpyAsync(xf, a.out, bytes, cudaMemcpyDeviceToHost, st));
   if (xc && !cdev) CU(cudaMemcpyAsync(xc, a.out2, bytes, cudaMemcpyDeviceToHost, st));
   if ((rc = timed_end())) return rc;
@@ -1292,7 +1305,7 @@ static int queue_level(sdeb200_model *m, const sde_ktable *kt, const sdeb200_opt
   if (coupled) {
     if ((rc = mlmc_args(&a, m, o, params, x0, dt_fine, substeps, ncoarse, npaths))) return rc;
     grid = cdiv(npaths, SDE_BLOCK);
-    k = kt->mlmc[o->scheme][o->precision];
+    k = kt->mlmc[o->scheme][kslot(o)];
   } else {
     fill_args(&a, m, o, params, x0);
     a.nsteps = ncoarse;

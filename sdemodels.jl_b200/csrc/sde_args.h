@@ -21,6 +21,20 @@ typedef long long int64_t;
 #define SDE_BLOCK 128     /* threads per CTA for every path kernel */
 #endif
 #define SDE_TAB_DOUBLES 2304 /* FP64 transform tables in shared memory: 256 (log) + 2048 (rotation) */
+/* SDE_V2_FINE = 1 (default): normal stream v2 evaluates its transform on finer tables — 512 log cells (|r| <= 2^-10: three
+ * FMAs instead of four) and 2048 rotation cells (|phi| <= pi/2048: one-term sine residual) — 40 KB of shared memory per
+ * CTA for 2 FP64 instructions less per pair.  The SPECIFICATION (u1, angle -> normals) does not depend on it. */
+#ifndef SDE_V2_FINE
+#define SDE_V2_FINE 1
+#endif
+#if SDE_V2_FINE
+#define SDE_V2_LOGN 512
+#define SDE_V2_ROTN 2048
+#else
+#define SDE_V2_LOGN 128
+#define SDE_V2_ROTN 1024
+#endif
+#define SDE_TAB2_DOUBLES (2 * SDE_V2_LOGN + 2 * SDE_V2_ROTN)
 #define SDE_SIMREF_PW 1   /* paths per lane in the reference-layout trajectory kernels (2 measured slower: 128 registers) */
 #define SDE_SOA_VEC 4  /* consecutive paths per thread in the [time][D][path] trajectory kernel (8 measured no better in FP32) */
 #ifndef SDE_SIMW_ROWBYTES

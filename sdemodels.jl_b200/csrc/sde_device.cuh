@@ -125,10 +125,25 @@ SDE_HD double sqrt_core(double v) { return sqrt_from_seed(v, rsqrt_seed(v)); }  
 // Model-side sqrt of the FAST math mode: sqrt(0) = 0 (the +inf seed is clamped to 2^1023 with one integer min, so
 // g = 0 * 2^1023 = 0 exactly); v < 0 gives a non-finite result (NaN or -inf) that propagates to the state and is
 // counted as a non-finite path — the reference throws DomainError there.  Subnormal v is flushed.
+#ifndef SDE_V2_IMAD
+#define SDE_V2_IMAD 0
+#endif
+#ifndef SDE_V2_ROT1
+#define SDE_V2_ROT1 0
+#endif
+#ifndef SDE_SQRT_FAST6
+#define SDE_SQRT_FAST6 1 /* six-operation form (sqrt_from_seed6, <= 1 ulp) instead of the seven-operation one */
+#endif
+SDE_HD double sqrt_from_seed6(double v, double y);
 SDE_HD double sqrt_fast(double v) {
   const double y = rsqrt_seed(v);
   const int32_t hy = (int32_t)double2hi(y);
-  return sqrt_from_seed(v, hilo2double((uint32_t)(hy < 0x7FE00000 ? hy : 0x7FE00000), 0));
+  const double yc = hilo2double((uint32_t)(hy < 0x7FE00000 ? hy : 0x7FE00000), 0);
+#if SDE_SQRT_FAST6
+  return sqrt_from_seed6(v, yc);
+#else
+  return sqrt_from_seed(v, yc);
+#endif
 }
 SDE_HD float sqrt_fast(float v) {  // FAST math, FP32: one MUFU.SQRT (max relative error 2^-23) instead of the IEEE sequence
 #if defined(__CUDA_ARCH__)
@@ -314,6 +329,120 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const dou
   z1 = g * sb;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// "sdeb200 normal stream v2", FP64 (opt-in: sdeb200_opts.rng = 2): 96 Philox bits per pair instead of 128, i.e. three
+// Philox4x32-10 blocks per four pairs (-25 % of the generator's integer work, which is what bounds the FP64 kernels:
+// an IMAD.WIDE costs 5.5 issue cycles on sm_100a, profiles/r01_mb_cost.txt).  The path's Philox output is read as a
+// stream of 32-bit words W = 0, 1, 2, ... (word W = lane W % 4 of block W / 4); pair P takes words (3P, 3P+1, 3P+2):
+//   X1 = w[3P+1]:w[3P]  -> u1 exactly as in v1 (64-bit uniform, full relative precision near 0, tail to 9.4 sigma)
+//   c  = w[3P+2]        -> angle = c / 2^32 turns = (i + 1/2 + d) / 1024: the top 10 bits pick the cell of the same
+//                          1024-entry table, the low 22 bits (re-centred) are the offset; t = 2^32 d is produced by ONE
+//                          integer multiply-add, c * 2^10 + 2^31 (mod 2^32), and one 32-bit I2F.
+// The radius uses the 6-operation Goldschmidt form (sqrt_from_seed6).  FP32 kernels: v2 == v1 (32 bits per variate already).
+// ---------------------------------------------------------------------------------------------------
+// sqrt_from_seed without the refinement of h: the last correction d*h only needs h to 2^-22 (d is already 2^-45 g).
+SDE_HD double sqrt_from_seed6(double v, double y) {
+  double g = v * y;
+  const double h = y * 0.5;
+  const double e = fma(-g, h, 0.5);
+  g = fma(g, e, g);
+  const double d = fma(-g, g, v);
+  return fma(d, h, g);
+}
+//   lk (v2, fine) = noise_var * {Q2_0, Q2_1, Q2_2, Q2_3, -, 2 ln 2};  tab = [0, 2 LOGN): log pairs, then the rotation pairs
+SDE_HD void make_log_consts_v2(double dt, double *lk) {
+#if SDE_V2_FINE
+  lk[0] = SDE_LOG2_C0_V * dt;
+  lk[1] = SDE_LOG2_C1_V * dt;
+  lk[2] = SDE_LOG2_C2_V * dt;
+  lk[3] = SDE_LOG2_C3_V * dt;
+  lk[4] = 0.0;
+  lk[5] = SDE_TWO_LN2_V * dt;
+#else
+  lk[0] = SDE_LOG_C1_V * dt;
+  lk[1] = SDE_LOG_C2_V * dt;
+  lk[2] = SDE_LOG_C3_V * dt;
+  lk[3] = SDE_LOG_C4_V * dt;
+  lk[4] = -2.0 * dt;
+  lk[5] = SDE_TWO_LN2_V * dt;
+#endif
+}
+SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double *tab, const double *lk, double &z0, double &z1,
+                               const double *kr = nullptr) {
+  const uint64_t X1 = ((uint64_t)b << 32) | a;
+  const double d1 = (double)X1;
+  const uint32_t h1 = double2hi(d1);
+#if defined(__CUDA_ARCH__)
+  uint32_t one_hi, mh;
+  asm("mov.u32 %0, 0x3FF00000;" : "=r"(one_hi));
+  asm("lop3.b32 %0, %1, 0x000FFFFF, %2, 0xEA;" : "=r"(mh) : "r"(h1), "r"(one_hi));
+  const double m = hilo2double(mh, double2lo(d1));
+#else
+  const double m = hilo2double((h1 & 0x000FFFFFu) | 0x3FF00000u, double2lo(d1));
+#endif
+  const double kd = (double)(int)(1087u - (h1 >> 20));
+#if SDE_V2_FINE
+  const int j = (int)((h1 >> 11) & 0x1FFu);
+  const double inv_c = tab[2 * j], tl = tab[2 * j + 1];
+  const double rr = fma(m, inv_c, -1.0);
+  double q = kr ? kr[0] : lk[3];
+  q = fma(q, rr, lk[2]);
+  q = fma(q, rr, lk[1]);
+  q = fma(q, rr, lk[0]);
+#else
+  const int j = (int)((h1 >> 13) & 0x7Fu);
+  const double inv_c = tab[2 * j], tl = tab[2 * j + 1];
+  const double rr = fma(m, inv_c, -1.0);
+  double q = kr ? kr[0] : lk[3];
+  q = fma(q, rr, lk[2]);
+  q = fma(q, rr, lk[1]);
+  q = fma(q, rr, lk[0]);
+  q = fma(q, rr, lk[4]);
+#endif
+  double w = fma(rr, q, tl);
+  w = fma(kd, lk[5], w);
+  const double g = sqrt_from_seed6(w, rsqrt_seed(w));
+#if SDE_V2_FINE
+  const double *rot = tab + 2 * SDE_V2_LOGN + 2 * (c >> 21);
+  const double C = rot[0], S = rot[1];
+#if defined(__CUDA_ARCH__) && SDE_V2_IMAD
+  int32_t ti;   // ((c & 0x1FFFFF) - 2^20) * 2^11 as ONE integer multiply-add (the compiler splits c * 2048u + 0x80000000u into shift + xor)
+  asm("mad.lo.s32 %0, %1, 2048, 0x80000000;" : "=r"(ti) : "r"(c));
+  const double t = (double)ti;
+#else
+  const double t = (double)(int32_t)(c * 2048u + 0x80000000u);   // ((c & 0x1FFFFF) - 2^20) * 2^11, exact
+#endif
+  const double u = t * t;
+  const double sp = fma(kr ? kr[1] : SDE_K(SDE_ROT3_S1), u, SDE_K(SDE_ROT3_S0));
+  const double sn = t * sp;
+  double cm = fma(kr ? kr[2] : SDE_K(SDE_ROT3_C2), u, SDE_K(SDE_ROT3_C1));
+#if SDE_V2_ROT1
+  // rotation with the cosine of the residual formed explicitly (1 + cm: one rounding at 2^-53 absolute): two of the
+  // three-register FMAs become two-register multiplies, which dispatch faster (profiles/r01_mb_cost.txt)
+  const double c1 = fma(cm, u, 1.0);
+  const double ca1 = fma(C, c1, -(S * sn));
+  const double sb1 = fma(S, c1, C * sn);
+  z0 = g * ca1;
+  z1 = g * sb1;
+  return;
+#endif
+#else
+  const double *rot = tab + 2 * SDE_V2_LOGN + 2 * (c >> 22);
+  const double C = rot[0], S = rot[1];
+  const double t = (double)(int32_t)(c * 1024u + 0x80000000u);   // ((c & 0x3FFFFF) - 2^21) * 2^10, exact
+  const double u = t * t;
+  double sp = fma(kr ? kr[1] : SDE_K(SDE_ROT2_S2), u, SDE_K(SDE_ROT2_S1));
+  sp = fma(sp, u, SDE_K(SDE_ROT2_S0));
+  const double sn = t * sp;
+  double cm = fma(kr ? kr[2] : SDE_K(SDE_ROT2_C2), u, SDE_K(SDE_ROT2_C1));
+#endif
+  cm = cm * u;
+  const double ca = fma(C, cm, fma(-S, sn, C));
+  const double sb = fma(S, cm, fma(C, sn, S));
+  z0 = g * ca;
+  z1 = g * sb;
+}
+
 // FP32 stream: 128 Philox bits -> four N(0, scale2) variates.  u1 = (r + 1/2) 2^-32, angle = r' / 2^32 turns.
 // log2 and sqrt on the MUFU unit; (cos, sin) from a 256-entry table of cell centres (top 8 bits of r') plus a
 // one-term residual rotation in the 24-bit offset — no quadrant logic.  rotf: {cos, sin} float pairs.
@@ -371,6 +500,19 @@ constexpr int sde_gcd(int a, int b) { return b == 0 ? a : sde_gcd(b, a % b); }
 static const double h_log_tab[256] = SDE_LOG_TAB_INIT;
 static const double h_rot_tab[2048] = SDE_ROT_TAB_INIT;
 static const float h_rotf_tab[512] = SDE_ROTF_TAB_INIT;
+#if SDE_V2_FINE
+static const double h_log2_tab[2 * SDE_V2_LOGN] = SDE_LOG2_TAB_INIT;
+static const double h_rot3_tab[2 * SDE_V2_ROTN] = SDE_ROT3_TAB_INIT;
+#endif
+static inline void h_scaled_tables_v2(double dt, double *tab) {  // tab[SDE_TAB2_DOUBLES]
+#if SDE_V2_FINE
+  for (int i = 0; i < SDE_V2_LOGN; i++) { tab[2 * i] = h_log2_tab[2 * i]; tab[2 * i + 1] = h_log2_tab[2 * i + 1] * dt; }
+  for (int i = 0; i < 2 * SDE_V2_ROTN; i++) tab[2 * SDE_V2_LOGN + i] = h_rot3_tab[i];
+#else
+  for (int i = 0; i < 128; i++) { tab[2 * i] = h_log_tab[2 * i]; tab[2 * i + 1] = h_log_tab[2 * i + 1] * dt; }
+  for (int i = 0; i < 2048; i++) tab[256 + i] = h_rot_tab[i];
+#endif
+}
 static inline void h_scaled_tables(double dt, double *tab) {  // tab[SDE_TAB_DOUBLES]
   for (int i = 0; i < 128; i++) { tab[2 * i] = h_log_tab[2 * i]; tab[2 * i + 1] = h_log_tab[2 * i + 1] * dt; }
   for (int i = 0; i < 2048; i++) tab[256 + i] = h_rot_tab[i];
@@ -385,9 +527,18 @@ static __device__ const double g_log_tab[256] = SDE_LOG_TAB_INIT;
 static __device__ const double g_rot_tab[2048] = SDE_ROT_TAB_INIT;
 static __device__ const float g_rotf_tab[512] = SDE_ROTF_TAB_INIT;
 
-// tables of the transforms -> shared memory: FP64 18 KB (log + rotation), FP32 2 KB (rotation, float pairs)
-template <typename T> SDE_D void load_tables(double *s_tab, double dt) {
-  if (sizeof(T) == 8) {
+#if SDE_V2_FINE
+static __device__ const double g_log2_tab[2 * SDE_V2_LOGN] = SDE_LOG2_TAB_INIT;
+static __device__ const double g_rot3_tab[2 * SDE_V2_ROTN] = SDE_ROT3_TAB_INIT;
+#endif
+// tables of the transforms -> shared memory: FP64 18 KB (log + rotation; stream v2: 40 KB), FP32 2 KB (rotation, float pairs)
+template <typename T, int V = 1> SDE_D void load_tables(double *s_tab, double dt) {
+  if (sizeof(T) == 8 && V == 2 && SDE_V2_FINE) {
+#if SDE_V2_FINE
+    for (int i = threadIdx.x; i < 2 * SDE_V2_LOGN; i += blockDim.x) s_tab[i] = (i & 1) ? g_log2_tab[i] * dt : g_log2_tab[i];
+    for (int i = threadIdx.x; i < 2 * SDE_V2_ROTN; i += blockDim.x) s_tab[2 * SDE_V2_LOGN + i] = g_rot3_tab[i];
+#endif
+  } else if (sizeof(T) == 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = (i & 1) ? g_log_tab[i] * dt : g_log_tab[i];
     for (int i = threadIdx.x; i < 2048; i += blockDim.x) s_tab[256 + i] = g_rot_tab[i];
   } else {
@@ -396,7 +547,9 @@ template <typename T> SDE_D void load_tables(double *s_tab, double dt) {
   }
   __syncthreads();
 }
-template <typename T> struct TabSize { static constexpr int value = sizeof(T) == 8 ? SDE_TAB_DOUBLES : 256; };
+template <typename T, int V = 1> struct TabSize {
+  static constexpr int value = sizeof(T) == 8 ? (V == 2 ? SDE_TAB2_DOUBLES : SDE_TAB_DOUBLES) : 256;
+};
 
 template <typename T> struct Consts {
   T c[SDE_MAXC];
@@ -405,26 +558,56 @@ template <typename T> struct Consts {
 // A batch of U steps' worth of increments for one path: dW[u*M + j] ~ N(0, dt), generated from the path's
 // sub-stream blocks [blk0, blk0 + NB).  Flat normal index q = step*M + j follows the reference's draw order
 // (path outer, step inner, M draws left to right: src/simulation.jl:4-11,42-46).
-template <typename T, int M> struct Batch {
-  static constexpr int NPB = NPC<T>::value;                              // normals per Philox block
-  static constexpr int U = (M == 0) ? 1 : NPB / sde_gcd(M, NPB);         // steps per batch
-  static constexpr int NB = (M == 0) ? 0 : (U * M) / NPB;                // Philox blocks per batch
+// V = normal-stream version (sdeb200_opts.rng): 1 = two FP64 normals per Philox block; 2 = eight per three blocks
+// (FP64 only; the FP32 stream is the same in both versions).
+template <typename T, int M, int V = 1> struct Batch {
+  static constexpr bool V2 = (V == 2) && sizeof(T) == 8;
+  static constexpr int NPB = NPC<T>::value;                              // normals per Philox block (v1)
+  static constexpr int U = (M == 0) ? 1 : (V2 ? 8 / sde_gcd(M, 8) : NPB / sde_gcd(M, NPB));   // steps per batch
+  static constexpr int NB = (M == 0) ? 0 : (V2 ? (U * M * 3) / 8 : (U * M) / NPB);             // Philox blocks per batch
   static constexpr int NZ = (M == 0) ? 1 : U * M;
 };
 
-template <typename T, int M>
+// normals of one batch from its Philox words (V2: w[4*NB] holds the NB blocks back to back)
+template <typename T, int M, int V>
+SDE_HD void normals_from_words_v2(const uint32_t *w, const double *s_tab, const double *lk, T *dw, const double *kr) {
+  typedef Batch<T, M, V> B;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int P = 0; P < B::NZ / 2; P++) {
+    double z0, z1;
+    normal_pair_f64_v2(w[3 * P], w[3 * P + 1], w[3 * P + 2], s_tab, lk, z0, z1, kr);
+    dw[2 * P] = (T)z0;
+    dw[2 * P + 1] = (T)z1;
+  }
+}
+
+template <typename T, int M, int V = 1>
 SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const PhiloxKeys &ks, const double *s_tab,
                      const double *lk, T scale2, T *dw, const double *kr = nullptr) {
-  typedef Batch<T, M> B;
+  typedef Batch<T, M, V> B;
   if (M == 0) {
     dw[0] = (T)0;
     return;
   }
+  if (B::V2) {
+    uint32_t w[4 * (B::NB > 0 ? B::NB : 1)];
 #pragma unroll
-  for (int b = 0; b < B::NB; b++) {
-    uint32_t r[4];
-    philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, ks, r);
-    normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
+    for (int b = 0; b < B::NB; b++) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, ks, r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) w[4 * b + i] = r[i];
+    }
+    normals_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
+  } else {
+#pragma unroll
+    for (int b = 0; b < B::NB; b++) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, ks, r);
+      normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
+    }
   }
 }
 
@@ -433,39 +616,90 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const Philox
 // from where every use as a DFMA multiplicand costs two moves (measured: +1.3 % on the headline kernel).
 struct PinnedCoef {
   double v[3];
-  SDE_D PinnedCoef(const double *lk, bool fp64) {
+  SDE_D PinnedCoef(const double *lk, bool fp64, int ver = 1) {
     v[0] = lk[3];
-    v[1] = SDE_K(SDE_ROT_S2);
-    v[2] = SDE_K(SDE_ROT_C2);
+#if SDE_V2_FINE
+    v[1] = ver == 2 ? SDE_K(SDE_ROT3_S1) : SDE_K(SDE_ROT_S2);
+    v[2] = ver == 2 ? SDE_K(SDE_ROT3_C2) : SDE_K(SDE_ROT_C2);
+#else
+    v[1] = ver == 2 ? SDE_K(SDE_ROT2_S2) : SDE_K(SDE_ROT_S2);
+    v[2] = ver == 2 ? SDE_K(SDE_ROT2_C2) : SDE_K(SDE_ROT_C2);
+#endif
     if (fp64) asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]) : "r"(threadIdx.x));   // FP32 kernels: dead code
   }
 };
 
 // gen_batch for a path whose round-0/1 invariants are precomputed (philox_path_init)
-template <typename T, int M>
+template <typename T, int M, int V = 1>
 SDE_D void gen_batch(const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, const double *s_tab, const double *lk, T scale2,
                      T *dw, const double *kr = nullptr) {
-  typedef Batch<T, M> B;
+  typedef Batch<T, M, V> B;
   if (M == 0) {
     dw[0] = (T)0;
     return;
   }
+  if (B::V2) {
+    uint32_t w[4 * (B::NB > 0 ? B::NB : 1)];
 #pragma unroll
-  for (int b = 0; b < B::NB; b++) {
-    uint32_t r[4];
-    philox4x32_10(pp, blk0 + (uint32_t)b, ks, r);
-    normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
+    for (int b = 0; b < B::NB; b++) {
+      uint32_t r[4];
+      philox4x32_10(pp, blk0 + (uint32_t)b, ks, r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) w[4 * b + i] = r[i];
+    }
+    normals_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
+  } else {
+#pragma unroll
+    for (int b = 0; b < B::NB; b++) {
+      uint32_t r[4];
+      philox4x32_10(pp, blk0 + (uint32_t)b, ks, r);
+      normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
+    }
   }
 }
 
 // FP64 kernels take the per-path Philox form and the pinned coefficients, FP32 kernels the plain block function
 // (measured 0.45 % faster there: fewer live registers); `pp` is dead code in the FP32 instantiations.
-template <typename T, int M>
+template <typename T, int M, int V = 1>
 SDE_D void gen_batch(const PhiloxPath &pp, uint64_t path, uint32_t blk0, uint32_t stream, const PhiloxKeys &ks, const double *s_tab,
                      const double *lk, T scale2, T *dw, const double *kr) {
-  if (sizeof(T) == 8) gen_batch<T, M>(pp, blk0, ks, s_tab, lk, scale2, dw, kr);
-  else gen_batch<T, M>(path, blk0, stream, ks, s_tab, lk, scale2, dw);
+  if (sizeof(T) == 8) gen_batch<T, M, V>(pp, blk0, ks, s_tab, lk, scale2, dw, kr);
+  else gen_batch<T, M, V>(path, blk0, stream, ks, s_tab, lk, scale2, dw);
 }
+
+// Stream v2, step by step: the normals of step u of a batch are produced just before the step needs them — pair P is
+// generated when the first step that reads it comes up, Philox block b when the first pair that reads one of its words
+// does — so that a thread carrying several paths holds at most three left-over words and one spare normal per path
+// between steps instead of a whole batch (8 normals, 12 words).  u is a constant after unrolling; every loop bound and
+// condition below folds at compile time.  Same words -> same normals as gen_batch<T, M, 2>.
+template <typename T, int M> struct LazyV2 {
+  typedef Batch<T, M, 2> B;
+  uint32_t w[4 * (B::NB > 0 ? B::NB : 1)];
+  T z[B::NZ];
+  static SDE_HD constexpr int pairs_before(int u) { return (u * M + 1) / 2; }                 // pairs steps [0, u) read
+  static SDE_HD constexpr int blocks_before(int P) { return P == 0 ? 0 : (3 * P - 1) / 4 + 1; }  // blocks pairs [0, P) read
+  SDE_D void produce(int u, const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, const double *s_tab, const double *lk,
+                     const double *kr) {
+#pragma unroll
+    for (int P = 0; P < B::NZ / 2; P++) {
+      if (P >= pairs_before(u) && P < pairs_before(u + 1)) {
+#pragma unroll
+        for (int b = 0; b < B::NB; b++) {
+          if (b >= blocks_before(P) && b < blocks_before(P + 1)) {
+            uint32_t r[4];
+            philox4x32_10(pp, blk0 + (uint32_t)b, ks, r);
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[4 * b + i] = r[i];
+          }
+        }
+        double z0, z1;
+        normal_pair_f64_v2(w[3 * P], w[3 * P + 1], w[3 * P + 2], s_tab, lk, z0, z1, kr);
+        z[2 * P] = (T)z0;
+        z[2 * P + 1] = (T)z1;
+      }
+    }
+  }
+};
 
 template <typename T> SDE_D bool all_finite(const T *x, int D) {
   bool ok = true;
@@ -515,15 +749,20 @@ template <int NQ> SDE_D void block_reduce_store(double (&v)[NQ], int nq, double 
 //     + optional fused payoff reduction (north_star (c)).  PPT paths per thread for ILP.
 //     chunk = blockDim.x * PPT consecutive paths per CTA; path = chunk_base + p*blockDim.x + tid.
 // ---------------------------------------------------------------------------------------------------
-template <class Model, typename T, int SCHEME, int PPT>
+template <class Model, typename T, int SCHEME, int PPT, int V = 1>
 SDE_D void sample_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
-  typedef Batch<T, M> B;
-  __shared__ double s_tab[TabSize<T>::value];
+  typedef Batch<T, M, V> B;
+  // transform tables: static shared memory, except the 40 KB of stream v2's fine tables, which come from the launch's
+  // dynamic shared memory (static + the one-path-per-thread form's staging arrays would pass the 48 KB static limit)
+  constexpr bool DYN_TAB = B::V2 && SDE_V2_FINE;
+  __shared__ double s_tab_static[DYN_TAB ? 1 : TabSize<T, V>::value];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double *s_tab = DYN_TAB ? (double *)s_dyn : s_tab_static;
   __shared__ double s_red[(SDE_BLOCK * SDE_PPT / PPT / 32) * 2 * SDE_MAXF];
   __shared__ double s_stage[PPT == SDE_PPT ? 1 : SDE_MAXF * SDE_BLOCK * SDE_PPT];   // features of a chunk (PPT < SDE_PPT forms)
   __shared__ unsigned char s_ok[PPT == SDE_PPT ? 1 : SDE_BLOCK * SDE_PPT];
-  load_tables<T>(s_tab, a.noise_var);
+  load_tables<T, V>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
 
@@ -552,14 +791,32 @@ SDE_D void sample_body(const sde_args &a) {
   PhiloxPath pp[PPT];
 #pragma unroll
   for (int p = 0; p < PPT; p++) philox_path_init(gpath0 + (uint64_t)(p * (int)blockDim.x), a.stream, ks, pp[p], sizeof(T) == 8);
-  PinnedCoef pc(a.lk, sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8, V);
   const double *kr = pc.v;
 
+  if (B::V2 && M > 0) {
+    // stream v2: step-major order inside a batch, normals produced lazily (LazyV2) — the same arithmetic per path
+    LazyV2<T, (M > 0 ? M : 1)> lz[PPT];
+    for (int64_t it = 0; it <= nbatch; it++) {
+      if (it == nbatch && rem == 0) break;
+#pragma unroll
+      for (int u = 0; u < B::U; u++) {
+        if (it < nbatch || u < rem) {
+          const T t = t0 + (T)(it * B::U + u) * dt;
+#pragma unroll
+          for (int p = 0; p < PPT; p++) {
+            lz[p].produce(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr);
+            Model::template step<SCHEME>(cst.c, t, dt, lz[p].z + u * (M > 0 ? M : 0), x[p]);
+          }
+        }
+      }
+    }
+  } else {
   for (int64_t it = 0; it < nbatch; it++) {
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
-      gen_batch<T, M>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk,
+      gen_batch<T, M, V>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk,
                       (T)a.noise_var, dw, kr);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
@@ -572,7 +829,7 @@ SDE_D void sample_body(const sde_args &a) {
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
       T dw[B::NZ];
-      gen_batch<T, M>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, ks, s_tab, a.lk,
+      gen_batch<T, M, V>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, ks, s_tab, a.lk,
                       (T)a.noise_var, dw, kr);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
@@ -583,6 +840,7 @@ SDE_D void sample_body(const sde_args &a) {
       }
     }
   }
+  }  // stream v1 order
 
   // terminal states, reference layout [path][D]  (Vector{SVector{D}}: simulation.jl:59-60)
   if (a.out) {
@@ -676,13 +934,13 @@ SDE_D void sample_body(const sde_args &a) {
 //     ΔW accumulates the fine increments sequentially from zero exactly as multilevel.jl:79-83 does.
 //     out = fine terminals, out2 = coarse terminals; partial features (Pf - Pc, Pf, Pc).
 // ---------------------------------------------------------------------------------------------------
-template <class Model, typename T, int SCHEME>
+template <class Model, typename T, int SCHEME, int V = 1>
 SDE_D void mlmc_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
-  typedef Batch<T, M> B;
-  __shared__ double s_tab[TabSize<T>::value];
+  typedef Batch<T, M, V> B;
+  __shared__ double s_tab[TabSize<T, V>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
-  load_tables<T>(s_tab, a.noise_var);
+  load_tables<T, V>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
 
@@ -693,7 +951,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   const T dtf = (T)a.dt, dtc = (T)a.dt_coarse, t0 = (T)a.t0;
   Model::prepare(prm, dtf, cf.c);
   Model::prepare(prm, dtc, cc.c);
-  PinnedCoef pc(a.lk, sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8, V);
 
   const int64_t nchunks = (a.npaths + blockDim.x - 1) / blockDim.x;
   for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -723,7 +981,7 @@ SDE_D void mlmc_body(const sde_args &a) {
       T dw[NBG][B::NZ];
 #pragma unroll
       for (int b = 0; b < NBG; b++)
-        gen_batch<T, M>(pp, gpath, (uint32_t)((gi * NBG + b) * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[b], pc.v);
+        gen_batch<T, M, V>(pp, gpath, (uint32_t)((gi * NBG + b) * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[b], pc.v);
 #pragma unroll
       for (int j = 0; j < G; j++) {
         const T tc = t0 + (T)(gi * (G / 2) + j / 2) * dtc;
@@ -742,7 +1000,7 @@ SDE_D void mlmc_body(const sde_args &a) {
   }
   for (; it < nbatch; it++) {
     T dw[B::NZ];
-    gen_batch<T, M>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
+    gen_batch<T, M, V>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t fstep = it * B::U + u;
@@ -833,12 +1091,12 @@ template <> struct VecStore<float, 8> {
   }
 };
 
-template <class Model, typename T, int SCHEME>
+template <class Model, typename T, int SCHEME, int V = 1>
 SDE_D void simulate_soa_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M, VEC = SDE_SOA_VEC;
-  typedef Batch<T, M> B;
-  __shared__ double s_tab[TabSize<T>::value];
-  load_tables<T>(s_tab, a.noise_var);
+  typedef Batch<T, M, V> B;
+  __shared__ double s_tab[TabSize<T, V>::value];
+  load_tables<T, V>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
@@ -883,16 +1141,16 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   PhiloxPath pp[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; v++) philox_path_init(gpath + (uint64_t)v, a.stream, ks, pp[v], sizeof(T) == 8 && SDE_SOA_PP);
-  PinnedCoef pc(a.lk, sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8, V);
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[VEC][B::NZ];
 #pragma unroll
     for (int v = 0; v < VEC; v++)
 #if SDE_SOA_PP
-      gen_batch<T, M>(pp[v], gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v], pc.v);
+      gen_batch<T, M, V>(pp[v], gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v], pc.v);
 #else
-      gen_batch<T, M>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v],
+      gen_batch<T, M, V>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v],
                       sizeof(T) == 8 ? pc.v : nullptr);
 #endif
 #pragma unroll
@@ -961,17 +1219,17 @@ SDE_D void tile_store(const T *tile, T *g, int64_t gstride, int nlive, int ncols
 //     each warp stages a (32 paths) x (TS time rows) tile in shared memory and writes whole path rows,
 //     so global stores stay coalesced (32 consecutive elements per instruction) without a transpose pass.
 // ---------------------------------------------------------------------------------------------------
-template <class Model, typename T, int SCHEME>
+template <class Model, typename T, int SCHEME, int V = 1>
 SDE_D void simulate_ref_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   constexpr int PW = SDE_SIMREF_PW;           // paths per lane: a warp owns 32 * PW consecutive paths
   constexpr int TS = (sizeof(T) == 8 ? 16 : 32) / D;  // time rows per tile: 128-byte row segments per path
   constexpr int ROW = TS * D;                 // elements per path per tile
   constexpr int LDS = ROW | 1;                // odd stride: conflict-free column writes
-  typedef Batch<T, M> B;
-  __shared__ double s_tab[TabSize<T>::value];
+  typedef Batch<T, M, V> B;
+  __shared__ double s_tab[TabSize<T, V>::value];
   extern __shared__ __align__(16) unsigned char s_dyn[];   // [warps][32 * PW rows][LDS]: sde_simref_smem_bytes()
-  load_tables<T>(s_tab, a.noise_var);
+  load_tables<T, V>(s_tab, a.noise_var);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
@@ -1015,13 +1273,13 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   PhiloxPath pp[PW];
 #pragma unroll
   for (int p = 0; p < PW; p++) philox_path_init(gpath + (uint64_t)(32 * p), a.stream, ks, pp[p], sizeof(T) == 8);
-  PinnedCoef pc(a.lk, sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8, V);
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
     T dw[PW][B::NZ];
 #pragma unroll
     for (int p = 0; p < PW; p++)
-      gen_batch<T, M>(pp[p], gpath + (uint64_t)(32 * p), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[p],
+      gen_batch<T, M, V>(pp[p], gpath + (uint64_t)(32 * p), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[p],
                       pc.v);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
@@ -1353,7 +1611,7 @@ static __device__ __noinline__ void simrt_acquire(int pending) {
   __syncwarp();
 }
 
-template <class Model, typename T, int SCHEME>
+template <class Model, typename T, int SCHEME, int V = 1>
 SDE_D void simulate_ref_tma_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   constexpr int ROWB = D * (int)sizeof(T);
@@ -1362,12 +1620,12 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
   constexpr int TS = OK ? 128 / ROWB : 1;     // rows per tile (a power of two)
   constexpr int TILE = 32 * 128;
   static_assert(NSX == 2 && TILE == 4096, "ring arithmetic below assumes two 4 KB stages");
-  typedef Batch<T, M> B;
+  typedef Batch<T, M, V> B;
   constexpr int U = B::U;
-  __shared__ double s_tab[TabSize<T>::value];
+  __shared__ double s_tab[TabSize<T, V>::value];
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  load_tables<T>(s_tab, a.noise_var);
-  if (!OK) return;
+  load_tables<T, V>(s_tab, a.noise_var);
+  if (!OK || U > TS) return;   // at most one tile boundary per batch (the host routes 8-byte rows here: TS = 16 >= U)
   unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned char *tiles = smem + (size_t)wid * (NSX * TILE);
@@ -1466,11 +1724,11 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
   const uint64_t gpath = (uint64_t)(a.path0 + p);
   PhiloxPath pp;
   philox_path_init(gpath, a.stream, ks, pp, sizeof(T) == 8);
-  PinnedCoef pc(a.lk, sizeof(T) == 8);
+  PinnedCoef pc(a.lk, sizeof(T) == 8, V);
   const int64_t nbatch = (a.nsteps + U - 1) / U;
   auto slow_batch = [&](int64_t it) {
     T dw[B::NZ];
-    gen_batch<T, M>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
+    gen_batch<T, M, V>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int64_t i = it * U + u;
@@ -1491,7 +1749,7 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
       const int i_last = (int)(it * U) + U;
       begin_check(i_last);
       T dw[B::NZ];
-      gen_batch<T, M>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
+      gen_batch<T, M, V>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const T t = t0 + (T)(it * U + u) * dt;
@@ -1647,6 +1905,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #ifndef SDE_SAMPLE_MINB
 #define SDE_SAMPLE_MINB 1
 #endif
+#ifndef SDE_SAMPLE_MINB_V2
+#define SDE_SAMPLE_MINB_V2 2 /* stream v2 terminal kernel: measured 245.6 (2 CTAs, 214 registers) vs 232.3 (3 CTAs, 164) vs 220.6 G path-steps/s (4 CTAs, 128): the same instruction count, better scheduled with more registers */
+#endif
 #ifndef SDE_SAMPLE1_MINB
 #define SDE_SAMPLE1_MINB 0
 #endif
@@ -1687,6 +1948,22 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simwt_##SNAME##_##PNAME(                 \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_tma_body<MODEL, T, SCH>(a); }
 
+// The RNG-driven FP64 kernels again for normal stream v2 (sdeb200_opts.rng = 2); FP32 and the Wiener-driven kernels
+// do not depend on the stream version.
+#define SDE_KERNELS_V2(MODEL, TAG, SCH, SNAME)                                                                   \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SAMPLE_MINB_V2) sdek_##TAG##_sample_##SNAME##_f64v2(    \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, SCH, SDE_PPT, 2>(a); }          \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT, SDE_SAMPLE1_MINB) sdek_##TAG##_sample1_##SNAME##_f64v2( \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, SCH, 1, 2>(a); }                \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_F64_MINB) sdek_##TAG##_mlmc_##SNAME##_f64v2(         \
+      const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, double, SCH, 2>(a); }                     \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_F64_MINB) sdek_##TAG##_simsoa_##SNAME##_f64v2(       \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, double, SCH, 2>(a); }             \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_##SNAME##_f64v2(    \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, double, SCH, 2>(a); }             \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_##SNAME##_f64v2(      \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, double, SCH, 2>(a); }
+
 // Exact one-step samplers exist for a few models only and have no Wiener-driven or coupled form
 // (src/simulation.jl:50-57,78-89): terminal and full-trajectory kernels, scheme id 3.
 #define SDE_KERNELS_EXACT(MODEL, TAG, T, PNAME)                                                                  \
@@ -1701,9 +1978,22 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_exact_##PNAME(                  \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, 3>(a); }
 
+#define SDE_KERNELS_EXACT_V2(MODEL, TAG)                                                                          \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_exact_f64v2(                      \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, 3, SDE_PPT, 2>(a); }            \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT) sdek_##TAG##_sample1_exact_f64v2(           \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, 3, 1, 2>(a); }                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_exact_f64v2(                      \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, double, 3, 2>(a); }               \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_exact_f64v2(        \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, double, 3, 2>(a); }               \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_exact_f64v2(          \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, double, 3, 2>(a); }
+
 #define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \
   SDE_KERNELS(MODEL, TAG, SCH, SNAME, double, f64)  \
-  SDE_KERNELS(MODEL, TAG, SCH, SNAME, float, f32)
+  SDE_KERNELS(MODEL, TAG, SCH, SNAME, float, f32)   \
+  SDE_KERNELS_V2(MODEL, TAG, SCH, SNAME)
 
 #define SDE_KERNELS_LOGT(MODEL, TAG, T, PNAME)                                                                   \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##_logt_##PNAME(                          \

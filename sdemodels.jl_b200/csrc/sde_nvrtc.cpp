@@ -129,6 +129,10 @@ int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision,
   src += std::string("\nSDE_KERNELS(sdeb200::GenModel, gen, 0, em, ") + T + ", " + P + ")\n";
   if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 1, mil, ") + T + ", " + P + ")\n";
   if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 2, rk, ") + T + ", " + P + ")\n";
+  if (precision == 0) {  // the RNG-driven FP64 kernels on normal stream v2 as well
+    src += "SDE_KERNELS_V2(sdeb200::GenModel, gen, 0, em)\n";
+    if (M == 1) src += "SDE_KERNELS_V2(sdeb200::GenModel, gen, 1, mil)\nSDE_KERNELS_V2(sdeb200::GenModel, gen, 2, rk)\n";
+  }
   src += "SDE_KERNELS_COEF(sdeb200::GenModel, gen)\n";
   src += std::string("SDE_KERNELS_LOGT(sdeb200::GenModel, gen, ") + T + ", " + P + ")\n";
   const char *hdr_src[] = {sde_embedded_device_cuh, sde_embedded_args_h, sde_embedded_coeffs_inc};
@@ -188,14 +192,26 @@ int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precisio
   };
   const int nsch = M == 1 ? 3 : 1;
   const char *sn[3] = {"em", "mil", "rk"};
+  const int slot = precision == 0 ? 0 : 1;
   for (int s = 0; s < nsch; s++) {
     const std::string suf = std::string("_") + sn[s] + "_" + P;
-    if (!get("sdek_gen_sample" + suf, &kt->sample[s][precision]) || !get("sdek_gen_sample1" + suf, &kt->sample1[s][precision]) || !get("sdek_gen_mlmc" + suf, &kt->mlmc[s][precision]) ||
-        !get("sdek_gen_simsoa" + suf, &kt->simsoa[s][precision]) || !get("sdek_gen_simref" + suf, &kt->simref[s][precision]) ||
-        !get("sdek_gen_simw" + suf, &kt->simw[s][precision]) || !get("sdek_gen_simwt" + suf, &kt->simwt[s][precision]) ||
-        !get("sdek_gen_simrt" + suf, &kt->simrt[s][precision])) {
+    if (!get("sdek_gen_sample" + suf, &kt->sample[s][slot]) || !get("sdek_gen_sample1" + suf, &kt->sample1[s][slot]) ||
+        !get("sdek_gen_mlmc" + suf, &kt->mlmc[s][slot]) || !get("sdek_gen_simsoa" + suf, &kt->simsoa[s][slot]) ||
+        !get("sdek_gen_simref" + suf, &kt->simref[s][slot]) || !get("sdek_gen_simw" + suf, &kt->simw[s][slot]) ||
+        !get("sdek_gen_simwt" + suf, &kt->simwt[s][slot]) || !get("sdek_gen_simrt" + suf, &kt->simrt[s][slot])) {
       cudaLibraryUnload(lib);
       return SDEB200_E_CUDA;
+    }
+    if (precision == 0) {
+      const std::string s2 = suf + "v2";
+      if (!get("sdek_gen_sample" + s2, &kt->sample[s][2]) || !get("sdek_gen_sample1" + s2, &kt->sample1[s][2]) ||
+          !get("sdek_gen_mlmc" + s2, &kt->mlmc[s][2]) || !get("sdek_gen_simsoa" + s2, &kt->simsoa[s][2]) ||
+          !get("sdek_gen_simref" + s2, &kt->simref[s][2]) || !get("sdek_gen_simrt" + s2, &kt->simrt[s][2])) {
+        cudaLibraryUnload(lib);
+        return SDEB200_E_CUDA;
+      }
+      kt->simw[s][2] = kt->simw[s][0];
+      kt->simwt[s][2] = kt->simwt[s][0];
     }
   }
   if (!get(std::string("sdek_gen_logt_") + P, &kt->logt[precision]) || !get("sdek_gen_coef", &kt->coef)) {

@@ -68,7 +68,7 @@ def _level_counts(s, n):
     return n
 
 
-def _ml_sample(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, path_offset, device):
+def _ml_sample(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, path_offset, device, rng=None):
     """sample(model, ::MultilevelScheme, ...) -> [x_L0, xc_1, xf_1, ...]   (multilevel.jl:52-63, 104-108)"""
     from . import simulation as sim
     L = _lib.lib()
@@ -78,12 +78,12 @@ def _ml_sample(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, pa
     v0, scalar = sim._x0(model, x0)
     p = sim._params(model)
     out = [sim.sample(model, ml_schemes[0], t0, x0, nsteps * ml_steps[0], counts[0], seed=seed, precision=precision,
-                      math=math, stream=stream, path_offset=path_offset, device=device)]
+                      math=math, stream=stream, path_offset=path_offset, rng=rng, device=device)]
     for i in range(1, len(s.levels)):
         coarse, fine = ml_schemes[i - 1], ml_schemes[i]
         shape = (counts[i],) if scalar else (counts[i], model._D)
         xc, xf = sim._Buf(shape, precision, None, device), sim._Buf(shape, precision, None, device)
-        o = sim._opts(coarse, t0, seed, precision, math, stream + i, path_offset)
+        o = sim._opts(coarse, t0, seed, precision, math, stream + i, path_offset, rng=rng)
         _lib.check(L.sdeb200_mlmc_sample_level(model._handle, C.byref(o), p.ctypes.data_as(_PD),
                                                v0.ctypes.data_as(_PD), fine.dt, s.substeps,
                                                nsteps * ml_steps[i - 1], counts[i], xc.ptr, xf.ptr))
@@ -92,7 +92,7 @@ def _ml_sample(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, pa
 
 
 def multilevel_sample_level(model, coarse, fine, substeps, t0, x0, nsteps, n, *, seed=0, precision="f64",
-                            math="fast", stream=0, path_offset=0, device=False):
+                            math="fast", stream=0, path_offset=0, rng=None, device=False):
     """_multilevel_sample(model, coarse_scheme, fine_scheme, substeps, t0, x0, nsteps, npaths) -> (xc, xf)
     (multilevel.jl:65-89); nsteps counts COARSE steps."""
     from . import simulation as sim
@@ -101,14 +101,14 @@ def multilevel_sample_level(model, coarse, fine, substeps, t0, x0, nsteps, n, *,
     p = sim._params(model)
     shape = (n,) if scalar else (n, model._D)
     xc, xf = sim._Buf(shape, precision, None, device), sim._Buf(shape, precision, None, device)
-    o = sim._opts(coarse, t0, seed, precision, math, stream, path_offset)
+    o = sim._opts(coarse, t0, seed, precision, math, stream, path_offset, rng=rng)
     _lib.check(L.sdeb200_mlmc_sample_level(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
                                            fine.dt, substeps, nsteps, n, xc.ptr, xf.ptr))
     return xc.arr, xf.arr
 
 
 def multilevel_simulate_level(model, coarse, fine, substeps, t0, x0, nsteps, n, *, seed=0, precision="f64",
-                              math="fast", stream=0, path_offset=0, device=False):
+                              math="fast", stream=0, path_offset=0, rng=None, device=False):
     """_multilevel_simulate(...) -> (xc, xf, tc, tf)   (multilevel.jl:91-100)"""
     from . import simulation as sim
     L = _lib.lib()
@@ -118,7 +118,7 @@ def multilevel_simulate_level(model, coarse, fine, substeps, t0, x0, nsteps, n, 
     fs = (n, nf) if scalar else (n, nf, model._D)
     cs = (n, nc) if scalar else (n, nc, model._D)
     xc, xf = sim._Buf(cs, precision, None, device), sim._Buf(fs, precision, None, device)
-    o = sim._opts(coarse, t0, seed, precision, math, stream, path_offset)
+    o = sim._opts(coarse, t0, seed, precision, math, stream, path_offset, rng=rng)
     _lib.check(L.sdeb200_mlmc_simulate_level(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
                                              fine.dt, substeps, nsteps, n, xc.ptr, xf.ptr))
     tf = t0 + fine.dt * np.arange(nsteps * substeps + 1)   # multilevel.jl:92
@@ -126,20 +126,20 @@ def multilevel_simulate_level(model, coarse, fine, substeps, t0, x0, nsteps, n, 
     return xc.arr, xf.arr, tc, tf
 
 
-def _ml_simulate(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, path_offset, device):
+def _ml_simulate(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, path_offset, device, rng=None):
     """simulate(model, ::MultilevelScheme, ...) -> (x, t), 2L-1 entries each   (multilevel.jl:37-50, 110-115)"""
     from . import simulation as sim
     counts = _level_counts(s, n)
     ml_schemes = schemes(s)
     ml_steps = [s.substeps ** l for l in s.levels]
     x1, t1 = sim.simulate(model, ml_schemes[0], t0, x0, nsteps * ml_steps[0], counts[0], seed=seed,
-                          precision=precision, math=math, stream=stream, path_offset=path_offset, device=device)
+                          precision=precision, math=math, stream=stream, path_offset=path_offset, rng=rng, device=device)
     xs, ts = [x1], [t1]
     for i in range(1, len(s.levels)):
         xc, xf, tc, tf = multilevel_simulate_level(model, ml_schemes[i - 1], ml_schemes[i], s.substeps, t0, x0,
                                                    nsteps * ml_steps[i - 1], counts[i], seed=seed,
                                                    precision=precision, math=math, stream=stream + i,
-                                                   path_offset=path_offset, device=device)
+                                                   path_offset=path_offset, rng=rng, device=device)
         xs += [xc, xf]
         ts += [tc, tf]
     return xs, ts
@@ -158,7 +158,7 @@ class MultilevelEstimate:
 
 
 def ml_estimate(model, s, payoff, t0, x0, nsteps, n, *, seed=0, precision="f64", math="fast", stream=0,
-                path_offset=0):
+                path_offset=0, rng=None):
     """Multilevel estimator of E[payoff(X_T)]: all levels run concurrently on separate streams, each level ends
     in its own all-reduce.  `n`: this rank's paths per level."""
     from . import simulation as sim
@@ -168,7 +168,7 @@ def ml_estimate(model, s, payoff, t0, x0, nsteps, n, *, seed=0, precision="f64",
     p = sim._params(model)
     nl = len(s.levels)
     res = np.zeros((nl, 8))
-    o = sim._opts(s.scheme, t0, seed, precision, math, stream, path_offset)
+    o = sim._opts(s.scheme, t0, seed, precision, math, stream, path_offset, rng=rng)
     pay = sim._payoff(payoff)
     _lib.check(L.sdeb200_mlmc_estimate(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
                                        s.substeps, s.levels[0], nl, int(nsteps),
@@ -196,7 +196,7 @@ class AdaptiveMLMC:
 
 
 def mlmc_adaptive(model, scheme, substeps, payoff, t0, x0, nsteps, eps, *, lmin=2, lmax=10, n0=1 << 14, seed=0,
-                  precision="f64", math="fast", stream=0, alpha=1.0):
+                  precision="f64", math="fast", stream=0, alpha=1.0, rng=None):
     """Giles' adaptive multilevel estimator on top of the per-level exact sums (the reference
     stops at the raw level samples, multilevel.jl:52-63).  Levels 0..L with base `scheme`; N_l is raised to
     ceil(2 eps^-2 sqrt(V_l / C_l) sum_k sqrt(V_k C_k)); a level is added while the extrapolated bias
@@ -215,12 +215,12 @@ def mlmc_adaptive(model, scheme, substeps, payoff, t0, x0, nsteps, eps, *, lmin=
             return
         if level == 0:
             e = sim.estimate(model, scheme, payoff, t0, x0, nsteps, int(n_add), seed=seed, precision=precision,
-                             math=math, stream=stream, path_offset=int(done[0]))
+                             math=math, stream=stream, path_offset=int(done[0]), rng=rng)
             sums[0] += e.sums[0]
         else:
             coarse = subdivide(scheme, substeps ** (level - 1))
             fine = subdivide(scheme, substeps ** level)
-            o = sim._opts(coarse, t0, seed, precision, math, stream + level, int(done[level]))
+            o = sim._opts(coarse, t0, seed, precision, math, stream + level, int(done[level]), rng=rng)
             out = np.zeros(8)
             _lib.check(L_.sdeb200_mlmc_estimate_level(model._handle, C.byref(o), p.ctypes.data_as(_PD),
                                                       v0.ctypes.data_as(_PD), fine.dt, substeps,

@@ -24,9 +24,10 @@ from .multilevel import MultilevelScheme, _ml_sample, _ml_simulate
 _PD = C.POINTER(C.c_double)
 _PREC = {"f64": _lib.F64, "f32": _lib.F32, "float64": _lib.F64, "float32": _lib.F32}
 _MATH = {"fast": _lib.MATH_FAST, "strict": _lib.MATH_STRICT}
+DEFAULT_RNG = int(__import__("os").environ.get("SDEB200_RNG", "0"))   # sdeb200_opts.rng: 0/1 = normal stream v1 (the default), 2 = stream v2 (96 Philox bits per FP64 pair)
 
 
-def _opts(scheme, t0, seed=0, precision="f64", math="fast", stream=0, path_offset=0, dt=None):
+def _opts(scheme, t0, seed=0, precision="f64", math="fast", stream=0, path_offset=0, rng=None, dt=None):
     o = _lib.Opts()
     o.scheme = scheme._id
     o.precision = _PREC[precision]
@@ -36,6 +37,7 @@ def _opts(scheme, t0, seed=0, precision="f64", math="fast", stream=0, path_offse
     o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     o.stream = int(stream)
     o.path_offset = int(path_offset)
+    o.rng = int(DEFAULT_RNG if rng is None else rng)
     return o
 
 
@@ -82,20 +84,20 @@ class _Buf:
 
 
 def sample(model, scheme, t0, x0, nsteps, npaths=None, *, seed=0, precision="f64", math="fast", stream=0,
-           path_offset=0, out=None, device=False):
+           path_offset=0, rng=None, out=None, device=False):
     """sample(model, scheme, t0, x0, nsteps[, npaths])   (simulation.jl:39-48, 59-67; multilevel.jl:34-35,52-63)
 
     Terminal state(s) after `nsteps` steps of `scheme`.  Without `npaths`: one path (a float or a D-vector).
     With a MultilevelScheme: the list [x_L0, xc_1, xf_1, xc_2, xf_2, ...] of 2L-1 arrays."""
     if isinstance(scheme, MultilevelScheme):
         return _ml_sample(model, scheme, t0, x0, nsteps, npaths, seed=seed, precision=precision, math=math,
-                          stream=stream, path_offset=path_offset, device=device)
+                          stream=stream, path_offset=path_offset, rng=rng, device=device)
     L = _lib.lib()
     v0, scalar = _x0(model, x0)
     single = npaths is None
     n = 1 if single else int(npaths)
     buf = _Buf((n,) if scalar else (n, model._D), precision, out, device)
-    o = _opts(scheme, t0, seed, precision, math, stream, path_offset)
+    o = _opts(scheme, t0, seed, precision, math, stream, path_offset, rng=rng)
     p = _params(model)
     _lib.check(L.sdeb200_sample(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
                                 int(nsteps), n, buf.ptr))
@@ -115,14 +117,14 @@ def _times(t0, dt, nsteps):
 
 
 def simulate(model, scheme, t0, x0, nsteps, npaths=None, *, seed=0, precision="f64", math="fast", stream=0,
-             path_offset=0, out=None, device=False, layout="reference"):
+             path_offset=0, rng=None, out=None, device=False, layout="reference"):
     """simulate(model, scheme, t0, x0, nsteps[, npaths]) -> (x, t)   (simulation.jl:71-76, 104-117, 149-154)
 
     Full trajectories, start point included.  layout="soa" keeps the coalesced device layout
     (nsteps+1, D, npaths) instead of the reference's."""
     if isinstance(scheme, MultilevelScheme):
         return _ml_simulate(model, scheme, t0, x0, nsteps, npaths, seed=seed, precision=precision, math=math,
-                            stream=stream, path_offset=path_offset, device=device)
+                            stream=stream, path_offset=path_offset, rng=rng, device=device)
     L = _lib.lib()
     v0, scalar = _x0(model, x0)
     single = npaths is None
@@ -135,7 +137,7 @@ def simulate(model, scheme, t0, x0, nsteps, npaths=None, *, seed=0, precision="f
         shape = (nrows, n) if scalar else (nrows, D, n)
         lay = _lib.LAYOUT_SOA
     buf = _Buf(shape, precision, out, device)
-    o = _opts(scheme, t0, seed, precision, math, stream, path_offset)
+    o = _opts(scheme, t0, seed, precision, math, stream, path_offset, rng=rng)
     p = _params(model)
     _lib.check(L.sdeb200_simulate(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
                                   int(nsteps), n, lay, buf.ptr))
@@ -145,7 +147,7 @@ def simulate(model, scheme, t0, x0, nsteps, npaths=None, *, seed=0, precision="f
     return x, _times(t0, scheme.dt, int(nsteps))
 
 
-def simulate_(x, model, scheme, t0, x0, w=None, *, seed=0, precision=None, math="fast", stream=0, path_offset=0):
+def simulate_(x, model, scheme, t0, x0, w=None, *, seed=0, precision=None, math="fast", stream=0, path_offset=0, rng=None):
     """simulate!(x, model, scheme, t0, x0[, w])   (simulation.jl:104-117 and 119-134)
 
     With `w`: trajectories driven by the cumulative Wiener path w (same layout as x, last axis M); `x is w`
@@ -158,7 +160,7 @@ def simulate_(x, model, scheme, t0, x0, w=None, *, seed=0, precision=None, math=
             raise ValueError("simulate_ works in place: x and w must be C-contiguous")
     if precision is None:
         precision = "f32" if str(x.dtype).endswith("float32") else "f64"
-    o = _opts(scheme, t0, seed, precision, math, stream, path_offset)
+    o = _opts(scheme, t0, seed, precision, math, stream, path_offset, rng=rng)
     p = _params(model)
     D, M = model._D, max(model._M, 1)
     xs = tuple(x.shape)
@@ -181,7 +183,7 @@ def simulate_(x, model, scheme, t0, x0, w=None, *, seed=0, precision=None, math=
     return x
 
 
-def wiener_(w, dt, *, seed=0, stream=0, path_offset=0, math="fast"):
+def wiener_(w, dt, *, seed=0, stream=0, path_offset=0, rng=None, math="fast"):
     """wiener!(w, Δt)   (simulation.jl:22-35): w[(npaths,) nrows (, dim)], row 0 = 0, running sums of N(0, Δt)."""
     L = _lib.lib()
     is_torch = hasattr(w, "data_ptr")
@@ -189,6 +191,7 @@ def wiener_(w, dt, *, seed=0, stream=0, path_offset=0, math="fast"):
     o = _lib.Opts()
     o.precision, o.math, o.dt = _PREC[precision], _MATH[math], float(dt)
     o.seed, o.stream, o.path_offset = int(seed), int(stream), int(path_offset)
+    o.rng = int(DEFAULT_RNG if rng is None else rng)
     ws = tuple(w.shape)
     if len(ws) == 1:
         n, nrows, dim = 1, ws[0], 1
@@ -291,17 +294,17 @@ class Estimate:
 
 
 def estimate(model, scheme, payoff, t0, x0, nsteps, npaths, *, seed=0, precision="f64", math="fast", stream=0,
-             path_offset=0, terminal=None):
+             path_offset=0, rng=None, terminal=None):
     """Monte Carlo estimate of E[payoff(X_T)]: `sample` with the payoff reduced on the fly (warp shuffles, CTA
     partials, exact accumulation, one NCCL all-reduce when a communicator is up).  `npaths` is this rank's
     share; the returned sums cover all ranks.  Oracle: mean(payoff.(sample(model, scheme, ...)))."""
     if isinstance(scheme, MultilevelScheme):
         from .multilevel import ml_estimate
         return ml_estimate(model, scheme, payoff, t0, x0, nsteps, npaths, seed=seed, precision=precision, math=math,
-                           stream=stream, path_offset=path_offset)
+                           stream=stream, path_offset=path_offset, rng=rng)
     L = _lib.lib()
     v0, _ = _x0(model, x0)
-    o = _opts(scheme, t0, seed, precision, math, stream, path_offset)
+    o = _opts(scheme, t0, seed, precision, math, stream, path_offset, rng=rng)
     p = _params(model)
     nf = model._D if payoff.kind == _lib.PAYOFF_MOMENTS else 1
     res = np.zeros(2 * nf + 2)

@@ -42,6 +42,35 @@ extern "C" void h_pair_from_bits(const uint32_t *r4, double scale2, double *z) {
   make_log_consts(scale2, lk);
   normal_pair_f64(r, tab, lk, z[0], z[1]);
 }
+// stream v2: pair P of a path from words 3P..3P+2 of its Philox word stream
+static uint32_t h_word(uint64_t seed, uint32_t stream, uint64_t path, uint64_t W) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), (uint32_t)(W >> 2), stream, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  return r[W & 3];
+}
+extern "C" void h_normals_f64_v2(uint64_t seed, uint32_t stream, uint64_t path, uint64_t q0, int64_t n, double scale2,
+                                 double *out) {
+  static double tab[SDE_TAB2_DOUBLES];
+  double lk[6];
+  h_scaled_tables_v2(scale2, tab);
+  make_log_consts_v2(scale2, lk);
+  for (int64_t i = 0; i < n; i++) {
+    const uint64_t q = q0 + (uint64_t)i, P = q >> 1;
+    double z[2];
+    normal_pair_f64_v2(h_word(seed, stream, path, 3 * P), h_word(seed, stream, path, 3 * P + 1), h_word(seed, stream, path, 3 * P + 2),
+                       tab, lk, z[0], z[1]);
+    out[i] = z[q & 1];
+  }
+}
+extern "C" void h_pair_from_words_v2(const uint32_t *w3, double scale2, double *z) {
+  static double tab[SDE_TAB2_DOUBLES];
+  double lk[6];
+  h_scaled_tables_v2(scale2, tab);
+  make_log_consts_v2(scale2, lk);
+  normal_pair_f64_v2(w3[0], w3[1], w3[2], tab, lk, z[0], z[1]);
+}
+extern "C" double h_sqrt6(double v) { return sqrt_from_seed6(v, rsqrt_seed(v)); }
+extern "C" double h_sqrt7(double v) { return sqrt_core(v); }
 // geometry of the TMA trajectory tiles (sde_args.h): paths per tensor-map row and the first aligned row of a sub-path
 extern "C" int h_tma_group(int64_t pitch_bytes) { return sde_tma_group(pitch_bytes); }
 extern "C" int h_tma_head(int j, int64_t pitch_bytes, int rowb) { return sde_tma_head(j, pitch_bytes, rowb); }

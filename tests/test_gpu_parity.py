@@ -68,17 +68,21 @@ def test_wiener_driven_fast_within_1e12(gpu, O, name, params, x0, sid, nsteps):
 
 @pytest.mark.parametrize("name,params,x0,sid,nsteps", CASES)
 def test_wiener_driven_f32_within_1e5(gpu, O, name, params, x0, sid, nsteps):
+    """north_star: FP32 trajectories within 1e-5 of the reference arithmetic ON IDENTICAL INCREMENTS: the Wiener path is
+    float-valued (drawn with the float oracle's wiener!), so w[i] - w[i-1] is exact in float and in double; every row of
+    every path is compared with the Float64 oracle.  (tests/test_gpu_fp32_parity.py pins the FP32 kernels bit for bit
+    to a float restatement of the same loops and records the per-row deviation table.)"""
     dt = 1.0 / nsteps
     D, M, _ = O.dims(name)
-    w = wiener_paths(O, 130, nsteps, M, dt, 3).astype(np.float32)
+    z = np.random.default_rng(3).standard_normal((2000, nsteps, M)).astype(np.float32)
+    w = O.wiener_z(dt, z, precision="f32")
     ref = O.simulate_wiener(name, sid, params, 0.0, dt, x0, w.astype(np.float64))
-    x = np.empty(ref.shape, dtype=np.float32)
-    xs = x[..., 0] if D == 1 else x
-    ws = w[..., 0] if M == 1 else w
-    gpu.simulate_(xs, _model(gpu, name, params), _scheme(gpu, sid, dt), 0.0, x0, np.ascontiguousarray(ws))
-    # FP32 rounding accumulates over the trajectory: compare terminal S relative, all rows with a path-length factor
-    assert rel_err(x[:, -1, 0], ref[:, -1, 0]) <= 2e-4
-    assert rel_err(x[:, :32], ref[:, :32]) <= 1e-5
+    for math in ("strict", "fast"):
+        x = np.empty(ref.shape, dtype=np.float32)
+        xs = x[..., 0] if D == 1 else x
+        ws = w[..., 0] if M == 1 else w
+        gpu.simulate_(xs, _model(gpu, name, params), _scheme(gpu, sid, dt), 0.0, x0, np.ascontiguousarray(ws), math=math)
+        assert rel_err(x, ref) <= 1e-5, (name, sid, math)
 
 
 def test_wiener_driven_in_place(gpu, O):

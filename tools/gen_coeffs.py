@@ -131,6 +131,40 @@ def main():
     for nm, v in (("SDE_ROT_S0", a), ("SDE_ROT_S1", -a ** 3 / 6), ("SDE_ROT_S2", a ** 5 / 120),
                   ("SDE_ROT_C1", -a ** 2 / 2), ("SDE_ROT_C2", a ** 4 / 24)):
         kidx.append((nm, hexf(v)))
+    # stream v2 (32-bit angle word c): the same 1024 cells, offset t = ((c & 0x3FFFFF) - 2^21) * 2^10 = 2^32 d as a 32-bit
+    # signed integer: exact power-of-two rescalings of the coefficients above (a2 = a * 2^22)
+    a2 = 2 * mp.pi / 1024 / mp.mpf(2) ** 32
+    for nm, v in (("SDE_ROT2_S0", a2), ("SDE_ROT2_S1", -a2 ** 3 / 6), ("SDE_ROT2_S2", a2 ** 5 / 120),
+                  ("SDE_ROT2_C1", -a2 ** 2 / 2), ("SDE_ROT2_C2", a2 ** 4 / 24)):
+        kidx.append((nm, hexf(v)))
+    # stream v2, finer tables (fewer polynomial terms): 2048 rotation cells, idx = c >> 21, t = ((c & 0x1FFFFF) - 2^20) * 2^11
+    a3 = 2 * mp.pi / 2048 / mp.mpf(2) ** 32
+    for nm, v in (("SDE_ROT3_S0", a3), ("SDE_ROT3_S1", -a3 ** 3 / 6), ("SDE_ROT3_C1", -a3 ** 2 / 2), ("SDE_ROT3_C2", a3 ** 4 / 24)):
+        kidx.append((nm, hexf(v)))
+    phi3 = mp.pi / 2048
+    report.append(f"ROT3 (2048 cells): truncation errors sin {mp.nstr(phi3 ** 5 / 120, 3)}, cos {mp.nstr(phi3 ** 6 / 720, 3)}")
+    out.append("// " + report[-1])
+    out.append("// rotation table of stream v2: {cos, sin}(2 pi (i + 1/2) / 2048), i = 0..2047")
+    out.append("#define SDE_ROT3_TAB_INIT { \\")
+    for i in range(2048):
+        th = 2 * mp.pi * (mp.mpf(i) + mp.mpf(1) / 2) / 2048
+        out.append(f"  {hexf(mp.cos(th))}, {hexf(mp.sin(th))}, \\")
+    out.append("}")
+    # stream v2 log table: 512 entries, c_j = 1 + (j + 1/2)/512, |r| <= 2^-10 (1 + 2^-9): -2 log1p(r) = r * Q2(r), 4 coefficients
+    R2 = mp.mpf(2) ** -10 * (1 + mp.mpf(2) ** -9)
+    c2 = rnd(cheb_fit(fq, -R2, R2, 4))
+    e2 = max_err(lambda r: fq(r) * r, [mp.mpf(0)] + c2, -R2, R2)
+    report.append(f"LOG1P v2 (512-entry table): 4 coefficients, max abs err of r*Q2(r) {mp.nstr(e2, 3)}")
+    out.append(f"// {report[-1]}")
+    for i, v in enumerate(c2):
+        kidx.append((f"SDE_LOG2_C{i}", hexf(v)))
+    out.append("// log table of stream v2: {rn(1/c_j), rn(2 ln rn(1/c_j) + 2^-50)}, c_j = 1 + (j + 1/2)/512")
+    out.append("#define SDE_LOG2_TAB_INIT { \\")
+    for j in range(512):
+        cj = 1 + (mp.mpf(j) + mp.mpf(1) / 2) / 512
+        ic = mp.mpf(float(1 / cj))
+        out.append(f"  {hexf(ic)}, {hexf(mp.mpf(float(2 * mp.log(ic) + mp.mpf(2) ** -50)))}, \\")
+    out.append("}")
     phi = mp.pi / 1024
     report.append(f"ROT: truncation errors sin {mp.nstr(phi ** 7 / 5040, 3)}, cos {mp.nstr(phi ** 6 / 720, 3)}")
     out.append("// " + report[-1])
