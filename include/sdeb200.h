@@ -17,8 +17,10 @@
  *     (cudaPointerGetAttributes) and stages host buffers through pinned memory overlapped with compute.
  *     Element type is double for SDEB200_F64 and float for SDEB200_F32.
  *   - the caller owns every array; the library owns model handles (sdeb200_model_free).
- *   - calls are blocking and not thread-safe (one call at a time per process), like the reference,
- *     which is single-threaded and uses a process-global RNG (src/simulation.jl:4-18).
+ *   - calls are blocking; ONE call at a time per process (the reference itself is single-threaded and uses a
+ *     process-global RNG, src/simulation.jl:4-18).  Any host thread may make that call: every entry point selects the
+ *     primary device's context and makes its device current for the calling thread.  Internally a call may use one
+ *     worker thread per GPU (sdeb200_init_devices); sdeb200_last_error() is per calling thread.
  *   - there is no CPU fallback: without a CUDA device every compute call returns SDEB200_E_CUDA.
  */
 #ifndef SDEB200_H
@@ -83,11 +85,16 @@ typedef struct {
   double t0;           /* start time (argument t0 of sample/simulate) */
   double dt;           /* scheme.Δt (src/schemes/schemes.jl:5-7) */
   uint64_t seed;       /* Philox key — replaces Random.seed! on the process-global RNG */
-  uint32_t stream;     /* independent sub-stream selector (MLMC level pairs use stream + pair index) */
+  uint32_t stream;     /* independent sub-stream selector; multilevel runs need stream < 2^24 (SDEB200_LEVEL_STREAM) */
   uint32_t reserved2;
   int64_t path_offset; /* global index of this call's first path: shards of one logical run pass their offset
                           so results do not depend on how paths are spread over GPUs */
 } sdeb200_opts;
+
+/* Philox stream word of level pair i of a multilevel run on the caller's stream: pair 0 (a plain `sample`,
+ * multilevel.jl:56) is the stream itself, pair i >= 1 gets i in the top byte — a plain run on stream 1 no longer shares
+ * its noise with level 1. */
+#define SDEB200_LEVEL_STREAM(stream, i) ((uint32_t)(stream) + ((uint32_t)(i) << 24))
 
 typedef struct {
   int32_t kind, comp;
@@ -99,6 +106,13 @@ int sdeb200_version(void);
 const char *sdeb200_last_error(void);
 int sdeb200_device_count(int *n);
 int sdeb200_init(int device);              /* bind this process to one GPU (one process per GPU) */
+/* One process, several GPUs: bind devices 0 .. n-1 (ndev_requested <= 0: all).  Afterwards every driver
+ * whose data pointers are HOST memory (or NULL) shards its paths over the devices — contiguous ranges on
+ * SDEB200_SHARD_ALIGN boundaries, one worker thread per device, the estimators' exact integer sums added on the host —
+ * and returns the same bits as on one GPU.  Calls on DEVICE pointers run on device 0.  Not combinable with
+ * sdeb200_comm_init.  *ndev_out = number of devices bound. */
+int sdeb200_init_devices(int ndev_requested, int *ndev_out);
+int sdeb200_device_info(int *ndev, int *primary);
 int sdeb200_shutdown(void);
 int sdeb200_set_stream(void *cuda_stream); /* run on a caller-owned cudaStream_t (NULL: internal stream) */
 int sdeb200_synchronize(void);
@@ -202,6 +216,16 @@ int sdeb200_mlmc_estimate_level(sdeb200_model *m, const sdeb200_opts *o, const d
 int sdeb200_mlmc_estimate(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
                           int64_t substeps, int64_t level_first, int nlevels, int64_t nsteps,
                           const int64_t *npaths, const sdeb200_payoff *payoff, double *result);
+
+/* ---- library-owned device buffers: results that stay on the GPU for callers without a device array type ---- */
+/* shape[ndim] in C order (last extent contiguous); pass sdeb200_buffer_ptr(b) wherever a driver takes a data pointer. */
+typedef struct sdeb200_buffer sdeb200_buffer;
+int sdeb200_buffer_alloc(int precision, int ndim, const int64_t *shape, sdeb200_buffer **out);
+void *sdeb200_buffer_ptr(const sdeb200_buffer *b);
+int sdeb200_buffer_info(const sdeb200_buffer *b, int *precision, int *ndim, int64_t *shape, int64_t *strides_bytes);
+int sdeb200_buffer_copy_to_host(const sdeb200_buffer *b, int64_t offset_elems, int64_t count_elems, void *host);
+int sdeb200_buffer_copy_from_host(sdeb200_buffer *b, int64_t offset_elems, int64_t count_elems, const void *host);
+int sdeb200_buffer_free(sdeb200_buffer *b);
 
 /* ---- multi-GPU: one process per GPU, one NCCL communicator ---- */
 int sdeb200_comm_unique_id(void *id128);                          /* rank 0: ncclGetUniqueId (128 bytes) */

@@ -7,10 +7,10 @@ include/sdeb200.h (csrc/).  Import as `sdemodels_jl_b200` via the repo-root load
 """
 from . import _lib
 from ._lib import DomainError, SDEB200Error
-from .distributed import comm_info, init as init_distributed, shard_range
+from .distributed import DeviceBuffer, comm_info, device_info, init as init_distributed, init_devices, shard_range
 from .models import (AbstractSDE, REGISTRY, diffusion, dim, drift, fieldnames, registry_model, sde_model,
                      variables)
-from .multilevel import (AdaptiveMLMC, MultilevelEstimate, MultilevelScheme, cost, ml_estimate, mlmc_adaptive,
+from .multilevel import (AdaptiveMLMC, MultilevelEstimate, MultilevelScheme, cost, level_stream, ml_estimate, mlmc_adaptive,
                          multilevel_sample_level, multilevel_simulate_level, npaths, schemes)
 from .schemes import EulerMaruyama, Exact, Milstein, RungeKutta, subdivide
 from .simulation import (Call, Component, Estimate, Moments, Put, estimate, logtransition, sample, sample_, simulate,

@@ -48,6 +48,8 @@ SYMBOLS = {
     "sdeb200_last_error": (C.c_char_p, []),
     "sdeb200_device_count": (_I, [C.POINTER(C.c_int)]),
     "sdeb200_init": (_I, [_I]),
+    "sdeb200_init_devices": (_I, [_I, C.POINTER(C.c_int)]),
+    "sdeb200_device_info": (_I, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdeb200_shutdown": (_I, []),
     "sdeb200_set_stream": (_I, [_VP]),
     "sdeb200_synchronize": (_I, []),
@@ -79,6 +81,12 @@ SYMBOLS = {
     "sdeb200_estimate": (_I, [_VP, _PO, _PD, _PD, _I64, _I64, _PP, _VP, _PD]),
     "sdeb200_mlmc_estimate_level": (_I, [_VP, _PO, _PD, _PD, _D, _I64, _I64, _I64, _PP, _PD]),
     "sdeb200_mlmc_estimate": (_I, [_VP, _PO, _PD, _PD, _I64, _I64, _I, _I64, C.POINTER(C.c_int64), _PP, _PD]),
+    "sdeb200_buffer_alloc": (_I, [_I, _I, C.POINTER(C.c_int64), C.POINTER(_VP)]),
+    "sdeb200_buffer_ptr": (_VP, [_VP]),
+    "sdeb200_buffer_info": (_I, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sdeb200_buffer_copy_to_host": (_I, [_VP, _I64, _I64, _VP]),
+    "sdeb200_buffer_copy_from_host": (_I, [_VP, _I64, _I64, _VP]),
+    "sdeb200_buffer_free": (_I, [_VP]),
     "sdeb200_comm_unique_id": (_I, [_VP]),
     "sdeb200_comm_init": (_I, [_VP, _I, _I]),
     "sdeb200_comm_destroy": (_I, []),

@@ -13,7 +13,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sdeb200.h"
@@ -32,8 +35,9 @@ extern "C" void sde_launch_subsample(int precision, const void *src, void *dst, 
                                      int64_t nrows_src, int64_t substeps, int dim, cudaStream_t st);
 extern "C" double sde_launch_peak(int precision, void *scratch, int blocks, int iters, cudaStream_t st);
 // sde_nvrtc.cpp
-int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precision, int math, sde_ktable *kt,
+int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int slot, int math, int family, sde_ktable *kt,
                       void **library_out, std::string *log);
+enum { FAM_TERMINAL = 0, FAM_TRAJ = 1, FAM_WIENER = 2, FAM_MISC = 3, FAM_COUNT = 4 };  // kernel families (sde_device.cuh)
 
 static_assert(SDEB200_NBINS == SDE_NBINS, "bins");
 static_assert(SDEB200_SHARD_ALIGN == SDE_SHARD_ALIGN, "align");
@@ -135,17 +139,91 @@ struct Ctx {
   cudaStream_t lvl[MAX_LEVELS] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, kdone[2] = {}, cdone[2] = {}, lvl_done[MAX_LEVELS] = {};
   DevBuf slab[2], win[2], partials[MAX_LEVELS], red, misc;
+  void *pin[2] = {nullptr, nullptr};   // pinned staging ring for pageable host outputs (run_slabs)
+  size_t pin_cap[2] = {0, 0};
+  std::vector<const void *> opted;     // kernels whose dynamic shared-memory limit was raised on THIS device
   double last_ms = 0.0;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0}, tma_launches{0};
   nccl_comm comm = nullptr;
   int nranks = 1, rank = 0;
   cudaStream_t stream() const { return use_ext ? ext : own; }
 };
-static Ctx g;
+// One context per device.  A call runs on the context of the calling thread: the primary device (sdeb200_init /
+// sdeb200_init_devices), or — inside a sharded call — the device a worker thread was bound to (run_sharded).
+static const int MAX_DEV = 16;
+static Ctx g_ctx[MAX_DEV];
+static int g_primary = 0;              // device of single-device calls
+static int g_ndev = 1;                 // devices host-memory calls are spread over (sdeb200_init_devices)
+static thread_local Ctx *tl_ctx = &g_ctx[0];
+static thread_local bool tl_shard = false;                       // this thread is a worker of a sharded call
+static thread_local unsigned long long *tl_raw = nullptr;        // worker: where finish_reductions leaves the raw integer records
+static thread_local const int64_t *tl_level_off = nullptr;       // worker: per-level path offsets of a sharded multilevel call
+#define g (*tl_ctx)
+static std::mutex g_compile_mutex;     // NVRTC compilation / kernel-table updates of a model
 
+static int ctx_init(Ctx &c, int device) {
+  if (c.up) return 0;
+  CU(cudaSetDevice(device));
+  c.device = device;
+  CU(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c.ev0));
+  CU(cudaEventCreate(&c.ev1));
+  for (int i = 0; i < 2; i++) {
+    CU(cudaEventCreateWithFlags(&c.kdone[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c.cdone[i], cudaEventDisableTiming));
+  }
+  c.up = true;
+  return 0;
+}
+static void ctx_release(Ctx &c) {
+  if (!c.up) return;
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
+  c.comm = nullptr;
+  c.nranks = 1;
+  c.rank = 0;
+  for (int i = 0; i < 2; i++) {
+    c.slab[i].release();
+    c.win[i].release();
+    if (c.pin[i]) cudaFreeHost(c.pin[i]);
+    c.pin[i] = nullptr;
+    c.pin_cap[i] = 0;
+    if (c.kdone[i]) cudaEventDestroy(c.kdone[i]);
+    if (c.cdone[i]) cudaEventDestroy(c.cdone[i]);
+    c.kdone[i] = c.cdone[i] = nullptr;
+  }
+  for (int i = 0; i < MAX_LEVELS; i++) {
+    c.partials[i].release();
+    if (c.lvl[i]) cudaStreamDestroy(c.lvl[i]);
+    if (c.lvl_done[i]) cudaEventDestroy(c.lvl_done[i]);
+    c.lvl[i] = nullptr;
+    c.lvl_done[i] = nullptr;
+  }
+  c.red.release();
+  c.misc.release();
+  if (c.ev0) cudaEventDestroy(c.ev0);
+  if (c.ev1) cudaEventDestroy(c.ev1);
+  if (c.own) cudaStreamDestroy(c.own);
+  if (c.copy) cudaStreamDestroy(c.copy);
+  c.ev0 = c.ev1 = nullptr;
+  c.own = c.copy = nullptr;
+  c.use_ext = false;
+  c.opted.clear();
+  c.up = false;
+}
+
+// Every entry point starts here: select the calling thread's context (worker threads keep the one they were bound to)
+// and make its device current for this thread (the CUDA current device is per host thread).
 static int ensure_up() {
-  if (g.up) return 0;
-  return sdeb200_init(-1);
+  if (!tl_shard) tl_ctx = &g_ctx[g_primary];
+  if (!g.up) {
+    int rc = sdeb200_init(-1);
+    if (rc) return rc;
+  }
+  CU(cudaSetDevice(g.device));
+  return 0;
 }
 
 extern "C" int sdeb200_version(void) { return SDEB200_VERSION; }
@@ -163,56 +241,56 @@ extern "C" int sdeb200_init(int device) {
     return fail(SDEB200_E_CUDA, "no CUDA device (%s); sdeb200 has no CPU fallback",
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   if (device < 0) {
-    if (g.up) return SDEB200_OK;
+    if (g_ctx[g_primary].up) return SDEB200_OK;
     CU(cudaGetDevice(&device));
   }
-  if (device >= n) return fail(SDEB200_E_ARG, "device %d out of range (%d devices)", device, n);
-  if (g.up && g.device == device) return SDEB200_OK;
-  if (g.up) sdeb200_shutdown();
-  CU(cudaSetDevice(device));
-  g.device = device;
-  CU(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&g.ev0));
-  CU(cudaEventCreate(&g.ev1));
-  for (int i = 0; i < 2; i++) {
-    CU(cudaEventCreateWithFlags(&g.kdone[i], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&g.cdone[i], cudaEventDisableTiming));
+  if (device >= n || device >= MAX_DEV) return fail(SDEB200_E_ARG, "device %d out of range (%d devices)", device, n);
+  if (g_ctx[g_primary].up && g_primary != device && g_ndev == 1) ctx_release(g_ctx[g_primary]);   // re-bind: one GPU per process
+  g_primary = device;
+  g_ndev = 1;
+  tl_ctx = &g_ctx[device];
+  if (g_ctx[device].up && g_ctx[device].device != device) ctx_release(g_ctx[device]);   // left over from SDEB200_FAKE_DEVICES
+  return ctx_init(g_ctx[device], device);
+}
+// one host process owning several GPUs.  Binds devices 0 .. n-1 (ndev_requested <= 0: all); calls whose
+// data pointers are HOST memory (or null) are then sharded over them — contiguous path ranges on SDEB200_SHARD_ALIGN
+// boundaries, one worker thread per device, exact integer sums combined on the host — with results identical, bit for
+// bit, to a single-GPU run (the global path index is the Philox counter).  Calls on DEVICE pointers run on the primary
+// device (0).  Not to be mixed with sdeb200_comm_init (one process per GPU).
+extern "C" int sdeb200_init_devices(int ndev_requested, int *ndev_out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SDEB200_E_CUDA, "no CUDA device (%s); sdeb200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  int want = ndev_requested <= 0 ? n : std::min(ndev_requested, n);
+  // test hook: SDEB200_FAKE_DEVICES=k binds k logical devices round-robin onto the physical ones, so that the sharding,
+  // the worker threads and the host-side combination of the exact sums can be exercised on a single-GPU box
+  if (const char *fake = getenv("SDEB200_FAKE_DEVICES")) want = std::max(1, atoi(fake));
+  want = std::min(want, MAX_DEV);
+  if (g_ctx[g_primary].comm) return fail(SDEB200_E_ARG, "a NCCL communicator is up: one process per GPU and one process for all GPUs do not mix");
+  if (g_ndev == 1 && g_primary != 0) ctx_release(g_ctx[g_primary]);
+  for (int d = 0; d < want; d++) {
+    if (g_ctx[d].up && g_ctx[d].device != d % n) ctx_release(g_ctx[d]);
+    int rc = ctx_init(g_ctx[d], d % n);
+    if (rc) return rc;
   }
-  g.up = true;
+  for (int d = want; d < MAX_DEV; d++) ctx_release(g_ctx[d]);
+  g_primary = 0;
+  g_ndev = want;
+  tl_ctx = &g_ctx[0];
+  CU(cudaSetDevice(0));
+  if (ndev_out) *ndev_out = want;
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_device_info(int *ndev, int *primary) {
+  if (ndev) *ndev = g_ndev;
+  if (primary) *primary = g_primary;
   return SDEB200_OK;
 }
 extern "C" int sdeb200_shutdown(void) {
-  if (!g.up) return SDEB200_OK;
-  cudaDeviceSynchronize();
-  if (g.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g.comm);
-  g.comm = nullptr;
-  g.nranks = 1;
-  g.rank = 0;
-  for (int i = 0; i < 2; i++) {
-    g.slab[i].release();
-    g.win[i].release();
-    if (g.kdone[i]) cudaEventDestroy(g.kdone[i]);
-    if (g.cdone[i]) cudaEventDestroy(g.cdone[i]);
-    g.kdone[i] = g.cdone[i] = nullptr;
-  }
-  for (int i = 0; i < MAX_LEVELS; i++) {
-    g.partials[i].release();
-    if (g.lvl[i]) cudaStreamDestroy(g.lvl[i]);
-    if (g.lvl_done[i]) cudaEventDestroy(g.lvl_done[i]);
-    g.lvl[i] = nullptr;
-    g.lvl_done[i] = nullptr;
-  }
-  g.red.release();
-  g.misc.release();
-  if (g.ev0) cudaEventDestroy(g.ev0);
-  if (g.ev1) cudaEventDestroy(g.ev1);
-  if (g.own) cudaStreamDestroy(g.own);
-  if (g.copy) cudaStreamDestroy(g.copy);
-  g.ev0 = g.ev1 = nullptr;
-  g.own = g.copy = nullptr;
-  g.use_ext = false;
-  g.up = false;
+  for (int d = 0; d < MAX_DEV; d++) ctx_release(g_ctx[d]);
+  g_ndev = 1;
   return SDEB200_OK;
 }
 extern "C" int sdeb200_set_stream(void *s) {
@@ -228,8 +306,12 @@ extern "C" int sdeb200_synchronize(void) {
   CU(cudaStreamSynchronize(g.stream()));
   return SDEB200_OK;
 }
-extern "C" double sdeb200_last_kernel_ms(void) { return g.last_ms; }
-extern "C" int64_t sdeb200_launch_count(void) { return g.launches; }
+extern "C" double sdeb200_last_kernel_ms(void) { return g_ctx[g_primary].last_ms; }
+extern "C" int64_t sdeb200_launch_count(void) {
+  int64_t n = 0;
+  for (int d = 0; d < MAX_DEV; d++) n += g_ctx[d].launches.load();
+  return n;
+}
 
 extern "C" int sdeb200_measure_peak(int precision, double *tflops, double *ms_out) {
   int rc = ensure_up();
@@ -267,8 +349,9 @@ struct sdeb200_model {
   bool has_exact = false;
   std::vector<std::string> params, vars, drift, diffusion;  // diffusion row-major D x max(M,1)
   std::string source;                                       // generated functor (empty for built-ins)
+  std::string milstein_error;                               // why Milstein is unavailable (diffusion not differentiable symbolically)
   sde_ktable kt[2];                                         // [math]
-  bool have[2][2] = {{false, false}, {false, false}};       // [math][precision]
+  bool have[2][3][FAM_COUNT] = {};                          // [math][slot][family]: compiled (NVRTC, lazily) or built in
   std::vector<void *> libs;
 };
 
@@ -297,7 +380,8 @@ extern "C" int sdeb200_model_builtin(const char *name, sdeb200_model **out) {
   sde_aot_table_fast(m->builtin, &m->kt[0]);
   sde_aot_table_strict(m->builtin, &m->kt[1]);
   for (int a = 0; a < 2; a++)
-    for (int b = 0; b < 2; b++) m->have[a][b] = true;
+    for (int b = 0; b < 3; b++)
+      for (int f = 0; f < FAM_COUNT; f++) m->have[a][b][f] = true;
   *out = m;
   return SDEB200_OK;
 }
@@ -319,6 +403,7 @@ extern "C" int sdeb200_model_create(const char *name, const char *eqs, const cha
   m->D = dm.D; m->M = dm.M; m->kind = dm.kind;
   m->params = dm.params; m->vars = dm.vars; m->drift = dm.drift_str; m->diffusion = dm.diffusion_str;
   m->source = dm.cuda_source;
+  m->milstein_error = dm.milstein_error;
   memset(m->kt, 0, sizeof m->kt);
   *out = m;
   return SDEB200_OK;
@@ -355,18 +440,30 @@ extern "C" const char *sdeb200_model_diffusion_expr(const sdeb200_model *m, int 
 }
 extern "C" const char *sdeb200_model_cuda_source(const sdeb200_model *m) { return m ? m->source.c_str() : nullptr; }
 
-extern "C" int sdeb200_model_compile(sdeb200_model *m, int precision, int math) {
-  if (!m) return fail(SDEB200_E_ARG, "model is NULL");
-  if (precision < 0 || precision > 1 || math < 0 || math > 1) return fail(SDEB200_E_ARG, "bad precision/math");
-  if (m->have[math][precision]) return SDEB200_OK;
+// Compile one kernel family of a generated model for (math, slot) if that has not happened yet: NVRTC costs seconds, so
+// a model pays only for what it is used for ("lazily per (scheme, precision, kernel-kind)").
+static int ensure_family(sdeb200_model *m, int math, int slot, int family) {
+  if (m->have[math][slot][family]) return SDEB200_OK;
+  std::lock_guard<std::mutex> lock(g_compile_mutex);
+  if (m->have[math][slot][family]) return SDEB200_OK;
   int rc = ensure_up();
   if (rc) return rc;
   void *lib = nullptr;
   std::string log;
-  rc = sde_nvrtc_compile(m->source, m->D, m->M, precision, math, &m->kt[math], &lib, &log);
+  rc = sde_nvrtc_compile(m->source, m->D, m->M, slot, math, family, &m->kt[math], &lib, &log);
   if (rc) return fail(rc, "NVRTC/load of model '%s' failed:\n%s", m->name.c_str(), log.c_str());
   m->libs.push_back(lib);
-  m->have[math][precision] = true;
+  m->have[math][slot][family] = true;
+  return SDEB200_OK;
+}
+
+extern "C" int sdeb200_model_compile(sdeb200_model *m, int precision, int math) {
+  if (!m) return fail(SDEB200_E_ARG, "model is NULL");
+  if (precision < 0 || precision > 1 || math < 0 || math > 1) return fail(SDEB200_E_ARG, "bad precision/math");
+  for (int f = 0; f < FAM_COUNT; f++) {
+    int rc = ensure_family(m, math, precision == SDEB200_F32 ? 1 : 0, f);
+    if (rc) return rc;
+  }
   return SDEB200_OK;
 }
 
@@ -390,6 +487,10 @@ static int check_common(const sdeb200_model *m, const sdeb200_opts *o, const dou
                 "%s is defined for models with one Wiener process only (M == 1), as in the reference "
                 "(src/schemes/milstein.jl:4, runge_kutta.jl:4); '%s' has M == %d",
                 o->scheme == SDEB200_MILSTEIN ? "Milstein" : "RungeKutta", m->name.c_str(), m->M);
+  if (o->scheme == SDEB200_MILSTEIN && !m->milstein_error.empty())
+    return fail(SDEB200_E_UNSUPPORTED, "Milstein needs the derivative of the diffusion (src/schemes/milstein.jl:1-2) and the "
+                "front end %s in '%s'; use RungeKutta (derivative-free, runge_kutta.jl:4-11) or EulerMaruyama",
+                m->milstein_error.c_str(), m->name.c_str());
   if (o->precision < 0 || o->precision > 1 || o->math < 0 || o->math > 1) return fail(SDEB200_E_ARG, "bad precision/math");
   if (o->rng < 0 || o->rng > SDEB200_RNG_V2) return fail(SDEB200_E_ARG, "unknown normal stream version %d", o->rng);
   if (!(o->dt > 0.0) || !isfinite(o->dt)) return fail(SDEB200_E_ARG, "scheme Δt must be positive and finite");
@@ -441,10 +542,9 @@ static int launch(const void *k, int64_t grid, const sde_args *a, cudaStream_t s
   if (grid <= 0) return 0;
   if (grid > 2147483647LL) return fail(SDEB200_E_ARG, "too many paths for one launch");
   if (smem > 0) {  // static + dynamic shared memory above 48 KB needs an opt-in, once per kernel
-    static std::vector<const void *> opted;
-    if (std::find(opted.begin(), opted.end(), k) == opted.end()) {
+    if (std::find(g.opted.begin(), g.opted.end(), k) == g.opted.end()) {   // per device
       CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      opted.push_back(k);
+      g.opted.push_back(k);
     }
   }
   void *args[1] = {(void *)a};
@@ -468,13 +568,16 @@ static size_t simw_smem(int D, int M, int precision) {
 }
 static int64_t g_sample1_max = getenv("SDEB200_SAMPLE1_MAX") ? atoll(getenv("SDEB200_SAMPLE1_MAX")) : 262144;
 static bool g_tma_enabled = getenv("SDEB200_NO_TMA") == nullptr;
-static int64_t g_tma_launches = 0;
 extern "C" int sdeb200_set_tma(int enabled) {
   const int prev = g_tma_enabled ? 1 : 0;
   g_tma_enabled = enabled != 0;
   return prev;
 }
-extern "C" int64_t sdeb200_tma_launch_count(void) { return g_tma_launches; }
+extern "C" int64_t sdeb200_tma_launch_count(void) {
+  int64_t n = 0;
+  for (int d = 0; d < MAX_DEV; d++) n += g_ctx[d].tma_launches.load();
+  return n;
+}
 extern "C" int64_t sdeb200_set_sample1_max(int64_t npaths) {
   const int64_t prev = g_sample1_max;
   g_sample1_max = npaths;
@@ -503,14 +606,14 @@ static int tmap_encoder(tmap_encode_fn *out) {
 // Tensor map of a trajectory buffer in reference order [path][row][D]: g paths per map row (sde_args.h), boxes of
 // (32/g map rows) x (128 bytes), 128-byte shared-memory swizzle.  npaths must be a multiple of g.
 static_assert(sizeof(sde_tmap) == sizeof(CUtensorMap) && alignof(sde_tmap) == alignof(CUtensorMap), "sde_tmap mirrors CUtensorMap");
-static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, int64_t nrows, int64_t npaths, int g) {
+static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, int64_t nrows, int64_t npaths, int grp) {
   tmap_encode_fn enc = nullptr;
   int rc = tmap_encoder(&enc);
   if (rc) return rc;
   const size_t es = precision == SDEB200_F64 ? 8 : 4;
-  const cuuint64_t dims[2] = {(cuuint64_t)g * nrows * D, (cuuint64_t)(npaths / g)};
-  const cuuint64_t strides[1] = {(cuuint64_t)g * nrows * D * es};
-  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)(32 / g)};
+  const cuuint64_t dims[2] = {(cuuint64_t)grp * nrows * D, (cuuint64_t)(npaths / grp)};
+  const cuuint64_t strides[1] = {(cuuint64_t)grp * nrows * D * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)(32 / grp)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc((CUtensorMap *)tm, precision == SDEB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -537,15 +640,15 @@ static int launch_simref(const void *k, const void *k_tma, int D, int precision,
   // 16-byte rows (-3 %): route by row size
   if (k_tma && g_tma_enabled && rowb == 8 && ((uintptr_t)out % 16) == 0 && nrows >= 2 * (128 / rowb) + 4 &&
       nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
-    const int g = sde_tma_group(nrows * rowb);
-    const int64_t ncov = npaths - npaths % g;
+    const int grp = sde_tma_group(nrows * rowb);
+    const int64_t ncov = npaths - npaths % grp;
     if (ncov >= 32) {
       sde_args b = a;
       b.npaths = ncov;
       b.out = out;
-      if ((rc = make_traj_tmap(&b.tm_x, out, precision, D, nrows, ncov, g))) return rc;
+      if ((rc = make_traj_tmap(&b.tm_x, out, precision, D, nrows, ncov, grp))) return rc;
       if ((rc = launch(k_tma, (ncov + SDE_BLOCK - 1) / SDE_BLOCK, &b, st, simrt_smem()))) return rc;
-      g_tma_launches++;
+      g.tma_launches++;
       done = ncov;
     }
   }
@@ -572,15 +675,107 @@ static bool is_device_ptr(const void *p) {
 static inline size_t esize(int precision) { return precision == SDEB200_F64 ? 8 : 4; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-static int get_ktable(sdeb200_model *m, const sdeb200_opts *o, const sde_ktable **kt) {
-  int rc = sdeb200_model_compile(m, o->precision, o->math);
+static int get_ktable(sdeb200_model *m, const sdeb200_opts *o, const sde_ktable **kt, int family) {
+  int rc = ensure_family(m, o->math, kslot(o), family);
   if (rc) return rc;
   *kt = &m->kt[o->math];
   return 0;
 }
 
-// Generic slab pipeline for path-major outputs: kernel(slab i) on the compute stream overlaps the
-// device->host copy of slab i-1 on the copy stream.  bytes_per_path of contiguous host memory per path.
+// ---------------------------------------------------------------------------------------------------
+// one process, several GPUs: shard a call over the bound devices
+// ---------------------------------------------------------------------------------------------------
+static bool is_host_or_null(const void *p) { return p == nullptr || !is_device_ptr(p); }
+static bool sharded_call(int64_t npaths) { return g_ndev > 1 && !tl_shard && npaths >= 2 * SDE_SHARD_ALIGN; }
+
+// Contiguous path range of device d: boundaries on multiples of SDE_SHARD_ALIGN (the chunking of the payoff reduction,
+// and with it every rounding, is then independent of the number of devices) — the same split distributed.shard_range
+// applies across processes.
+static void shard_range(int64_t npaths, int d, int nd, int64_t *lo, int64_t *hi) {
+  const int64_t units = cdiv(npaths, SDE_SHARD_ALIGN);
+  *lo = std::min<int64_t>(npaths, units * d / nd * SDE_SHARD_ALIGN);
+  *hi = std::min<int64_t>(npaths, units * (d + 1) / nd * SDE_SHARD_ALIGN);
+}
+
+// fn(d, lo, n) runs on a worker thread bound to device d (its own context, streams and scratch buffers) for the paths
+// [lo, lo + n); all devices run concurrently.  Errors: the first hard error wins; SDEB200_E_DOMAIN (outputs written, some
+// paths non-finite) is reported after everything else succeeded, like the single-device call does.
+template <class Fn> static int run_devices(Fn &&fn) {   // fn(d) on a worker thread bound to device d, all devices at once
+  const int nd = g_ndev;
+  std::vector<int> rcs(nd, 0);
+  std::vector<std::string> errs(nd);
+  std::vector<double> ms(nd, 0.0);
+  std::vector<std::thread> th;
+  for (int d = 0; d < nd; d++) {
+    th.emplace_back([&, d]() {
+      tl_ctx = &g_ctx[d];
+      tl_shard = true;
+      cudaSetDevice(g_ctx[d].device);
+      g_ctx[d].last_ms = 0.0;
+      rcs[d] = fn(d);
+      if (rcs[d]) errs[d] = g_err;
+      ms[d] = g_ctx[d].last_ms;
+    });
+  }
+  for (auto &t : th) t.join();
+  cudaSetDevice(g_ctx[g_primary].device);
+  g_ctx[g_primary].last_ms = *std::max_element(ms.begin(), ms.end());
+  int domain = -1;
+  for (int d = 0; d < nd; d++) {
+    if (rcs[d] == SDEB200_E_DOMAIN) { if (domain < 0) domain = d; continue; }
+    if (rcs[d]) return fail(rcs[d], "device %d: %s", d, errs[d].c_str());
+  }
+  if (domain >= 0) return fail(SDEB200_E_DOMAIN, "%s", errs[domain].c_str());
+  return 0;
+}
+template <class Fn> static int run_sharded(int64_t npaths, Fn &&fn) {
+  const int nd = g_ndev;
+  return run_devices([&](int d) -> int {
+    int64_t lo, hi;
+    shard_range(npaths, d, nd, &lo, &hi);
+    return hi > lo ? fn(d, lo, hi - lo) : 0;
+  });
+}
+
+// memcpy with a few threads: a single core moves ~10 GB/s, less than one PCIe 5 link delivers
+static void par_memcpy(void *dst, const void *src, size_t n) {
+  const size_t MINB = (size_t)8 << 20;
+  const int nt = (int)std::min<size_t>(4, n / MINB);
+  if (nt <= 1) { memcpy(dst, src, n); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n / nt + 63) & ~(size_t)63;
+  for (int i = 0; i < nt; i++) {
+    const size_t o = (size_t)i * per, len = i == nt - 1 ? n - o : per;
+    if (o >= n) break;
+    th.emplace_back([=]() { memcpy((char *)dst + o, (const char *)src + o, len); });
+  }
+  for (auto &t : th) t.join();
+}
+
+static bool is_pinned_host(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+static int ensure_pin(int b, size_t bytes) {
+  if (bytes <= g.pin_cap[b]) return 0;
+  if (g.pin[b]) cudaFreeHost(g.pin[b]);
+  g.pin[b] = nullptr;
+  g.pin_cap[b] = 0;
+  cudaError_t e = cudaHostAlloc(&g.pin[b], bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(SDEB200_E_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+  g.pin_cap[b] = bytes;
+  return 0;
+}
+
+// Generic slab pipeline for path-major outputs: kernel(slab i) on the compute stream overlaps the device->host copy of
+// slab i-1 on the copy stream.  bytes_per_path of contiguous host memory per path.  PINNED host memory (CUDA-allocated or
+// registered) is the copy's destination itself.  PAGEABLE memory — what a Julia `Array` or a numpy array is — would make
+// cudaMemcpyAsync a staged, host-blocking copy and lose the overlap, so the copy goes into the library's own pinned ring
+// and the host moves slab i-2 from the ring into the caller's array (par_memcpy) while the GPU computes slab i-1.
 template <class LaunchFn>
 static int run_slabs(int64_t npaths, size_t bytes_per_path, void *host_out, LaunchFn &&fn) {
   cudaStream_t st = g.stream();
@@ -588,25 +783,38 @@ static int run_slabs(int64_t npaths, size_t bytes_per_path, void *host_out, Laun
   slab = std::max<int64_t>(SDE_SHARD_ALIGN, slab / SDE_SHARD_ALIGN * SDE_SHARD_ALIGN);
   slab = std::min<int64_t>(slab, cdiv(npaths, SDE_SHARD_ALIGN) * SDE_SHARD_ALIGN);
   const int nb = npaths > slab ? 2 : 1;
+  const bool staged = !is_pinned_host(host_out);
   for (int b = 0; b < nb; b++) {
     int rc = g.slab[b].ensure((size_t)slab * bytes_per_path);
     if (rc) return rc;
+    if (staged && (rc = ensure_pin(b, (size_t)slab * bytes_per_path))) return rc;
   }
   bool used[2] = {false, false};
+  int64_t first[2] = {0, 0}, count[2] = {0, 0};
+  auto drain = [&](int b) -> int {   // the copy engine released buffer b; staged: hand its slab over to the caller's array
+    CU(cudaEventSynchronize(g.cdone[b]));
+    if (staged) par_memcpy((char *)host_out + (size_t)first[b] * bytes_per_path, g.pin[b], (size_t)count[b] * bytes_per_path);
+    used[b] = false;
+    return 0;
+  };
   int b = 0;
   for (int64_t s0 = 0; s0 < npaths; s0 += slab, b ^= 1) {
     const int64_t n = std::min<int64_t>(slab, npaths - s0);
-    if (used[b]) {
-      CU(cudaEventSynchronize(g.cdone[b]));      // host: the copy engine released this buffer
-    }
-    int rc = fn(s0, n, g.slab[b].p, st);
-    if (rc) return rc;
+    int rc;
+    if (used[b] && (rc = drain(b))) return rc;
+    if ((rc = fn(s0, n, g.slab[b].p, st))) return rc;
     CU(cudaEventRecord(g.kdone[b], st));
     CU(cudaStreamWaitEvent(g.copy, g.kdone[b], 0));
-    CU(cudaMemcpyAsync((char *)host_out + (size_t)s0 * bytes_per_path, g.slab[b].p, (size_t)n * bytes_per_path,
-                       cudaMemcpyDeviceToHost, g.copy));
+    void *dst = staged ? g.pin[b] : (void *)((char *)host_out + (size_t)s0 * bytes_per_path);
+    CU(cudaMemcpyAsync(dst, g.slab[b].p, (size_t)n * bytes_per_path, cudaMemcpyDeviceToHost, g.copy));
     CU(cudaEventRecord(g.cdone[b], g.copy));
     used[b] = true;
+    first[b] = s0;
+    count[b] = n;
+  }
+  for (int k = 0; k < 2; k++, b ^= 1) {   // oldest first
+    int rc;
+    if (used[b] && (rc = drain(b))) return rc;
   }
   CU(cudaStreamSynchronize(g.copy));
   return 0;
@@ -647,7 +855,7 @@ extern "C" int sdeb200_model_coefficients(sdeb200_model *m, const double *params
   o.t0 = t;
   o.math = SDEB200_MATH_STRICT;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, &o, &kt))) return rc;
+  if ((rc = get_ktable(m, &o, &kt, FAM_MISC))) return rc;
   const int MW = m->M > 0 ? m->M : 1, nout = m->D + m->D * MW;
   if ((rc = g.misc.ensure(256 * 8))) return rc;
   sde_args a;
@@ -696,8 +904,15 @@ extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const dou
   if (nsteps < 0 || npaths < 0 || (!out && npaths > 0)) return fail(SDEB200_E_ARG, "bad nsteps/npaths/out");
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = get_ktable(m, o, &kt, FAM_TERMINAL))) return rc;
   if (npaths == 0) return SDEB200_OK;
+  const size_t bpp = (size_t)m->D * esize(o->precision);
+  if (sharded_call(npaths) && is_host_or_null(out))   // one process, several GPUs: contiguous shards, one worker per device
+    return run_sharded(npaths, [&](int, int64_t lo, int64_t n) {
+      sdeb200_opts os = *o;
+      os.path_offset += lo;
+      return sdeb200_sample(m, &os, params, x0, nsteps, n, (char *)out + (size_t)lo * bpp);
+    });
   if ((rc = g.red.ensure(RED_WORDS * 8))) return rc;
   cudaStream_t st = g.stream();
   unsigned long long *d_bad = (unsigned long long *)g.red.p;
@@ -706,7 +921,6 @@ extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const dou
   fill_args(&a, m, o, params, x0);
   a.nsteps = nsteps;
   a.nonfinite = d_bad;
-  const size_t bpp = (size_t)m->D * esize(o->precision);
   if ((rc = timed_begin())) return rc;
   if (is_device_ptr(out)) {
     a.npaths = npaths;
@@ -742,14 +956,24 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
   if (layout != SDEB200_LAYOUT_REFERENCE && layout != SDEB200_LAYOUT_SOA) return fail(SDEB200_E_ARG, "bad layout");
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = get_ktable(m, o, &kt, FAM_TRAJ))) return rc;
   if (npaths == 0) return SDEB200_OK;
-  cudaStream_t st = g.stream();
   const size_t es = esize(o->precision);
   const int64_t nrows = nsteps + 1;
+  if (layout == SDEB200_LAYOUT_REFERENCE && sharded_call(npaths) && is_host_or_null(out))
+    return run_sharded(npaths, [&](int, int64_t lo, int64_t n) {
+      sdeb200_opts os = *o;
+      os.path_offset += lo;
+      return sdeb200_simulate(m, &os, params, x0, nsteps, n, layout, (char *)out + (size_t)lo * nrows * m->D * es);
+    });
+  cudaStream_t st = g.stream();
+  if ((rc = g.red.ensure(RED_WORDS * 8))) return rc;
+  unsigned long long *d_bad = (unsigned long long *)g.red.p;
+  CU(cudaMemsetAsync(d_bad, 0, 8, st));
   sde_args a;
   fill_args(&a, m, o, params, x0);
   a.nsteps = nsteps;
+  a.nonfinite = d_bad;
   const bool dev = is_device_ptr(out);
   if ((rc = timed_begin())) return rc;
   if (layout == SDEB200_LAYOUT_REFERENCE) {
@@ -797,6 +1021,11 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
     }
   }
   if ((rc = timed_end())) return rc;
+  unsigned long long bad = 0;
+  if ((rc = read_nonfinite(d_bad, &bad))) return rc;
+  if (bad)
+    return fail(SDEB200_E_DOMAIN, "%llu of %lld trajectories ended non-finite (the reference raises DomainError, e.g. sqrt "
+                "of a negative variance); the trajectories are written", bad, (long long)npaths);
   return SDEB200_OK;
 }
 
@@ -816,16 +1045,16 @@ static int launch_simw(const sde_ktable *kt, const sdeb200_model *m, const sdeb2
   int64_t done = 0;
   if (kt_tma && g_tma_enabled && D == MW && 128 % rowb == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)x % 16) == 0 &&
       nrows >= 2 * (128 / rowb) + 4 && nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
-    const int g = sde_tma_group((int64_t)nrows * rowb);
-    const int64_t ncov = npaths - npaths % g;
+    const int grp = sde_tma_group((int64_t)nrows * rowb);
+    const int64_t ncov = npaths - npaths % grp;
     if (ncov >= 32) {
       a.npaths = ncov;
       a.out = x;
       a.out2 = (void *)w;
-      if ((rc = make_traj_tmap(&a.tm_w, w, o->precision, D, nrows, ncov, g))) return rc;
-      if ((rc = make_traj_tmap(&a.tm_x, x, o->precision, D, nrows, ncov, g))) return rc;
+      if ((rc = make_traj_tmap(&a.tm_w, w, o->precision, D, nrows, ncov, grp))) return rc;
+      if ((rc = make_traj_tmap(&a.tm_x, x, o->precision, D, nrows, ncov, grp))) return rc;
       if ((rc = launch(kt_tma, cdiv(ncov, SDE_BLOCK), &a, st, simwt_smem()))) return rc;
-      g_tma_launches++;
+      g.tma_launches++;
       done = ncov;
     }
   }
@@ -848,13 +1077,22 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
     return fail(SDEB200_E_ARG, "x === w needs eltype(x) == eltype(w), i.e. D == M (D=%d, M=%d)", m->D, m->M);
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = get_ktable(m, o, &kt, FAM_WIENER))) return rc;
   if (npaths == 0) return SDEB200_OK;
-  cudaStream_t st = g.stream();
   const size_t es = esize(o->precision);
+  if (sharded_call(npaths) && is_host_or_null(w) && is_host_or_null(x))
+    return run_sharded(npaths, [&](int, int64_t lo, int64_t n) {
+      return sdeb200_simulate_wiener(m, o, params, x0, nrows, n, (const char *)w + (size_t)lo * nrows * MW * es,
+                                     (char *)x + (size_t)lo * nrows * m->D * es);
+    });
+  cudaStream_t st = g.stream();
+  if ((rc = g.red.ensure(RED_WORDS * 8))) return rc;
+  unsigned long long *d_bad = (unsigned long long *)g.red.p;
+  CU(cudaMemsetAsync(d_bad, 0, 8, st));
   sde_args a;
   fill_args(&a, m, o, params, x0);
   a.nsteps = nrows - 1;
+  a.nonfinite = d_bad;
   const bool wdev = is_device_ptr(w), xdev = is_device_ptr(x);
   if ((rc = timed_begin())) return rc;
   if (wdev && xdev) {
@@ -889,6 +1127,11 @@ extern "C" int sdeb200_simulate_wiener(sdeb200_model *m, const sdeb200_opts *o, 
     CU(cudaStreamSynchronize(st));
   }
   if ((rc = timed_end())) return rc;
+  unsigned long long bad = 0;
+  if ((rc = read_nonfinite(d_bad, &bad))) return rc;
+  if (bad)
+    return fail(SDEB200_E_DOMAIN, "%llu of %lld trajectories ended non-finite (the reference raises DomainError, e.g. sqrt "
+                "of a negative variance); the trajectories are written", bad, (long long)npaths);
   return SDEB200_OK;
 }
 
@@ -914,12 +1157,16 @@ extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, co
   sdeb200_opts oc = *o;
   oc.math = SDEB200_MATH_FAST;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, &oc, &kt))) return rc;
+  if ((rc = get_ktable(m, &oc, &kt, FAM_MISC))) return rc;
   if (npaths == 0 || nrows == 1) return SDEB200_OK;
   const void *k = kt->logt[o->precision];
-  cudaStream_t st = g.stream();
   const size_t es = esize(o->precision);
   const size_t xb = (size_t)nrows * m->D * es, ob = (size_t)(nrows - 1) * es;
+  if (sharded_call(npaths) && is_host_or_null(x) && is_host_or_null(out))
+    return run_sharded(npaths, [&](int, int64_t lo, int64_t n) {
+      return sdeb200_logtransition(m, o, params, nrows, n, (const char *)x + (size_t)lo * xb, (char *)out + (size_t)lo * ob);
+    });
+  cudaStream_t st = g.stream();
   double x0[SDE_MAXD] = {0, 0, 0, 0};
   sde_args a;
   fill_args(&a, m, &oc, params, x0);
@@ -991,11 +1238,19 @@ extern "C" int sdeb200_wiener(const sdeb200_opts *o, int dim, int64_t nrows, int
   if (!o || (!w && npaths > 0)) return fail(SDEB200_E_ARG, "null argument");
   if (nrows < 1 || npaths < 0 || dim < 1 || dim > 4) return fail(SDEB200_E_ARG, "bad nrows/npaths/dim");
   if (!(o->dt > 0.0)) return fail(SDEB200_E_ARG, "Δt must be positive");
+  if (o->rng < 0 || o->rng > SDEB200_RNG_V2 || o->precision < 0 || o->precision > 1 || o->math < 0 || o->math > 1)
+    return fail(SDEB200_E_ARG, "bad precision / math / rng");
   int rc = ensure_up();
   if (rc) return rc;
   if (npaths == 0) return SDEB200_OK;
-  cudaStream_t st = g.stream();
   const size_t bpp = (size_t)nrows * dim * esize(o->precision);
+  if (sharded_call(npaths) && is_host_or_null(w))
+    return run_sharded(npaths, [&](int, int64_t lo, int64_t n) {
+      sdeb200_opts os = *o;
+      os.path_offset += lo;
+      return sdeb200_wiener(&os, dim, nrows, n, (char *)w + (size_t)lo * bpp);
+    });
+  cudaStream_t st = g.stream();
   if ((rc = timed_begin())) return rc;
   if (is_device_ptr(w)) {
     if ((rc = wiener_device(o, dim, nrows, npaths, o->path_offset, w, st))) return rc;
@@ -1107,6 +1362,26 @@ static int check_payoff(const sdeb200_model *m, const sdeb200_payoff *p) {
 }
 
 // finish nrec reduction records: (allreduce) -> host -> doubles.  nq[i] quantities per record.
+// raw integer records -> doubles: res[0..nq) = the exactly accumulated sums rounded once, then n and n_nonfinite
+static int round_records(int nrec, const int *nq, const unsigned long long *host, double *result, int result_stride,
+                         unsigned long long *bad_total) {
+  *bad_total = 0;
+  for (int i = 0; i < nrec; i++) {
+    const unsigned long long *h = host + (size_t)i * RED_WORDS;
+    const unsigned long long *ex = h + 2 * SDE_MAXF * SDE_NBINS;
+    double *res = result + (size_t)i * result_stride;
+    for (int q = 0; q < nq[i]; q++) res[q] = sdeb200_bins_to_double((const int64_t *)h + q * SDE_NBINS);
+    res[nq[i]] = (double)ex[0];
+    res[nq[i] + 1] = (double)ex[1];
+    *bad_total += ex[1];
+    if (ex[2]) return fail(SDEB200_E_DOMAIN, "a partial payoff sum overflowed to inf/nan");
+  }
+  return 0;
+}
+
+// finish nrec reduction records: (allreduce) -> host -> doubles.  nq[i] quantities per record.  A worker of a sharded
+// call (tl_raw) also leaves the raw integer records for the parent, which adds the devices' records (integer addition:
+// exact, order-free) and rounds once — the same bits as one GPU.
 static int finish_reductions(int nrec, const int *nq, cudaStream_t *streams, double *result, int result_stride,
                              unsigned long long *bad_total) {
   std::vector<unsigned long long> host((size_t)nrec * RED_WORDS);
@@ -1123,18 +1398,14 @@ static int finish_reductions(int nrec, const int *nq, cudaStream_t *streams, dou
                        cudaMemcpyDeviceToHost, streams[i]));
   }
   for (int i = 0; i < nrec; i++) CU(cudaStreamSynchronize(streams[i]));
-  *bad_total = 0;
-  for (int i = 0; i < nrec; i++) {
-    const unsigned long long *h = host.data() + (size_t)i * RED_WORDS;
-    const unsigned long long *ex = h + 2 * SDE_MAXF * SDE_NBINS;
-    double *res = result + (size_t)i * result_stride;
-    for (int q = 0; q < nq[i]; q++) res[q] = sdeb200_bins_to_double((const int64_t *)h + q * SDE_NBINS);
-    res[nq[i]] = (double)ex[0];
-    res[nq[i] + 1] = (double)ex[1];
-    *bad_total += ex[1];
-    if (ex[2]) return fail(SDEB200_E_DOMAIN, "a partial payoff sum overflowed to inf/nan");
-  }
-  return 0;
+  if (tl_raw) memcpy(tl_raw, host.data(), host.size() * 8);
+  return round_records(nrec, nq, host.data(), result, result_stride, bad_total);
+}
+
+// parent of a sharded estimator: add the workers' raw records word by word
+static void add_records(std::vector<unsigned long long> &total, const std::vector<std::vector<unsigned long long>> &raw) {
+  for (const auto &r : raw)
+    for (size_t i = 0; i < total.size(); i++) total[i] += r[i];   // two's-complement wrap-around == int64 addition
 }
 
 extern "C" int sdeb200_estimate(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
@@ -1148,9 +1419,28 @@ extern "C" int sdeb200_estimate(sdeb200_model *m, const sdeb200_opts *o, const d
     return fail(SDEB200_E_ARG, "estimate: `terminal` must be device memory (use sdeb200_sample for host arrays)");
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
-  cudaStream_t st = g.stream();
+  if ((rc = get_ktable(m, o, &kt, FAM_TERMINAL))) return rc;
   const int nf = payoff_nf(m, payoff), nq = 2 * nf;
+  if (sharded_call(npaths) && !terminal) {
+    std::vector<std::vector<unsigned long long>> raw(g_ndev, std::vector<unsigned long long>(RED_WORDS, 0));
+    rc = run_sharded(npaths, [&](int d, int64_t lo, int64_t n) {
+      sdeb200_opts os = *o;
+      os.path_offset += lo;
+      double tmp[2 * SDE_MAXF + 2];
+      tl_raw = raw[d].data();
+      const int r = sdeb200_estimate(m, &os, params, x0, nsteps, n, payoff, nullptr, tmp);
+      tl_raw = nullptr;
+      return r;
+    });
+    if (rc && rc != SDEB200_E_DOMAIN) return rc;
+    std::vector<unsigned long long> total(RED_WORDS, 0);
+    add_records(total, raw);
+    unsigned long long bad = 0;
+    if ((rc = round_records(1, &nq, total.data(), result, nq + 2, &bad))) return rc;
+    if (bad) return fail(SDEB200_E_DOMAIN, "%llu paths ended non-finite; they are excluded from the sums", bad);
+    return SDEB200_OK;
+  }
+  cudaStream_t st = g.stream();
   const int64_t grid = sample_grid(npaths);
   if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
   if ((rc = g.partials[0].ensure((size_t)std::max<int64_t>(grid, 1) * 2 * SDE_MAXF * 8))) return rc;
@@ -1210,12 +1500,21 @@ extern "C" int sdeb200_mlmc_sample_level(sdeb200_model *m, const sdeb200_opts *o
   if (rc) return rc;
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = get_ktable(m, o, &kt, FAM_TERMINAL))) return rc;
   sde_args a;
   if ((rc = mlmc_args(&a, m, o, params, x0, dt_fine, substeps, ncoarse, npaths))) return rc;
   if (npaths == 0) return SDEB200_OK;
-  cudaStream_t st = g.stream();
   const size_t bytes = (size_t)npaths * m->D * esize(o->precision);
+  if (sharded_call(npaths) && is_host_or_null(xc) && is_host_or_null(xf)) {
+    const size_t bpp = (size_t)m->D * esize(o->precision);
+    return run_sharded(npaths, [&](int, int64_t lo, int64_t n) {
+      sdeb200_opts os = *o;
+      os.path_offset += lo;
+      return sdeb200_mlmc_sample_level(m, &os, params, x0, dt_fine, substeps, ncoarse, n, xc ? (char *)xc + lo * bpp : nullptr,
+                                       xf ? (char *)xf + lo * bpp : nullptr);
+    });
+  }
+  cudaStream_t st = g.stream();
   const bool cdev = xc && is_device_ptr(xc), fdev = xf && is_device_ptr(xf);
   if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
   unsigned long long *d_bad = (unsigned long long *)g.red.p;
@@ -1252,11 +1551,18 @@ extern "C" int sdeb200_mlmc_simulate_level(sdeb200_model *m, const sdeb200_opts 
   if (substeps < 1 || ncoarse < 0 || npaths < 0) return fail(SDEB200_E_ARG, "bad substeps/ncoarse/npaths");
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = get_ktable(m, o, &kt, FAM_WIENER))) return rc;
   if (npaths == 0) return SDEB200_OK;
-  cudaStream_t st = g.stream();
   const size_t es = esize(o->precision);
   const int64_t nf = ncoarse * substeps + 1, nc = ncoarse + 1;
+  if (sharded_call(npaths) && is_host_or_null(xc) && is_host_or_null(xf))
+    return run_sharded(npaths, [&](int, int64_t lo, int64_t n) {
+      sdeb200_opts os = *o;
+      os.path_offset += lo;
+      return sdeb200_mlmc_simulate_level(m, &os, params, x0, dt_fine, substeps, ncoarse, n, (char *)xc + (size_t)lo * nc * m->D * es,
+                                         (char *)xf + (size_t)lo * nf * m->D * es);
+    });
+  cudaStream_t st = g.stream();
   const size_t fb = (size_t)npaths * nf * m->D * es, cb = (size_t)npaths * nc * m->D * es;
   const bool fdev = is_device_ptr(xf), cdev = is_device_ptr(xc);
   void *dxf = xf, *dxc = xc;
@@ -1336,12 +1642,31 @@ extern "C" int sdeb200_mlmc_estimate_level(sdeb200_model *m, const sdeb200_opts 
   if (!result) return fail(SDEB200_E_ARG, "result is NULL");
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = get_ktable(m, o, &kt, FAM_TERMINAL))) return rc;
+  const int nq = 6;
+  if (sharded_call(npaths)) {
+    std::vector<std::vector<unsigned long long>> raw(g_ndev, std::vector<unsigned long long>(RED_WORDS, 0));
+    rc = run_sharded(npaths, [&](int d, int64_t lo, int64_t n) {
+      sdeb200_opts os = *o;
+      os.path_offset += lo;
+      double tmp[8];
+      tl_raw = raw[d].data();
+      const int r = sdeb200_mlmc_estimate_level(m, &os, params, x0, dt_fine, substeps, ncoarse, n, payoff, tmp);
+      tl_raw = nullptr;
+      return r;
+    });
+    if (rc && rc != SDEB200_E_DOMAIN) return rc;
+    std::vector<unsigned long long> total(RED_WORDS, 0);
+    add_records(total, raw);
+    unsigned long long bad = 0;
+    if ((rc = round_records(1, &nq, total.data(), result, 8, &bad))) return rc;
+    if (bad) return fail(SDEB200_E_DOMAIN, "%llu coupled paths ended non-finite; they are excluded from the sums", bad);
+    return SDEB200_OK;
+  }
   if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
   cudaStream_t st = g.stream();
   if ((rc = timed_begin())) return rc;
   if ((rc = queue_level(m, kt, o, params, x0, true, dt_fine, substeps, ncoarse, npaths, payoff, 0, st))) return rc;
-  const int nq = 6;
   unsigned long long bad = 0;
   if ((rc = finish_reductions(1, &nq, &st, result, 8, &bad))) return rc;
   if ((rc = timed_end())) return rc;
@@ -1364,21 +1689,65 @@ extern "C" int sdeb200_mlmc_estimate(sdeb200_model *m, const sdeb200_opts *o, co
   if (payoff->kind == SDEB200_PAYOFF_MOMENTS) return fail(SDEB200_E_ARG, "multilevel estimators need a scalar payoff");
   if (!npaths || !result || nlevels < 1 || nlevels > MAX_LEVELS || substeps < 1 || level_first < 0 || nsteps < 0)
     return fail(SDEB200_E_ARG, "bad level specification");
+  if (o->stream >= (1u << 24))
+    return fail(SDEB200_E_ARG, "multilevel runs keep the level index in the top 8 bits of the Philox stream word: stream must be < 2^24");
   if ((rc = ensure_up())) return rc;
   const sde_ktable *kt;
-  if ((rc = get_ktable(m, o, &kt))) return rc;
+  if ((rc = get_ktable(m, o, &kt, FAM_TERMINAL))) return rc;
+  int nq[MAX_LEVELS];
+  int64_t nmax = 0;
+  for (int i = 0; i < nlevels; i++) nmax = std::max(nmax, npaths[i]);
+  if (sharded_call(nmax)) {
+    // every level is sharded over all devices: worker d runs its slice of every level concurrently
+    for (int i = 0; i < nlevels; i++) nq[i] = i == 0 ? 2 : 6;
+    const int nd = g_ndev;
+    std::vector<std::vector<unsigned long long>> raw(nd, std::vector<unsigned long long>((size_t)nlevels * RED_WORDS, 0));
+    rc = run_devices([&](int d) -> int {
+      int64_t n_d[MAX_LEVELS], off_d[MAX_LEVELS], any = 0;
+      for (int i = 0; i < nlevels; i++) {
+        int64_t lo, hi;
+        shard_range(npaths[i], d, nd, &lo, &hi);
+        n_d[i] = hi - lo;
+        off_d[i] = lo;
+        any += n_d[i];
+      }
+      if (!any) return 0;
+      std::vector<double> tmp((size_t)nlevels * 8);
+      tl_raw = raw[d].data();
+      tl_level_off = off_d;
+      const int r = sdeb200_mlmc_estimate(m, o, params, x0, substeps, level_first, nlevels, nsteps, n_d, payoff, tmp.data());
+      tl_raw = nullptr;
+      tl_level_off = nullptr;
+      return r;
+    });
+    if (rc && rc != SDEB200_E_DOMAIN) return rc;
+    std::vector<unsigned long long> total((size_t)nlevels * RED_WORDS, 0);
+    add_records(total, raw);
+    std::vector<double> tmp((size_t)nlevels * 8, 0.0);
+    unsigned long long bad = 0;
+    if ((rc = round_records(nlevels, nq, total.data(), tmp.data(), 8, &bad))) return rc;
+    for (int i = 0; i < nlevels; i++) {
+      double *res = result + (size_t)i * 8, *t = tmp.data() + (size_t)i * 8;
+      if (nq[i] == 2) { res[0] = t[0]; res[1] = t[1]; res[2] = t[0]; res[3] = t[1]; res[4] = 0.0; res[5] = 0.0; res[6] = t[2]; res[7] = t[3]; }
+      else for (int q = 0; q < 8; q++) res[q] = t[q];
+    }
+    if (bad) return fail(SDEB200_E_DOMAIN, "%llu paths ended non-finite; they are excluded from the sums", bad);
+    return SDEB200_OK;
+  }
   if ((rc = g.red.ensure((size_t)RED_WORDS * 8 * MAX_LEVELS))) return rc;
   if ((rc = ensure_level_streams(nlevels))) return rc;
   cudaStream_t st = g.stream();
   if ((rc = timed_begin())) return rc;
-  int nq[MAX_LEVELS];
   cudaStream_t streams[MAX_LEVELS];
   // finest (longest) levels first so the short ones fill the machine's tail
   for (int i = nlevels - 1; i >= 0; i--) {
     streams[i] = g.lvl[i];
     CU(cudaStreamWaitEvent(streams[i], g.ev0, 0));
     sdeb200_opts ol = *o;
-    ol.stream = o->stream + (uint32_t)i;  // fresh, independent noise per level pair (multilevel.jl:58-60)
+    // fresh, independent noise per level pair (multilevel.jl:58-60): the pair index lives in the top byte of the Philox
+    // stream word, away from the streams a caller uses for plain runs (pair 0 IS a plain `sample` on the caller's stream)
+    ol.stream = SDEB200_LEVEL_STREAM(o->stream, i);
+    if (tl_level_off) ol.path_offset = o->path_offset + tl_level_off[i];   // worker of a sharded call
     const int64_t li = level_first + i;
     if (i == 0) {
       // x[1] = sample(model, ml_schemes[1], t0, x0, nsteps*ml_steps[1], npaths[1])   (multilevel.jl:56)
@@ -1414,6 +1783,83 @@ extern "C" int sdeb200_mlmc_estimate(sdeb200_model *m, const sdeb200_opts *o, co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// library-owned device buffers (hard part 4): a caller without a GPU array type of its own — plain Julia
+// without CUDA.jl — keeps large results (C3: 41 GB of trajectories) on the device, passes sdeb200_buffer_ptr(b) wherever
+// the drivers take a data pointer, and reads back the slices it needs.
+// ---------------------------------------------------------------------------------------------------
+struct sdeb200_buffer {
+  void *p = nullptr;
+  int device = 0, precision = 0, ndim = 0;
+  int64_t shape[4] = {0, 0, 0, 0};
+  size_t bytes = 0;
+};
+extern "C" int sdeb200_buffer_alloc(int precision, int ndim, const int64_t *shape, sdeb200_buffer **out) {
+  if (!out || !shape || ndim < 1 || ndim > 4 || precision < 0 || precision > 1) return fail(SDEB200_E_ARG, "bad buffer description");
+  int rc = ensure_up();
+  if (rc) return rc;
+  sdeb200_buffer *b = new sdeb200_buffer();
+  size_t n = 1;
+  for (int i = 0; i < ndim; i++) {
+    if (shape[i] < 0) { delete b; return fail(SDEB200_E_ARG, "negative extent"); }
+    b->shape[i] = shape[i];
+    n *= (size_t)shape[i];
+  }
+  b->precision = precision;
+  b->ndim = ndim;
+  b->device = g.device;
+  b->bytes = n * esize(precision);
+  cudaError_t e = cudaMalloc(&b->p, std::max<size_t>(b->bytes, 16));
+  if (e != cudaSuccess) { delete b; return fail(SDEB200_E_CUDA, "cudaMalloc(%zu): %s", n * esize(precision), cudaGetErrorString(e)); }
+  *out = b;
+  return SDEB200_OK;
+}
+extern "C" void *sdeb200_buffer_ptr(const sdeb200_buffer *b) { return b ? b->p : nullptr; }
+extern "C" int sdeb200_buffer_info(const sdeb200_buffer *b, int *precision, int *ndim, int64_t *shape, int64_t *strides_bytes) {
+  if (!b) return fail(SDEB200_E_ARG, "buffer is NULL");
+  if (precision) *precision = b->precision;
+  if (ndim) *ndim = b->ndim;
+  int64_t st = (int64_t)esize(b->precision);
+  for (int i = b->ndim - 1; i >= 0; i--) {   // C order: the last extent is contiguous (Julia reads the shape reversed)
+    if (shape) shape[i] = b->shape[i];
+    if (strides_bytes) strides_bytes[i] = st;
+    st *= b->shape[i];
+  }
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_buffer_copy_to_host(const sdeb200_buffer *b, int64_t offset_elems, int64_t count_elems, void *host) {
+  if (!b || !host || offset_elems < 0 || count_elems < 0) return fail(SDEB200_E_ARG, "bad argument");
+  const size_t es = esize(b->precision);
+  if (((size_t)offset_elems + (size_t)count_elems) * es > b->bytes) return fail(SDEB200_E_ARG, "range exceeds the buffer");
+  int rc = ensure_up();
+  if (rc) return rc;
+  CU(cudaSetDevice(b->device));
+  CU(cudaMemcpy(host, (const char *)b->p + (size_t)offset_elems * es, (size_t)count_elems * es, cudaMemcpyDeviceToHost));
+  CU(cudaSetDevice(g.device));
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_buffer_copy_from_host(sdeb200_buffer *b, int64_t offset_elems, int64_t count_elems, const void *host) {
+  if (!b || !host || offset_elems < 0 || count_elems < 0) return fail(SDEB200_E_ARG, "bad argument");
+  const size_t es = esize(b->precision);
+  if (((size_t)offset_elems + (size_t)count_elems) * es > b->bytes) return fail(SDEB200_E_ARG, "range exceeds the buffer");
+  int rc = ensure_up();
+  if (rc) return rc;
+  CU(cudaSetDevice(b->device));
+  CU(cudaMemcpy((char *)b->p + (size_t)offset_elems * es, host, (size_t)count_elems * es, cudaMemcpyHostToDevice));
+  CU(cudaSetDevice(g.device));
+  return SDEB200_OK;
+}
+extern "C" int sdeb200_buffer_free(sdeb200_buffer *b) {
+  if (!b) return SDEB200_OK;
+  if (b->p) {
+    cudaSetDevice(b->device);
+    cudaFree(b->p);
+    if (g_ctx[g_primary].up) cudaSetDevice(g_ctx[g_primary].device);
+  }
+  delete b;
+  return SDEB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // communicator
 // ---------------------------------------------------------------------------------------------------
 extern "C" int sdeb200_comm_unique_id(void *id128) {
@@ -1430,6 +1876,7 @@ extern "C" int sdeb200_comm_init(const void *id128, int nranks, int rank) {
   int rc = ensure_up();
   if (rc) return rc;
   if ((rc = nccl_load())) return rc;
+  if (g_ndev > 1) return fail(SDEB200_E_ARG, "sdeb200_init_devices bound %d GPUs to this process: one process per GPU and one process for all GPUs do not mix", g_ndev);
   if (g.comm) sdeb200_comm_destroy();
   nccl_uid id;
   memcpy(id.b, id128, 128);

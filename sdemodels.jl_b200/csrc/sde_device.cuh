@@ -126,10 +126,10 @@ SDE_HD double sqrt_core(double v) { return sqrt_from_seed(v, rsqrt_seed(v)); }  
 // g = 0 * 2^1023 = 0 exactly); v < 0 gives a non-finite result (NaN or -inf) that propagates to the state and is
 // counted as a non-finite path — the reference throws DomainError there.  Subnormal v is flushed.
 #ifndef SDE_V2_IMAD
-#define SDE_V2_IMAD 0
+#define SDE_V2_IMAD 1
 #endif
 #ifndef SDE_V2_ROT1
-#define SDE_V2_ROT1 0
+#define SDE_V2_ROT1 1
 #endif
 #ifndef SDE_SQRT_FAST6
 #define SDE_SQRT_FAST6 1 /* six-operation form (sqrt_from_seed6, <= 1 ulp) instead of the seven-operation one */
@@ -709,6 +709,18 @@ template <typename T> SDE_D bool all_finite(const T *x, int D) {
   return ok;
 }
 
+// Trajectory kernels: count the paths whose FINAL state is non-finite (the reference raises DomainError from sqrt inside
+// simulate / simulate! as well); outputs are written regardless.
+SDE_D void count_nonfinite_n(const sde_args &a, unsigned bad) {
+  if (!a.nonfinite) return;
+  const unsigned mask = __activemask();
+  bad = __reduce_add_sync(mask, bad);
+  if ((int)(threadIdx.x & 31) == __ffs((int)mask) - 1 && bad) atomicAdd(a.nonfinite, (unsigned long long)bad);
+}
+template <typename T> SDE_D void count_nonfinite(const sde_args &a, bool live, const T *x, int D) {
+  count_nonfinite_n(a, (live && !all_finite(x, D)) ? 1u : 0u);
+}
+
 // payoff features of one terminal state
 SDE_D int payoff_features(const sde_args &a, int D, const double *x, double *f) {
   switch (a.payoff_kind) {
@@ -1164,6 +1176,10 @@ SDE_D void simulate_soa_body(const sde_args &a) {
       }
     }
   }
+  unsigned bad = 0;
+#pragma unroll
+  for (int v = 0; v < VEC; v++) bad += (v < nlive && !all_finite(x[v], D)) ? 1u : 0u;
+  count_nonfinite_n(a, bad);
 }
 
 // Cooperative copy between a warp's shared-memory tile [32 paths][LD] and global memory where path r's row
@@ -1294,6 +1310,10 @@ SDE_D void simulate_ref_body(const sde_args &a) {
     }
   }
   flush();
+  unsigned bad = 0;
+#pragma unroll
+  for (int p = 0; p < PW; p++) bad += (lane + 32 * p < nrow_live && !all_finite(x[p], D)) ? 1u : 0u;
+  count_nonfinite_n(a, bad);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1363,6 +1383,7 @@ SDE_D void simulate_wiener_body(const sde_args &a) {
     tile_store<T, XROW, XLD>(tx, xo + (wbase * nrows + row0) * D, nrows * D, nlive, nr * D, lane);
     __syncwarp();
   }
+  count_nonfinite(a, lane < nlive, x, D);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1575,6 +1596,8 @@ SDE_D void simulate_wiener_tma_body(const sde_args &a) {
     tail_tile_store<T, TROW, TLD>(tt, (T *)a.out + (wbase * nrows + T0) * D, (int64_t)nrows * D, nlive, ncols, h0 * D, h1 * D, h2 * D,
                                   h3 * D, g - 1, lane);
   }
+  __syncwarp();
+  count_nonfinite(a, live, x, D);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1762,6 +1785,8 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
   }
   for (; it < nbatch; it++) slow_batch(it);                                 // rows after the last full tile
   if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the stores' reads
+  __syncwarp();
+  count_nonfinite(a, live, x, D);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1924,45 +1949,44 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #define SDE_F64_MINB 1 /* the same switch for the FP64 coupled-level and [time][D][path] kernels (+0.6 % / +1.1 %) */
 #endif
 
-// Kernel entry points for one model type, scheme and precision.  TAG makes the symbols unique.  The
-// reference defines Milstein for M == 1 models only (milstein.jl:4): instantiate SCH = 1 only there.
-#define SDE_KERNELS(MODEL, TAG, SCH, SNAME, T, PNAME)                                                            \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_SAMPLE_MINB : SDE_SAMPLE_MINB_F32) \
-      sdek_##TAG##_sample_##SNAME##_##PNAME(                                                                     \
-      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT>(a); }                       \
+// Kernel entry points for one model type, scheme, arithmetic type T, normal-stream version V and symbol suffix SUF
+// (f64 | f32 | f64v2).  TAG makes the symbols unique.  They come in FAMILIES so that NVRTC can compile a generated model
+// lazily, one family per (precision, stream, math) on first use (sde_nvrtc.cpp): TERMINAL = sample / sample1 / mlmc,
+// TRAJ = the RNG-driven trajectory kernels, WIENER = the Wiener-driven ones (no noise: no stream version).
+// The reference defines Milstein for M == 1 models only (milstein.jl:4): instantiate SCH = 1, 2 only there.
+#define SDE_KERNELS_TERMINAL(MODEL, TAG, SCH, SNAME, T, V, SUF)                                                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? (V == 2 ? SDE_SAMPLE_MINB_V2 : SDE_SAMPLE_MINB) : SDE_SAMPLE_MINB_F32) \
+      sdek_##TAG##_sample_##SNAME##_##SUF(                                                                       \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT, V>(a); }               \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT, sizeof(T) == 8 ? SDE_SAMPLE1_MINB : 0)        \
-      sdek_##TAG##_sample1_##SNAME##_##PNAME(                                                                    \
-      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 1>(a); }                        \
+      sdek_##TAG##_sample1_##SNAME##_##SUF(                                                                      \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 1, V>(a); }                     \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_F64_MINB : 0)                      \
-      sdek_##TAG##_mlmc_##SNAME##_##PNAME(                                                                       \
-      const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, T, SCH>(a); }                            \
+      sdek_##TAG##_mlmc_##SNAME##_##SUF(                                                                         \
+      const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, T, SCH, V>(a); }
+#define SDE_KERNELS_TRAJ(MODEL, TAG, SCH, SNAME, T, V, SUF)                                                      \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? SDE_F64_MINB : 0)                      \
-      sdek_##TAG##_simsoa_##SNAME##_##PNAME(                                                                     \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH>(a); }                    \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_##SNAME##_##PNAME(                \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH>(a); }                    \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_##SNAME##_##PNAME(                \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, SCH>(a); }                \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMW_MINBLOCKS) sdek_##TAG##_simw_##SNAME##_##PNAME(                  \
+      sdek_##TAG##_simsoa_##SNAME##_##SUF(                                                                       \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, T, SCH, V>(a); }                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_##SNAME##_##SUF(    \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH, V>(a); }                  \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_##SNAME##_##SUF(      \
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, SCH, V>(a); }
+#define SDE_KERNELS_WIENER(MODEL, TAG, SCH, SNAME, T, SUF)                                                       \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMW_MINBLOCKS) sdek_##TAG##_simw_##SNAME##_##SUF(   \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }                  \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simwt_##SNAME##_##PNAME(                 \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simwt_##SNAME##_##SUF(                    \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_tma_body<MODEL, T, SCH>(a); }
 
+#define SDE_KERNELS(MODEL, TAG, SCH, SNAME, T, PNAME)        \
+  SDE_KERNELS_TERMINAL(MODEL, TAG, SCH, SNAME, T, 1, PNAME)  \
+  SDE_KERNELS_TRAJ(MODEL, TAG, SCH, SNAME, T, 1, PNAME)      \
+  SDE_KERNELS_WIENER(MODEL, TAG, SCH, SNAME, T, PNAME)
 // The RNG-driven FP64 kernels again for normal stream v2 (sdeb200_opts.rng = 2); FP32 and the Wiener-driven kernels
 // do not depend on the stream version.
-#define SDE_KERNELS_V2(MODEL, TAG, SCH, SNAME)                                                                   \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SAMPLE_MINB_V2) sdek_##TAG##_sample_##SNAME##_f64v2(    \
-      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, SCH, SDE_PPT, 2>(a); }          \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT, SDE_SAMPLE1_MINB) sdek_##TAG##_sample1_##SNAME##_f64v2( \
-      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, SCH, 1, 2>(a); }                \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_F64_MINB) sdek_##TAG##_mlmc_##SNAME##_f64v2(         \
-      const __grid_constant__ sde_args a) { sdeb200::mlmc_body<MODEL, double, SCH, 2>(a); }                     \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_F64_MINB) sdek_##TAG##_simsoa_##SNAME##_f64v2(       \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_soa_body<MODEL, double, SCH, 2>(a); }             \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_##SNAME##_f64v2(    \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, double, SCH, 2>(a); }             \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_##SNAME##_f64v2(      \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, double, SCH, 2>(a); }
+#define SDE_KERNELS_V2(MODEL, TAG, SCH, SNAME)                     \
+  SDE_KERNELS_TERMINAL(MODEL, TAG, SCH, SNAME, double, 2, f64v2)   \
+  SDE_KERNELS_TRAJ(MODEL, TAG, SCH, SNAME, double, 2, f64v2)
 
 // Exact one-step samplers exist for a few models only and have no Wiener-driven or coupled form
 // (src/simulation.jl:50-57,78-89): terminal and full-trajectory kernels, scheme id 3.

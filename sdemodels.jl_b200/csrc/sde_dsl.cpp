@@ -770,8 +770,11 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
         jac.assign(D, std::vector<E>(D));
         for (int i = 0; i < D; i++)
           for (int k = 0; k < D; k++) jac[i][k] = hoist(simplify(diff(diffm[i][0], vars[k])), dyn, hoisted);
-      } catch (const std::exception &) {
+      } catch (const std::exception &e) {
+        // no derivative (max, min, sign, two-argument functions ...): Milstein(Δt) must FAIL for this model, not run plain
+        // Euler–Maruyama silently (the reference differentiates with ForwardDiff and would succeed); the caller records it
         have_mil = false;
+        out->milstein_error = e.what();
       }
     }
     const int NP = (int)params.size();

@@ -12,6 +12,7 @@ struct sde_dsl_model {
   std::vector<std::string> drift_str;      // D entries
   std::vector<std::string> diffusion_str;  // D * max(M,1), row-major
   std::string cuda_source;                 // struct GenModel { ... } in namespace sdeb200
+  std::string milstein_error;              // M == 1 only: non-empty when the diffusion could not be differentiated symbolically
 };
 
 bool sde_dsl_build(const std::string &name, const std::string &eqs_utf8, const std::vector<std::string> &param_names,

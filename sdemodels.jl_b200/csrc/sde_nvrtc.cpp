@@ -119,22 +119,31 @@ static void cache_write(const std::string &path, const std::vector<char> &cubin)
   if (!ok || rename(t.c_str(), path.c_str()) != 0) unlink(t.c_str());
 }
 
+// Kernel families (sde_device.cuh): a generated model is compiled lazily, one family per (slot, math) on first use.
+enum { FAM_TERMINAL = 0, FAM_TRAJ = 1, FAM_WIENER = 2, FAM_MISC = 3 };
+// slot: 0 = f64 on normal stream v1, 1 = f32, 2 = f64 on normal stream v2
+static const char *slot_type(int slot) { return slot == 1 ? "float" : "double"; }
+static const char *slot_suffix(int slot) { return slot == 1 ? "f32" : (slot == 2 ? "f64v2" : "f64"); }
+
 // Compile only (no device needed): used by the CPU test-suite to check that generated functors build.
-int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision, int math, std::vector<char> *cubin,
+int sde_nvrtc_compile_only(const std::string &functor_src, int M, int slot, int math, int family, std::vector<char> *cubin,
                            std::string *log) {
   if (!nvrtc_load(log)) return SDEB200_E_NVRTC;
   std::string src = "#include \"sde_device.cuh\"\n";
   src += functor_src;
-  const char *T = precision == 0 ? "double" : "float", *P = precision == 0 ? "f64" : "f32";
-  src += std::string("\nSDE_KERNELS(sdeb200::GenModel, gen, 0, em, ") + T + ", " + P + ")\n";
-  if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 1, mil, ") + T + ", " + P + ")\n";
-  if (M == 1) src += std::string("SDE_KERNELS(sdeb200::GenModel, gen, 2, rk, ") + T + ", " + P + ")\n";
-  if (precision == 0) {  // the RNG-driven FP64 kernels on normal stream v2 as well
-    src += "SDE_KERNELS_V2(sdeb200::GenModel, gen, 0, em)\n";
-    if (M == 1) src += "SDE_KERNELS_V2(sdeb200::GenModel, gen, 1, mil)\nSDE_KERNELS_V2(sdeb200::GenModel, gen, 2, rk)\n";
+  const std::string T = slot_type(slot), SUF = slot_suffix(slot), V = slot == 2 ? "2" : "1";
+  const int nsch = M == 1 ? 3 : 1;
+  const char *sn[3] = {"em", "mil", "rk"};
+  for (int s = 0; s < nsch; s++) {
+    const std::string head = std::string("(sdeb200::GenModel, gen, ") + std::to_string(s) + ", " + sn[s] + ", " + T;
+    if (family == FAM_TERMINAL) src += "\nSDE_KERNELS_TERMINAL" + head + ", " + V + ", " + SUF + ")\n";
+    if (family == FAM_TRAJ) src += "\nSDE_KERNELS_TRAJ" + head + ", " + V + ", " + SUF + ")\n";
+    if (family == FAM_WIENER) src += "\nSDE_KERNELS_WIENER" + head + ", " + SUF + ")\n";
   }
-  src += "SDE_KERNELS_COEF(sdeb200::GenModel, gen)\n";
-  src += std::string("SDE_KERNELS_LOGT(sdeb200::GenModel, gen, ") + T + ", " + P + ")\n";
+  if (family == FAM_MISC) {
+    src += "\nSDE_KERNELS_COEF(sdeb200::GenModel, gen)\n";
+    src += std::string("SDE_KERNELS_LOGT(sdeb200::GenModel, gen, ") + T + ", " + SUF + ")\n";
+  }
   const char *hdr_src[] = {sde_embedded_device_cuh, sde_embedded_args_h, sde_embedded_coeffs_inc};
   const char *hdr_name[] = {"sde_device.cuh", "sde_args.h", "sde_coeffs.inc"};
   std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
@@ -167,11 +176,11 @@ int sde_nvrtc_compile_only(const std::string &functor_src, int M, int precision,
   return 0;
 }
 
-int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precision, int math, sde_ktable *kt,
+int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int slot, int math, int family, sde_ktable *kt,
                       void **library_out, std::string *log) {
   (void)D;
   std::vector<char> cubin;
-  int rc = sde_nvrtc_compile_only(functor_src, M, precision, math, &cubin, log);
+  int rc = sde_nvrtc_compile_only(functor_src, M, slot, math, family, &cubin, log);
   if (rc) return rc;
   cudaLibrary_t lib = nullptr;
   cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
@@ -179,42 +188,40 @@ int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precisio
     *log = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e);
     return SDEB200_E_CUDA;
   }
-  const char *P = precision == 0 ? "f64" : "f32";
-  auto get = [&](const std::string &nm, const void **dst) -> bool {
+  bool ok = true;
+  auto get = [&](const std::string &nm, const void **dst) {
     cudaKernel_t k = nullptr;
     cudaError_t ee = cudaLibraryGetKernel(&k, lib, nm.c_str());
     if (ee != cudaSuccess) {
       *log = "cudaLibraryGetKernel(" + nm + "): " + cudaGetErrorString(ee);
-      return false;
+      ok = false;
+      return;
     }
     *dst = (const void *)k;
-    return true;
   };
   const int nsch = M == 1 ? 3 : 1;
   const char *sn[3] = {"em", "mil", "rk"};
-  const int slot = precision == 0 ? 0 : 1;
-  for (int s = 0; s < nsch; s++) {
-    const std::string suf = std::string("_") + sn[s] + "_" + P;
-    if (!get("sdek_gen_sample" + suf, &kt->sample[s][slot]) || !get("sdek_gen_sample1" + suf, &kt->sample1[s][slot]) ||
-        !get("sdek_gen_mlmc" + suf, &kt->mlmc[s][slot]) || !get("sdek_gen_simsoa" + suf, &kt->simsoa[s][slot]) ||
-        !get("sdek_gen_simref" + suf, &kt->simref[s][slot]) || !get("sdek_gen_simw" + suf, &kt->simw[s][slot]) ||
-        !get("sdek_gen_simwt" + suf, &kt->simwt[s][slot]) || !get("sdek_gen_simrt" + suf, &kt->simrt[s][slot])) {
-      cudaLibraryUnload(lib);
-      return SDEB200_E_CUDA;
-    }
-    if (precision == 0) {
-      const std::string s2 = suf + "v2";
-      if (!get("sdek_gen_sample" + s2, &kt->sample[s][2]) || !get("sdek_gen_sample1" + s2, &kt->sample1[s][2]) ||
-          !get("sdek_gen_mlmc" + s2, &kt->mlmc[s][2]) || !get("sdek_gen_simsoa" + s2, &kt->simsoa[s][2]) ||
-          !get("sdek_gen_simref" + s2, &kt->simref[s][2]) || !get("sdek_gen_simrt" + s2, &kt->simrt[s][2])) {
-        cudaLibraryUnload(lib);
-        return SDEB200_E_CUDA;
-      }
-      kt->simw[s][2] = kt->simw[s][0];
-      kt->simwt[s][2] = kt->simwt[s][0];
+  const std::string SUF = slot_suffix(slot);
+  for (int s = 0; s < nsch && ok; s++) {
+    const std::string suf = std::string("_") + sn[s] + "_" + SUF;
+    if (family == FAM_TERMINAL) {
+      get("sdek_gen_sample" + suf, &kt->sample[s][slot]);
+      get("sdek_gen_sample1" + suf, &kt->sample1[s][slot]);
+      get("sdek_gen_mlmc" + suf, &kt->mlmc[s][slot]);
+    } else if (family == FAM_TRAJ) {
+      get("sdek_gen_simsoa" + suf, &kt->simsoa[s][slot]);
+      get("sdek_gen_simref" + suf, &kt->simref[s][slot]);
+      get("sdek_gen_simrt" + suf, &kt->simrt[s][slot]);
+    } else if (family == FAM_WIENER) {   // no noise: stream v2 compiles (and caches) its own copy of the f64 kernels
+      get("sdek_gen_simw" + suf, &kt->simw[s][slot]);
+      get("sdek_gen_simwt" + suf, &kt->simwt[s][slot]);
     }
   }
-  if (!get(std::string("sdek_gen_logt_") + P, &kt->logt[precision]) || !get("sdek_gen_coef", &kt->coef)) {
+  if (family == FAM_MISC && ok) {
+    get(std::string("sdek_gen_logt_") + SUF, &kt->logt[slot == 1 ? 1 : 0]);
+    get("sdek_gen_coef", &kt->coef);
+  }
+  if (!ok) {
     cudaLibraryUnload(lib);
     return SDEB200_E_CUDA;
   }
@@ -222,14 +229,20 @@ int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int precisio
   return 0;
 }
 
-// C entry used by the CPU tests: does the functor of a model text compile for sm_100a?
+// C entry used by the CPU tests: does the functor of a model text compile for sm_100a?  (terminal-value kernels: every
+// `step` form; coefficient / logtransition kernels: `coefficients`)
 extern "C" int sdeb200_debug_nvrtc_check(const char *functor_src, int M, int precision, int math, char *log, int logcap) {
   std::vector<char> cubin;
   std::string lg;
-  int rc = sde_nvrtc_compile_only(functor_src, M, precision, math, &cubin, &lg);
-  if (log && logcap > 0) {
-    strncpy(log, lg.c_str(), logcap - 1);
-    log[logcap - 1] = 0;
+  int total = 0;
+  for (int family : {FAM_TERMINAL, FAM_MISC}) {
+    int rc = sde_nvrtc_compile_only(functor_src, M, precision == 1 ? 1 : 0, math, family, &cubin, &lg);
+    if (rc) {
+      if (log && logcap > 0) { strncpy(log, lg.c_str(), logcap - 1); log[logcap - 1] = 0; }
+      return rc;
+    }
+    total += (int)cubin.size();
   }
-  return rc ? rc : (int)cubin.size();
+  if (log && logcap > 0) { strncpy(log, lg.c_str(), logcap - 1); log[logcap - 1] = 0; }
+  return total;
 }

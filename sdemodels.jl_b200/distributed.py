@@ -42,6 +42,60 @@ def init(device=None):
     return rank, world
 
 
+def init_devices(n=0):
+    """One process owning several GPUs (sdeb200_init_devices): bind devices 0..n-1 (n <= 0: all).  Afterwards every call
+    on host arrays is sharded over them — contiguous path ranges, one worker thread per GPU, exact sums combined on the
+    host — with results identical to a single GPU.  Returns the number of devices bound."""
+    out = C.c_int()
+    _lib.check(_lib.lib().sdeb200_init_devices(int(n), C.byref(out)))
+    return out.value
+
+
+def device_info():
+    n, p = C.c_int(), C.c_int()
+    _lib.lib().sdeb200_device_info(C.byref(n), C.byref(p))
+    return n.value, p.value
+
+
+class DeviceBuffer:
+    """A library-owned device buffer (sdeb200_buffer_*): results that stay on the GPU for callers without a device array
+    type.  `.ptr` goes wherever a driver takes a data pointer (`out=` accepts the object itself)."""
+
+    def __init__(self, shape, precision="f64"):
+        self.shape = tuple(int(v) for v in shape)
+        self.precision = precision
+        self.dtype = np.float64 if precision in ("f64", "float64") else np.float32
+        arr = (C.c_int64 * len(self.shape))(*self.shape)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().sdeb200_buffer_alloc(_lib.F64 if self.dtype == np.float64 else _lib.F32, len(self.shape), arr, C.byref(h)))
+        self._h = h
+        self.ptr = _lib.lib().sdeb200_buffer_ptr(h)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def to_host(self, offset=0, count=None):
+        n = int(np.prod(self.shape, dtype=np.int64)) - offset if count is None else int(count)
+        out = np.empty(n, dtype=self.dtype)
+        _lib.check(_lib.lib().sdeb200_buffer_copy_to_host(self._h, int(offset), n, out.ctypes.data))
+        return out.reshape(self.shape) if (offset == 0 and count is None) else out
+
+    def from_host(self, arr, offset=0):
+        a = np.ascontiguousarray(arr, dtype=self.dtype)
+        _lib.check(_lib.lib().sdeb200_buffer_copy_from_host(self._h, int(offset), a.size, a.ctypes.data))
+
+    def free(self):
+        if self._h:
+            _lib.lib().sdeb200_buffer_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def comm_info():
     n, r = C.c_int(), C.c_int()
     _lib.lib().sdeb200_comm_info(C.byref(n), C.byref(r))

@@ -32,6 +32,15 @@ class MultilevelScheme:
         return self.scheme.dt
 
 
+def level_stream(stream, i):
+    """SDEB200_LEVEL_STREAM (include/sdeb200.h): Philox stream word of level pair i of a multilevel run on `stream` — the
+    pair index sits in the top byte, so a plain run on stream 1 does not share its noise with level 1 (pair 0 IS the plain
+    `sample` on the caller's stream, multilevel.jl:56)."""
+    if not 0 <= int(stream) < (1 << 24):
+        raise ValueError("multilevel runs need 0 <= stream < 2^24")
+    return int(stream) + (int(i) << 24)
+
+
 def schemes(s):
     """[subdivide(s.scheme, s.substeps^l) for l in s.levels]   (multilevel.jl:7-10)"""
     return [subdivide(s.scheme, s.substeps ** l) for l in s.levels]
@@ -83,7 +92,7 @@ def _ml_sample(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, pa
         coarse, fine = ml_schemes[i - 1], ml_schemes[i]
         shape = (counts[i],) if scalar else (counts[i], model._D)
         xc, xf = sim._Buf(shape, precision, None, device), sim._Buf(shape, precision, None, device)
-        o = sim._opts(coarse, t0, seed, precision, math, stream + i, path_offset, rng=rng)
+        o = sim._opts(coarse, t0, seed, precision, math, level_stream(stream, i), path_offset, rng=rng)
         _lib.check(L.sdeb200_mlmc_sample_level(model._handle, C.byref(o), p.ctypes.data_as(_PD),
                                                v0.ctypes.data_as(_PD), fine.dt, s.substeps,
                                                nsteps * ml_steps[i - 1], counts[i], xc.ptr, xf.ptr))
@@ -138,7 +147,7 @@ def _ml_simulate(model, s, t0, x0, nsteps, n, *, seed, precision, math, stream, 
     for i in range(1, len(s.levels)):
         xc, xf, tc, tf = multilevel_simulate_level(model, ml_schemes[i - 1], ml_schemes[i], s.substeps, t0, x0,
                                                    nsteps * ml_steps[i - 1], counts[i], seed=seed,
-                                                   precision=precision, math=math, stream=stream + i,
+                                                   precision=precision, math=math, stream=level_stream(stream, i),
                                                    path_offset=path_offset, rng=rng, device=device)
         xs += [xc, xf]
         ts += [tc, tf]
@@ -220,7 +229,7 @@ def mlmc_adaptive(model, scheme, substeps, payoff, t0, x0, nsteps, eps, *, lmin=
         else:
             coarse = subdivide(scheme, substeps ** (level - 1))
             fine = subdivide(scheme, substeps ** level)
-            o = sim._opts(coarse, t0, seed, precision, math, stream + level, int(done[level]), rng=rng)
+            o = sim._opts(coarse, t0, seed, precision, math, level_stream(stream, level), int(done[level]), rng=rng)
             out = np.zeros(8)
             _lib.check(L_.sdeb200_mlmc_estimate_level(model._handle, C.byref(o), p.ctypes.data_as(_PD),
                                                       v0.ctypes.data_as(_PD), fine.dt, substeps,

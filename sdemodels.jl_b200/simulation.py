@@ -64,7 +64,11 @@ class _Buf:
         dt = _np_dtype(precision)
         self.torch = False
         if out is not None:
-            if hasattr(out, "data_ptr"):  # torch tensor
+            if hasattr(out, "to_host"):  # DeviceBuffer (library-owned device memory)
+                if out.dtype != dt or tuple(out.shape) != tuple(shape):
+                    raise ValueError(f"out must be a {dt.__name__} DeviceBuffer of shape {tuple(shape)}")
+                self.arr, self.ptr, self.torch = out, out.ptr, False
+            elif hasattr(out, "data_ptr"):  # torch tensor
                 import torch
                 want = torch.float64 if dt == np.float64 else torch.float32
                 if out.dtype != want or not out.is_contiguous() or tuple(out.shape) != tuple(shape):
@@ -158,14 +162,22 @@ def simulate_(x, model, scheme, t0, x0, w=None, *, seed=0, precision=None, math=
     for arr in (x, w):
         if arr is not None and not (arr.is_contiguous() if hasattr(arr, "is_contiguous") else arr.flags.c_contiguous):
             raise ValueError("simulate_ works in place: x and w must be C-contiguous")
-    if precision is None:
-        precision = "f32" if str(x.dtype).endswith("float32") else "f64"
+    xprec = "f32" if str(x.dtype).endswith("float32") else ("f64" if str(x.dtype).endswith("float64") else None)
+    if xprec is None:
+        raise TypeError(f"x must be float32 or float64, not {x.dtype}")
+    if precision is not None and _PREC[precision] != _PREC[xprec]:
+        raise TypeError(f"precision={precision!r} disagrees with x.dtype {x.dtype}: the library would write past the buffer")
+    precision = xprec
+    if w is not None and str(w.dtype) != str(x.dtype):
+        raise TypeError(f"w.dtype {w.dtype} must equal x.dtype {x.dtype} (eltype(w) drives the arithmetic, simulation.jl:119-134)")
     o = _opts(scheme, t0, seed, precision, math, stream, path_offset, rng=rng)
     p = _params(model)
     D, M = model._D, max(model._M, 1)
     xs = tuple(x.shape)
+    if len(xs) < (1 if scalar else 2) or (not scalar and xs[-1] != D):
+        raise ValueError(f"x {xs} must be ([npaths,] nrows{'' if scalar else ', ' + str(D)})")
     if w is None:
-        n = xs[0] if len(xs) > (1 if scalar else 2) else 1
+        n = int(np.prod(xs[:-1] if scalar else xs[:-2], dtype=np.int64)) if len(xs) > (1 if scalar else 2) else 1
         nrows = xs[-1] if scalar else xs[-2]
         ptr = x.data_ptr() if is_torch else x.ctypes.data
         _lib.check(L.sdeb200_simulate(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
@@ -187,6 +199,10 @@ def wiener_(w, dt, *, seed=0, stream=0, path_offset=0, rng=None, math="fast"):
     """wiener!(w, Δt)   (simulation.jl:22-35): w[(npaths,) nrows (, dim)], row 0 = 0, running sums of N(0, Δt)."""
     L = _lib.lib()
     is_torch = hasattr(w, "data_ptr")
+    if not (w.is_contiguous() if hasattr(w, "is_contiguous") else w.flags.c_contiguous):
+        raise ValueError("wiener_ works in place: w must be C-contiguous")
+    if not str(w.dtype).endswith(("float32", "float64")):
+        raise TypeError(f"w must be float32 or float64, not {w.dtype}")
     precision = "f32" if str(w.dtype).endswith("float32") else "f64"
     o = _lib.Opts()
     o.precision, o.math, o.dt = _PREC[precision], _MATH[math], float(dt)

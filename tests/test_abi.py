@@ -95,3 +95,23 @@ def test_exact_accumulator_host_half(S):
     assert L.sdeb200_bins_to_double(b.ctypes.data_as(P64)) == 2.0 ** 53
     L.sdeb200_bins_add(b.ctypes.data_as(P64), 1.0)
     assert L.sdeb200_bins_to_double(b.ctypes.data_as(P64)) == 2.0 ** 53 + 2
+
+
+def test_milstein_without_a_symbolic_derivative_is_refused(S):
+    """when the front end cannot differentiate the diffusion (max, min, sign, ...), Milstein(Δt) must fail with
+    E_UNSUPPORTED instead of silently running Euler–Maruyama; EulerMaruyama and RungeKutta stay available.  The refusal
+    happens before any device is touched, so this runs on the CPU."""
+    import numpy as np
+    cls = S.sde_model("Floored", "dS = r*S*dt + σ*max(S, 0.5)*dW")
+    m = cls(0.01, 0.3)
+    with pytest.raises(S.SDEB200Error) as ei:
+        S.sample(m, S.Milstein(0.01), 0.0, 1.0, 4, 10)
+    assert ei.value.code == S._lib.E_UNSUPPORTED and "max" in str(ei.value) and "RungeKutta" in str(ei.value)
+    ok = S.sde_model("Smooth", "dS = r*S*dt + σ*sqrt(S)*dW")(0.01, 0.3)
+    for sch in (S.Milstein(0.01), S.RungeKutta(0.01), S.EulerMaruyama(0.01)):
+        with pytest.raises(S.SDEB200Error) as ei:       # no GPU here: the call gets past the scheme check and fails on the device
+            S.sample(ok, sch, 0.0, 1.0, 4, 10)
+        assert ei.value.code in (S._lib.E_CUDA, S._lib.E_NVRTC)
+    with pytest.raises(S.SDEB200Error) as ei:
+        S.sample(m, S.RungeKutta(0.01), 0.0, 1.0, 4, 10)
+    assert ei.value.code in (S._lib.E_CUDA, S._lib.E_NVRTC)
