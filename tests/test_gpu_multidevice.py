@@ -155,15 +155,15 @@ def test_level_streams_are_namespaced(gpu):
     stream 1 no longer shares its noise with level 1 of a run on stream 0."""
     S = gpu
     he = S.Heston(*HESTON_P)
-    ml = S.MultilevelScheme(S.EulerMaruyama(1 / 4), 2, range(0, 3))
-    xs = S.sample(he, ml, 0.0, [100.0, 0.4], 4, 2000, seed=3)
+    ml = S.MultilevelScheme(S.EulerMaruyama(1 / 16), 2, range(0, 3))              # κΔt = 0.625: the variance stays positive
+    xs = S.sample(he, ml, 0.0, [100.0, 0.4], 16, 2000, seed=3)
     assert len(xs) == 5
-    plain1 = S.sample(he, S.EulerMaruyama(1 / 8), 0.0, [100.0, 0.4], 8, 2000, seed=3, stream=1)
+    plain1 = S.sample(he, S.EulerMaruyama(1 / 32), 0.0, [100.0, 0.4], 32, 2000, seed=3, stream=1)
     assert not np.array_equal(xs[2], plain1)                                       # level 1's fine path: other noise
-    ns = S.sample(he, S.EulerMaruyama(1 / 8), 0.0, [100.0, 0.4], 8, 2000, seed=3, stream=S.level_stream(0, 1))
+    ns = S.sample(he, S.EulerMaruyama(1 / 32), 0.0, [100.0, 0.4], 32, 2000, seed=3, stream=S.level_stream(0, 1))
     assert np.array_equal(xs[2], ns)                                               # ... namely the namespaced stream's
-    assert np.array_equal(xs[0], S.sample(he, S.EulerMaruyama(1 / 4), 0.0, [100.0, 0.4], 4, 2000, seed=3))   # pair 0: plain sample
-    e = S.ml_estimate(he, ml, S.Component(0), 0.0, [100.0, 0.4], 4, 2000, seed=3)
+    assert np.array_equal(xs[0], S.sample(he, S.EulerMaruyama(1 / 16), 0.0, [100.0, 0.4], 16, 2000, seed=3))   # pair 0: plain sample
+    e = S.ml_estimate(he, ml, S.Component(0), 0.0, [100.0, 0.4], 16, 2000, seed=3)
     assert abs(e.fine_mean[1] - xs[2][:, 0].mean()) <= 1e-9 * 100 and abs(e.fine_mean[2] - xs[4][:, 0].mean()) <= 1e-9 * 100
     with pytest.raises(ValueError):
         S.level_stream(1 << 24, 1)
