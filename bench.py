@@ -6,11 +6,14 @@ Workload (BASELINE.json configs[1], "C2"): Heston (correlated dW1/dW2) Euler–M
 the fused sample+reduce kernel (terminal states kept in HBM, payoff sums reduced on the fly, one NCCL
 all-reduce per step when N > 1).  Metric: path-steps/s, whole job.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--paths P] [--nsteps S] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--paths P] [--nsteps S] [--rng 1|2] [--impl reference]
 
-Under torchrun (N > 1) every rank simulates its own 10^8 paths (weak scaling: global path ids
-rank*P .. (rank+1)*P - 1 of one logical run), timing is CUDA events on the launching stream, max over ranks.
-`--impl reference` times the reference's own execution model — the scalar per-path CPU loops of
+Noise: normal stream v2 (sdeb200_opts.rng = 2, DESIGN.md §4: Philox4x32-10, 96 bits per pair of FP64 normals) — an explicit
+option of the library; the same measurement on the default stream v1 (128 bits per pair, round 1's headline) is reported
+beside it as `stream_v1`.  Under torchrun (N > 1) `value` is WEAK scaling (every rank simulates its own 10^8 paths:
+global path ids rank*P .. (rank+1)*P - 1 of one logical run); `strong` holds the same step with 10^8 paths IN TOTAL split
+over the ranks (BASELINE's metric names 10^8 paths at 1/2/4/8 GPUs).  Timing is CUDA events on the launching stream, max
+over ranks.  `--impl reference` times the reference's own execution model — the scalar per-path CPU loops of
 src/simulation.jl:39-67 as restated in oracle/sde_oracle.c (Julia is not in the image) — on all host cores.
 """
 import argparse
@@ -71,6 +74,20 @@ def clocks_summary(proc):
             "power_w_max": max(power), "samples": len(sm)}
 
 
+def ncu_traffic(csv_name, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from a committed ncu summary (profiles/*.csv), in bytes"""
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    try:
+        for row in open(os.path.join(ROOT, "profiles", csv_name)):
+            f = row.strip().split(",")
+            if len(f) >= 5 and f[1] == kernel and f[2] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[4]) * unit.get(f[3], 1)
+    except OSError:
+        return None
+    return int(total) if total else None
+
+
 def host_threads():
     """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must not
     inherit that (it would time the reference on one core and call it the host), so the count is passed explicitly."""
@@ -114,9 +131,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "path-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Heston EM FP64, {args.paths} paths x {nsteps} steps, terminal values (C2)",
+        "config": {"workload": f"Heston EM FP64, terminal values (C2: 10^8 paths x {nsteps} steps); each step RAN a bounded sample "
+                               f"of {n} paths x {nsteps} steps on {cores} host cores, rate extrapolated",
+                   "sample_paths_per_step": n, "nsteps": nsteps, "host_cores": cores,
                    "note": "CPU restatement of SDEModels.jl's scalar per-path loops (src/simulation.jl:39-67), not Julia "
-                           "(Julia is not installed in this image); each step is a bounded sample of the workload"},
+                           "(Julia is not installed in this image)"},
         "cpu_baseline": {"value": value, "unit": "path-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{n} paths x {nsteps} steps per step, OpenMP over paths, ziggurat normals"},
         "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -135,6 +154,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--rng", type=int, default=2, choices=[1, 2], help="normal stream version of the headline measurement")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: no stream-v1 / strong-scaling / pageable / HBM-kernel legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -164,14 +185,37 @@ def main():
     terminal = torch.empty((P, 2), dtype=tdtype, device="cuda")
     off = rank * P  # weak scaling: rank r owns global paths [r*P, (r+1)*P) of one logical run
 
-    def step(seed):
-        return S.estimate(model, scheme, S.Moments(), 0.0, X0, N, P, seed=seed, precision=prec, path_offset=off,
-                          terminal=terminal)
+    def step(seed, rng=args.rng, n=P, offset=off):
+        return S.estimate(model, scheme, S.Moments(), 0.0, X0, N, n, seed=seed, precision=prec, path_offset=offset,
+                          terminal=terminal[:n] if n else None, rng=rng)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, steps, warmup):
+        """W untimed + K timed calls of fn(seed), barrier + synchronize on both sides; -> (ms per step, max over ranks; kernel ms)"""
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        kms = []
+        e0.record(stream)
+        for i in range(steps):
+            fn(100 + i)
+            kms.append(S.last_kernel_ms())
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, sum(kms) / len(kms)
 
     peak_tf, _ = S.measure_peak(prec)
     for i in range(args.warmup):
@@ -179,7 +223,6 @@ def main():
     barrier()
     smi = clocks_sampler(local) if rank == 0 else None
     l0 = S.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
     barrier()
     e0.record(stream)
@@ -191,31 +234,50 @@ def main():
     ms_total = e0.elapsed_time(e1)
     launches = S.launch_count() - l0
     clocks = clocks_summary(smi) if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
+    ms_per_step = max_over_ranks(ms_total) / args.steps
     value = world * P * N / (ms_per_step * 1e-3)
 
-    # end to end through the public API with HOST buffers: sample() into pinned host memory every step
+    extras = {}
+    if not args.no_extras:
+        # the same step on the library's default stream v1 (round 1's headline), for continuity
+        ms1, k1 = timed(lambda sd: step(sd, rng=1), max(2, args.steps // 2), 1)
+        extras["stream_v1"] = {"value": world * P * N / (ms1 * 1e-3), "unit": "path-steps/s", "ms_per_step": ms1, "kernel_ms": k1,
+                               "what": "same workload on normal stream v1 (128 Philox bits per FP64 pair; the library default)"}
+        # strong scaling: 10^8 paths IN TOTAL, contiguous shards on SHARD_ALIGN boundaries (what BASELINE's metric names)
+        lo, hi = S.shard_range(P, rank, world)
+        ms_s, _ = timed(lambda sd: step(sd, n=hi - lo, offset=lo), args.steps, 2)
+        extras["strong"] = {"value": P * N / (ms_s * 1e-3), "unit": "path-steps/s", "ms_per_step": ms_s, "paths_total": P,
+                            "paths_this_rank": hi - lo, "scaling": "strong",
+                            "what": f"{P} paths in total over {world} GPU(s), one all-reduce per step"}
+
+    # end to end through the public API with HOST buffers: sample() into host memory every step
     host = torch.empty((P, 2), dtype=tdtype, pin_memory=True)
     host_np = host.numpy()
-    S.sample(model, scheme, 0.0, X0, N, P, seed=7, precision=prec, path_offset=off, out=host_np)  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for i in range(args.steps):
-        S.sample(model, scheme, 0.0, X0, N, P, seed=200 + i, precision=prec, path_offset=off, out=host_np)
-        chk = float(host_np[0, 0])
-    e1.record(stream)
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * P * N / (e2e_ms / args.steps * 1e-3)
+
+    def e2e_leg(dst, steps):
+        S.sample(model, scheme, 0.0, X0, N, P, seed=7, precision=prec, path_offset=off, out=dst, rng=args.rng)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        chk = 0.0
+        for i in range(steps):
+            S.sample(model, scheme, 0.0, X0, N, P, seed=200 + i, precision=prec, path_offset=off, out=dst, rng=args.rng)
+            chk = float(dst[0, 0])
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+        return world * P * N / (ms / steps * 1e-3), ms / steps, chk
+
+    e2e_value, e2e_ms_step, chk = e2e_leg(host_np, args.steps)
+    if not args.no_extras:
+        # the caller the Julia shim actually has: a PAGEABLE array (Julia `Array`, numpy) — staged through the library's pinned ring
+        page = np.empty((P, 2), dtype=np.float64 if prec == "f64" else np.float32)
+        pv, pms, pchk = e2e_leg(page, max(2, args.steps // 2))
+        extras["e2e_pageable"] = {"value": pv, "unit": "path-steps/s", "ms_per_step": pms, "d2h_bytes_per_step": int(page.nbytes),
+                                  "call": "sample(...) into a pageable numpy array (what a Julia Array is): D2H into the library's "
+                                          "pinned ring, threaded memcpy into the caller's array, overlapped with compute", "check": pchk}
+        del page
+    e2e_ms = e2e_ms_step * args.steps
 
     if rank == 0:
         kms = sum(kern_ms) / len(kern_ms)
@@ -226,24 +288,34 @@ def main():
             sass = json.load(open(os.path.join(ROOT, "profiles", "sass_counts.json")))
         except OSError:
             pass
-        key = "heston_sample_em_" + prec
+        suffix = prec + ("v2" if (args.rng == 2 and prec == "f64") else "")
+        key = "heston_sample_em_" + suffix
+        # FP64 denominator: the larger of the live FMA-chain figure and the stored standalone DFMA measurement
+        # (profiles/r01_mb_mix.txt: 36.37 TFLOP/s), both recorded — the in-run figure is ~6 % low
+        stored_peak = 36.37 if prec == "f64" else None
+        peak_used = max(peak_tf, stored_peak) if stored_peak else peak_tf
         roofline = {
-            "bound": "fp64" if prec == "f64" else "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved / peak_tf, "traffic": None,
-            "kernel": f"sdek_heston_f_sample_em_{prec}", "kernel_ms": kms,
-            "peak_source": "measured live: FMA-chain micro-benchmark (sdeb200_measure_peak); MEASURED_PEAKS.json "
-                           "has no FP64/FP32 CUDA-core figure",
+            "bound": "fp64" if prec == "f64" else "fp32", "achieved": achieved, "peak": peak_used, "unit": "TFLOP/s",
+            "frac": achieved / peak_used, "traffic": None,
+            "kernel": f"sdek_heston_f_sample_em_{suffix}", "kernel_ms": kms,
+            "peak_live": peak_tf, "peak_stored": stored_peak,
+            "peak_source": "max(live FMA-chain micro-benchmark sdeb200_measure_peak, standalone DFMA stream of "
+                           "profiles/r01_mb_mix.txt); MEASURED_PEAKS.json has no FP64/FP32 CUDA-core figure",
             "note": "achieved = 18 algorithmic flops/path-step x path-steps/s (SURVEY §8d); the normal generator "
                     "legitimately executes several times that, see executed_frac",
         }
         try:
             cap = json.load(open(os.path.join(ROOT, "profiles", "headline_ncu.json")))
-            if prec == "f64":
-                roofline["ncu"] = cap  # pipe utilisation and DRAM bytes of one profiled launch (smaller batch)
-                roofline["traffic_note"] = ("algorithmic traffic is 16 B per path (terminal state), nothing per step: %d bytes "
-                                            "per launch here; ncu measured %d B for %d paths" %
-                                            (16 * P, cap["dram_bytes_read"] + cap["dram_bytes_write"], cap["paths"]))
-        except OSError:
+            if prec == "f64" and cap.get("kernel") == roofline["kernel"]:
+                # DRAM bytes of the ncu capture of the SAME kernel (kept under profiles/), scaled per path to this launch
+                per_path = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["paths"]
+                roofline["traffic"] = int(per_path * P)
+                roofline["ncu"] = cap
+                roofline["traffic_note"] = ("algorithmic traffic is 16 B per path (terminal state), nothing per step: %d bytes per "
+                                            "launch here; the ncu capture (%s) measured %d B for %d paths, scaled per path"
+                                            % (16 * P, cap.get("file", "profiles/"), cap["dram_bytes_read"] + cap["dram_bytes_write"],
+                                               cap["paths"]))
+        except (OSError, KeyError, ValueError):
             pass
         if key in sass:
             fl = sass[key]["fp_flops_per_path_step"]
@@ -254,7 +326,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": prec, "data": "synthetic",
             "config": {"workload": f"Heston EM {prec.upper()}, {P} paths x {N} steps per GPU, terminal values + fused "
-                                   f"moment reduction (C2)", "paths_per_gpu": P, "nsteps": N, "parallelism": f"paths x{world}",
+                                   f"moment reduction (C2), normal stream v{args.rng}", "paths_per_gpu": P, "nsteps": N,
+                       "parallelism": f"paths x{world}", "normal_stream": args.rng,
                        "l2": "no reusable input; the 1.6 GB terminal-state output per step exceeds the 126 MB L2",
                        "check": {"mean_S": float(est.mean[0]), "stderr_S": float(est.stderr[0]), "n": int(est.n),
                                  "closed_form_mean_S": 100.0 * (1 + 0.01 / N) ** N}},
@@ -265,7 +338,8 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
         }
-        if world == 1:
+        line.update(extras)
+        if world == 1 and not args.no_extras:
             # the HBM-bound kernel of the path, measured live for its own roofline line: Wiener-driven trajectories
             # simulate!(x, model, scheme, t0, x0, w) with x === w on TMA tensor tiles (2e6 paths x 513 rows, 8.2 GB)
             try:
@@ -288,9 +362,9 @@ def main():
                 line["roofline_hbm_kernel"] = {
                     "kernel": "sdek_bs_f_simwt_em_f64", "bound": "hbm", "achieved": nbytes / best / 1e6, "peak": hbm_peak,
                     "unit": "GB/s", "frac": nbytes / best / 1e6 / hbm_peak, "peak_source": src, "kernel_ms": best,
-                    "algorithmic_bytes": nbytes, "traffic": 16611395000,
-                    "traffic_note": "ncu --set full of the same launch shape: 8.394 GB read + 8.217 GB written "
-                                    "(profiles/r01d_tma_kernels_ncu_summary.csv); algorithmic 8.208 + 8.208 GB",
+                    "algorithmic_bytes": nbytes, "traffic": ncu_traffic("r01d_tma_kernels_ncu_summary.csv", "sdek_bs_f_simwt_em_f64"),
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture of the same launch "
+                                    "shape, read from profiles/r01d_tma_kernels_ncu_summary.csv; algorithmic 8.208 + 8.208 GB",
                     "workload": "BlackScholes EM FP64, simulate!(x, model, scheme, t0, x0, w) in place, 2e6 paths x 513 rows"}
                 del wbuf
             except Exception as err:  # the headline line must not depend on this extra

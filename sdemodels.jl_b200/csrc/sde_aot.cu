@@ -109,16 +109,16 @@ XCOEF(Heston, TAGGED(heston))
     sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, float, 0>(a);                                          \
   }                                                                                                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##t_f64(const __grid_constant__ sde_args a) { \
-    sdeb200::simulate_ref_tma_body<sdeb200::WienerN<DIM>, double, 0>(a);                                     \
+    sdeb200::simulate_ref_tma2_body<sdeb200::WienerN<DIM>, double, 0>(a);                                     \
   }                                                                                                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##t_f32(const __grid_constant__ sde_args a) { \
-    sdeb200::simulate_ref_tma_body<sdeb200::WienerN<DIM>, float, 0>(a);                                      \
+    sdeb200::simulate_ref_tma2_body<sdeb200::WienerN<DIM>, float, 0>(a);                                      \
   }                                                                                                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 5) sdek_##TAG##_f64v2(const __grid_constant__ sde_args a) { \
     sdeb200::simulate_ref_body<sdeb200::WienerN<DIM>, double, 0, 2>(a);                                      \
   }                                                                                                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##t_f64v2(const __grid_constant__ sde_args a) { \
-    sdeb200::simulate_ref_tma_body<sdeb200::WienerN<DIM>, double, 0, 2>(a);                                  \
+    sdeb200::simulate_ref_tma2_body<sdeb200::WienerN<DIM>, double, 0, 2>(a);                                  \
   }
 XWIENER(1, TAGGED(wiener1))
 XWIENER(2, TAGGED(wiener2))

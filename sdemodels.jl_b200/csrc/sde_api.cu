@@ -606,14 +606,15 @@ static int tmap_encoder(tmap_encode_fn *out) {
 // Tensor map of a trajectory buffer in reference order [path][row][D]: g paths per map row (sde_args.h), boxes of
 // (32/g map rows) x (128 bytes), 128-byte shared-memory swizzle.  npaths must be a multiple of g.
 static_assert(sizeof(sde_tmap) == sizeof(CUtensorMap) && alignof(sde_tmap) == alignof(CUtensorMap), "sde_tmap mirrors CUtensorMap");
-static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, int64_t nrows, int64_t npaths, int grp) {
+static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, int64_t nrows, int64_t npaths, int grp,
+                          int boxrows = 0) {
   tmap_encode_fn enc = nullptr;
   int rc = tmap_encoder(&enc);
   if (rc) return rc;
   const size_t es = precision == SDEB200_F64 ? 8 : 4;
   const cuuint64_t dims[2] = {(cuuint64_t)grp * nrows * D, (cuuint64_t)(npaths / grp)};
   const cuuint64_t strides[1] = {(cuuint64_t)grp * nrows * D * es};
-  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)(32 / grp)};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)(boxrows > 0 ? boxrows : 32 / grp)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc((CUtensorMap *)tm, precision == SDEB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -623,31 +624,43 @@ static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, 
 }
 
 // reference-order trajectories with TMA tensor stores (simulate_ref_tma_body): per warp a ring of two 4 KB tiles
-static size_t simrt_smem() { return (size_t)(SDE_BLOCK / 32) * 2 * 4096 + 1024; }
+static size_t simrt_smem(int precision) {
+  return (size_t)(SDE_BLOCK / 32) * (precision == SDEB200_F64 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32) * 4096 + 1024;
+}
 static int64_t simref_grid(int64_t npaths);
 static size_t simref_smem(int D, int precision);
-// One RNG-driven reference-order launch into a device buffer: the TMA-store kernel where its tiles apply
-// (D*sizeof(T) | 128, 16-byte aligned buffer, paths of at least two tiles), the shared-memory-tile kernel otherwise
-// and for the npaths % g leftover paths.  `a` carries everything but npaths / out (and path0 of the first path).
-static int launch_simref(const void *k, const void *k_tma, int D, int precision, sde_args a, int64_t npaths, void *out,
+// steps per Philox batch of a (precision, stream version, M) combination: Batch<T, M, V>::U of sde_device.cuh
+static int batch_steps(int M, int slot) {
+  if (M <= 0) return 1;
+  auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+  if (slot == 2) return 8 / gcd(M, 8);
+  const int npb = slot == 1 ? 4 : 2;
+  return npb / gcd(M, npb);
+}
+// One RNG-driven reference-order launch into a device buffer: the TMA-store kernel K2u (one sub-path per warp, whole
+// 16-byte chunks per Philox batch) where its geometry applies — rows of 4, 8 or 16 bytes, batches of whole chunks that
+// divide a 128-byte tile row, 16-byte aligned buffer, paths of at least two tiles — the shared-memory-tile kernel K2b
+// otherwise and for the npaths % g leftover paths.  `a` carries everything but npaths / out (and path0 of the first path).
+static int launch_simref(const void *k, const void *k_tma, int D, int M, int slot, sde_args a, int64_t npaths, void *out,
                          cudaStream_t st) {
+  const int precision = slot == 1 ? SDEB200_F32 : SDEB200_F64;
   const size_t es = precision == SDEB200_F64 ? 8 : 4;
   const int rowb = (int)(D * es);
   const int64_t nrows = a.nsteps + 1;
+  const int bb = batch_steps(M, slot) * rowb;
   int rc;
   int64_t done = 0;
-  // measured (profiles/README.md): the tensor-store form wins for 8-byte rows (+5..19 %), the tile kernel for 4- and
-  // 16-byte rows (-3 %): route by row size
-  if (k_tma && g_tma_enabled && rowb == 8 && ((uintptr_t)out % 16) == 0 && nrows >= 2 * (128 / rowb) + 4 &&
-      nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
+  if (k_tma && g_tma_enabled && M > 0 && 16 % rowb == 0 && bb % 16 == 0 && 128 % bb == 0 && ((uintptr_t)out % 16) == 0 &&
+      nrows >= 2 * (128 / rowb) + 4 && nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
     const int grp = sde_tma_group(nrows * rowb);
     const int64_t ncov = npaths - npaths % grp;
     if (ncov >= 32) {
       sde_args b = a;
       b.npaths = ncov;
       b.out = out;
-      if ((rc = make_traj_tmap(&b.tm_x, out, precision, D, nrows, ncov, grp))) return rc;
-      if ((rc = launch(k_tma, (ncov + SDE_BLOCK - 1) / SDE_BLOCK, &b, st, simrt_smem()))) return rc;
+      if ((rc = make_traj_tmap(&b.tm_x, out, precision, D, nrows, ncov, grp, 32))) return rc;
+      const int64_t units = (int64_t)grp * cdiv(ncov / grp, 32);     // warps: sub-path j of 32 map rows each
+      if ((rc = launch(k_tma, cdiv(units, SDE_BLOCK / 32), &b, st, simrt_smem(precision)))) return rc;
       g.tma_launches++;
       done = ncov;
     }
@@ -980,12 +993,12 @@ extern "C" int sdeb200_simulate(sdeb200_model *m, const sdeb200_opts *o, const d
     const void *k = kt->simref[o->scheme][kslot(o)], *k_tma = kt->simrt[o->scheme][kslot(o)];
     const size_t bpp = (size_t)nrows * m->D * es;
     if (dev) {
-      if ((rc = launch_simref(k, k_tma, m->D, o->precision, a, npaths, out, st))) return rc;
+      if ((rc = launch_simref(k, k_tma, m->D, m->M, kslot(o), a, npaths, out, st))) return rc;
     } else {
       rc = run_slabs(npaths, bpp, out, [&](int64_t s0, int64_t n, void *d, cudaStream_t s) {
         sde_args b = a;
         b.path0 = o->path_offset + s0;
-        return launch_simref(k, k_tma, m->D, o->precision, b, n, d, s);
+        return launch_simref(k, k_tma, m->D, m->M, kslot(o), b, n, d, s);
       });
       if (rc) return rc;
     }
@@ -1231,7 +1244,7 @@ static int wiener_device(const sdeb200_opts *o, int dim, int64_t nrows, int64_t 
   a.path0 = path0;
   a.nsteps = nrows - 1;
   const void *k_tma = o->math == SDEB200_MATH_STRICT ? sde_aot_wiener_strict(16 + dim, slot) : sde_aot_wiener_fast(16 + dim, slot);
-  return launch_simref(k, k_tma, dim, o->precision, a, npaths, dev, st);
+  return launch_simref(k, k_tma, dim, dim, slot, a, npaths, dev, st);
 }
 
 extern "C" int sdeb200_wiener(const sdeb200_opts *o, int dim, int64_t nrows, int64_t npaths, void *w) {

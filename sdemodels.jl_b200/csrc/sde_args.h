@@ -81,6 +81,15 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb) {
   while (((int64_t)j * pitch_bytes + (int64_t)h * rowb) % 16) h++;
   return h;
 }
+/* ring depth of the reference-order TMA store kernel K2u, 4 KB per stage and warp.  Measured on C3 (BlackScholes Milstein,
+ * 10^7 x 512): FP64 2 / 3 / 4 stages 3.64 / 3.16 / 3.06 TB/s (114 registers: occupancy pays, not slack), FP32 2.35 / 2.62 / 2.86
+ * TB/s (the warp waits on the tensor store of the tile that last used the stage: slack pays) */
+#ifndef SDE_SIMRT2_STAGES_F64
+#define SDE_SIMRT2_STAGES_F64 2
+#endif
+#ifndef SDE_SIMRT2_STAGES_F32
+#define SDE_SIMRT2_STAGES_F32 4
+#endif
 #ifndef SDE_SIMWT_STAGES
 #define SDE_SIMWT_STAGES 6 /* ring depth of the TMA Wiener-driven kernel: 4 KB per stage and warp */
 #endif

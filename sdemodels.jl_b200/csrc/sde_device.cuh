@@ -444,16 +444,37 @@ SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double 
 }
 
 // FP32 stream: 128 Philox bits -> four N(0, scale2) variates.  u1 = (r + 1/2) 2^-32, angle = r' / 2^32 turns.
-// log2 and sqrt on the MUFU unit; (cos, sin) from a 256-entry table of cell centres (top 8 bits of r') plus a
-// one-term residual rotation in the 24-bit offset — no quadrant logic.  rotf: {cos, sin} float pairs.
+// log2, sqrt, sin and cos on the MUFU unit (device, SDE_F32_MUFU); the host twin and the SDE_F32_MUFU = 0 build take
+// (cos, sin) from a 256-entry table of cell centres (top 8 bits of r') plus a one-term residual rotation in the 24-bit
+// offset.  rotf: {cos, sin} float pairs.
+#ifndef SDE_F32_MUFU
+#define SDE_F32_MUFU 1 /* device: (cos, sin) of the FP32 stream on the MUFU unit (sin.approx / cos.approx, |x| <= pi: abs error
+                          ~2^-21) instead of the 256-entry table + residual rotation: 10 instructions fewer per pair; the
+                          full-trajectory FP32 kernels are issue-bound (profiles/README.md) */
+#endif
 SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, const float *rotf, float &z0, float &z1) {
 #if defined(__CUDA_ARCH__)
   const float u1 = fmaf(__uint2float_rn(ra), 0x1.0p-32f, 0x1.0p-33f);
+#if SDE_F32_MUFU
+  // u1 <= 1 (the largest word rounds to exactly 1): log2 <= 0, so w >= 0 without a clamp; -0 passes through sqrt.approx
+  const float w = (-0x1.62e430p+0f /* 2 ln 2 */ * scale2) * __log2f(u1);
+  float g, sn, cs;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(w));
+  const float ang = __int2float_rn((int32_t)rb) * 0x1.921fb6p-30f;   // 2 pi rb / 2^32 with rb read as signed: [-pi, pi)
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+  (void)rotf;
+  z0 = g * cs;
+  z1 = g * sn;
+  return;
+#else
   float w = -0x1.62e430p+0f /* 2 ln 2 */ * __log2f(u1);
+#endif
 #else
   const float u1 = fmaf((float)ra, 0x1.0p-32f, 0x1.0p-33f);
   float w = -0x1.62e430p+0f * log2f(u1);
 #endif
+#if !(defined(__CUDA_ARCH__) && SDE_F32_MUFU)
   w = fmaxf(w * scale2, 0.0f);
 #if defined(__CUDA_ARCH__)
   float g;
@@ -469,6 +490,7 @@ SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, const float 
   const float cm = u * fmaf(SDE_ROTF_C2, u, SDE_ROTF_C1);
   z0 = g * fmaf(C, cm, fmaf(-S, sn, C));
   z1 = g * fmaf(S, cm, fmaf(C, sn, S));
+#endif
 }
 
 // Normals per Philox block for each precision.
@@ -494,6 +516,7 @@ SDE_HD void normals_from_block(const uint32_t (&r)[4], const double *tab, const 
 __host__ __device__
 #endif
 constexpr int sde_gcd(int a, int b) { return b == 0 ? a : sde_gcd(b, a % b); }
+template <int N> struct IntC { static constexpr int value = N; };   // a compile-time integer passed to a generic lambda
 
 #if !defined(__CUDACC__)
 // host twin of the log table, for the CPU unit tests of the transform (tests/host_math_harness.cpp)
@@ -1601,57 +1624,38 @@ SDE_D void simulate_wiener_tma_body(const sde_args &a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2t full trajectories in the reference's order [path][time][D] with TMA tensor stores (same results as K2b):
-//     every lane owns a path and writes its rows into the 128-byte row of the warp's swizzled tile; when all lanes
-//     have filled tile k, lane 0 stores it with g tensor stores (geometry: sde_args.h) and the warp goes on
-//     filling the other stage — no cooperative store pass, no second trip through registers.  The box of sub-path
-//     j starts at time row h_j (first 16-byte aligned row), so lanes of different sub-paths are h_j rows out of
-//     phase inside the ring; rows before h_j and after the last full tile are plain (fire-and-forget) stores.
-//     Used by simulate (reference layout), the Exact samplers and wiener!.
+// K2u full trajectories in the reference's order [path][time][D] with TMA tensor stores, ONE SUB-PATH PER WARP
+//     (round 2; same results as K2b / K2t, bit for bit).  In K2t a warp's 32 lanes cover the g sub-paths of 32/g map
+//     rows, so lanes sit at different phases h_j of the 16-byte grid and every row costs its own narrow shared-memory
+//     store plus ring arithmetic.  Here a warp owns sub-path j of 32 consecutive map rows (paths (32 br + lane) g + j): all
+//     lanes share the phase h_j, and the rows of a Philox batch are written as WHOLE 16-byte chunks — one STS.128 per two
+//     FP64 rows / four FP32 rows — at chunk positions that follow from warp-uniform counters.  Rows of a batch that do not
+//     fill a chunk (phase PH = (1 - h_j) mod rows-per-chunk) ride in registers into the next batch (`carry`).
+//     Tiles: [32 lanes][128 B], 128-byte swizzle, two stages; lane 0 stores a finished tile with one tensor store (box =
+//     128 B x 32 map rows) while the warp fills the other stage.  Rows before the first aligned row and after the last
+//     full tile are plain stores.  Needs rows of 4, 8 or 16 bytes and batches of whole chunks (U * ROWB a multiple of 16
+//     dividing 128); the host routes everything else to K2b.
 // ---------------------------------------------------------------------------------------------------
-#define SDE_SIMRT_STAGES 2
-// tile k of the warp is complete in shared memory: g tensor stores by lane 0 (rare: out of line)
-static __device__ __noinline__ void simrt_flush(const sde_tmap *tmx, uint32_t tiles_s, int g, int nrowsD, int tsD, int h1D, int h2D, int h3D,
-                                         int c1, int k) {
-  fence_async_smem();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) {
-    const uint32_t src = tiles_s + (uint32_t)(k % SDE_SIMRT_STAGES) * 4096u;
-    const int rpb128 = (32 / g) * 128;
-    for (int j = 0; j < g; j++) {
-      const int hD = j == 0 ? 0 : (j == 1 ? h1D : (j == 2 ? h2D : h3D));
-      tma_store_2d(tmx, j * nrowsD + hD + k * tsD, c1, src + (uint32_t)(j * rpb128));
-    }
-    bulk_commit();
-  }
-}
-// a lane is about to start writing a tile whose stage was used `SDE_SIMRT_STAGES` tiles ago: lane 0 waits until at
-// most `pending` tensor stores are still reading shared memory
-static __device__ __noinline__ void simrt_acquire(int pending) {
-  if ((threadIdx.x & 31) == 0) {
-    if (pending >= 1) bulk_wait_read<1>(); else bulk_wait_read<0>();
-  }
-  __syncwarp();
-}
-
 template <class Model, typename T, int SCHEME, int V = 1>
-SDE_D void simulate_ref_tma_body(const sde_args &a) {
+SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
-  constexpr int ROWB = D * (int)sizeof(T);
-  constexpr bool OK = (128 % ROWB == 0);
-  constexpr int NSX = SDE_SIMRT_STAGES;
-  constexpr int TS = OK ? 128 / ROWB : 1;     // rows per tile (a power of two)
-  constexpr int TILE = 32 * 128;
-  static_assert(NSX == 2 && TILE == 4096, "ring arithmetic below assumes two 4 KB stages");
   typedef Batch<T, M, V> B;
   constexpr int U = B::U;
+  constexpr int ROWB = D * (int)sizeof(T);
+  constexpr int BB = U * ROWB;                                   // bytes per batch and lane
+  constexpr bool OK = (16 % ROWB == 0) && (BB % 16 == 0) && (128 % BB == 0) && M > 0;
+  constexpr int RPC = OK ? 16 / ROWB : 1;                        // rows per 16-byte chunk
+  constexpr int NCB = OK ? BB / 16 : 1;                          // chunks per batch
+  constexpr int TS = OK ? 128 / ROWB : 1;                        // rows per tile
+  constexpr int EPC = 16 / (int)sizeof(T);                       // elements per chunk
   __shared__ double s_tab[TabSize<T, V>::value];
   extern __shared__ __align__(16) unsigned char s_dyn[];
   load_tables<T, V>(s_tab, a.noise_var);
-  if (!OK || U > TS) return;   // at most one tile boundary per batch (the host routes 8-byte rows here: TS = 16 >= U)
+  if (!OK) return;
   unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned char *tiles = smem + (size_t)wid * (NSX * TILE);
+  constexpr int NSTG = sizeof(T) == 8 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32;   // ring depth: tiles in flight per warp
+  unsigned char *tiles = smem + (size_t)wid * (NSTG * 4096);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
@@ -1661,94 +1665,74 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
   const T dt = (T)a.dt, t0 = (T)a.t0;
   Model::prepare(prm, dt, cst.c);
 
-  const int64_t wbase = ((int64_t)blockIdx.x * (SDE_BLOCK / 32) + wid) * 32;   // a.npaths is a multiple of g
-  if (wbase >= a.npaths) return;
   const int nrows = (int)(a.nsteps + 1);
   const int64_t pitch = (int64_t)nrows * ROWB;
-  const int g = sde_tma_group(pitch), rpb = 32 / g;
-  const int h1 = g > 1 ? sde_tma_head(1, pitch, ROWB) : 0, h2 = g > 2 ? sde_tma_head(2, pitch, ROWB) : 0,
-            h3 = g > 2 ? sde_tma_head(3, pitch, ROWB) : 0;
-  const int h12 = h1 > h2 ? h1 : h2, hmax = h12 > h3 ? h12 : h3;
-  const int ntile = nrows > hmax ? (nrows - hmax) / TS : 0;
-  const int r = (lane % rpb) * g + lane / rpb;        // lane <-> tile row `lane` <-> path wbase + r
-  const int jl = lane / rpb;
-  const int h = jl == 0 ? 0 : (jl == 1 ? h1 : (jl == 2 ? h2 : h3));
-  const int64_t p = wbase + r;
-  const bool live = p < a.npaths;
-  const int c1 = (int)(wbase / g);
+  const int g = sde_tma_group(pitch);
+  const int64_t maprows = a.npaths / g;                           // a.npaths is a multiple of g
+  const int64_t unit = (int64_t)blockIdx.x * (SDE_BLOCK / 32) + wid;
+  const int j = (int)(unit % g);
+  const int64_t br = unit / g;
+  if (br * 32 >= maprows) return;
+  const int64_t mr = br * 32 + lane;
+  const bool live = mr < maprows;
+  const int64_t p = (live ? mr : maprows - 1) * g + j;            // dead lanes shadow a live path (their tile rows are clipped)
+  const int h = sde_tma_head(j, pitch, ROWB);                     // first 16-byte aligned row of this sub-path: warp-uniform
+  const int ntile = nrows > h ? (nrows - h) / TS : 0;
+  const int qend = ntile * TS;                                    // ring rows are q = row - h in [0, qend)
   const sde_tmap *tmx = &a.tm_x;
   T *xp = (T *)a.out + p * (int64_t)nrows * D;
-  const uint32_t swz = (uint32_t)(lane & 7) << 4;
   unsigned char *trow = tiles + lane * 128;
   const uint32_t tiles_s = smem_u32(tiles);
-  const int qend = ntile * TS;
+  const int c0base = j * nrows * D + h * D, c1 = (int)(br * 32);
+  // chunk c (0..7) of this lane's 128-byte tile row under the 128-byte swizzle
+  const uint32_t sw = (uint32_t)(lane & 7);
 
+  auto acquire = [&](int k) {   // about to write tile k: the tensor store of tile k - NSTG must have read its stage
+    if (k >= NSTG) {
+      if (lane == 0) bulk_wait_read<NSTG - 1>();
+      __syncwarp();
+    }
+  };
+  auto flush = [&](int k) {     // tile k is complete in shared memory
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmx, c0base + k * TS * D, c1, tiles_s + (uint32_t)(k % NSTG) * 4096u);
+      bulk_commit();
+    }
+  };
   T x[SDE_MAXD];
 #pragma unroll
   for (int d = 0; d < SDE_MAXD; d++) x[d] = d < D ? (T)a.x0[d] : (T)0;
-
-  // warp-uniform ring state: tiles flushed so far, next tile a lane with h = 0 will start, and the rows at which the
-  // next of each happens (one compare per batch on the common path)
-  constexpr int NEVER = 0x7fffffff;
-  int nflushed = 0, tbeg = 0;
-  int begin_row = ntile > 0 ? 0 : NEVER;                     // tbeg * TS
-  int flush_row = ntile > 0 ? TS - 1 + hmax : NEVER;         // (nflushed + 1) * TS - 1 + hmax
-  // rows up to i_last are about to be written
-  auto begin_check = [&](int i_last) {
-    if (i_last >= begin_row) {
-      if (tbeg >= NSX) simrt_acquire(nflushed - (tbeg - NSX + 1));
-      tbeg++;
-      begin_row = tbeg < ntile ? begin_row + TS : NEVER;
-    }
-  };
-  // rows up to i_last have been written
-  auto flush_check = [&](int i_last) {
-    if (i_last >= flush_row) {
-      simrt_flush(tmx, tiles_s, g, nrows * D, TS * D, h1 * D, h2 * D, h3 * D, c1, nflushed);
-      nflushed++;
-      flush_row = nflushed < ntile ? flush_row + TS : NEVER;
-    }
-  };
-  // store x as the row at byte offset `off` (0..255: stage bit 7, 128-byte swizzled row below) of this lane's ring
-  auto put = [&](uint32_t off) {
-    unsigned char *dst = trow + ((off & 128u) << 5);
-    const uint32_t o = (off & 127u) ^ swz;
-    if (ROWB % 16 == 0) {
-#pragma unroll
-      for (int c = 0; c < ROWB / 16; c++) {
-        union { uint4 q4; T v[16 / sizeof(T)]; } u;
-#pragma unroll
-        for (int e = 0; e < (int)(16 / sizeof(T)); e++) u.v[e] = x[c * (16 / sizeof(T)) + e];
-        *(uint4 *)(dst + (((off & 127u) + 16u * c) ^ swz)) = u.q4;
-      }
-    } else if (ROWB == 8) {
-      union { uint2 q2; T v[8 / sizeof(T)]; } u;
-#pragma unroll
-      for (int e = 0; e < (int)(8 / sizeof(T)); e++) u.v[e] = x[e];
-      *(uint2 *)(dst + o) = u.q2;
-    } else {
-      *(T *)(dst + o) = x[0];
-    }
-  };
-  // general row: ring, or plain store before the first aligned row / after the last full tile
-  auto emit_slow = [&](int i) {
-    begin_check(i);
-    const int q = i - h;
+  // one row, any position: ring (narrow store) or plain global store
+  auto emit_row = [&](int r, const T *v) {
+    const int q = r - h;
     if (q >= 0 && q < qend) {
-      put((uint32_t)(q * ROWB) & 255u);
+      const int k = q / TS, qq = q - k * TS;
+      if (qq == 0) acquire(k);
+      const uint32_t off = (uint32_t)qq * ROWB;
+      unsigned char *dst = trow + (k % NSTG) * 4096 + ((((off >> 4) ^ sw) << 4) | (off & 15u));
+#pragma unroll
+      for (int d = 0; d < D; d++) ((T *)dst)[d] = v[d];
+      if (qq == TS - 1) flush(k);
     } else if (live) {
 #pragma unroll
-      for (int d = 0; d < D; d++) __stcs(xp + (int64_t)i * D + d, x[d]);
+      for (int d = 0; d < D; d++) __stcs(xp + (int64_t)r * D + d, v[d]);
     }
-    flush_check(i);
   };
+  emit_row(0, x);
 
-  emit_slow(0);
   const uint64_t gpath = (uint64_t)(a.path0 + p);
   PhiloxPath pp;
   philox_path_init(gpath, a.stream, ks, pp, sizeof(T) == 8);
   PinnedCoef pc(a.lk, sizeof(T) == 8, V);
-  const int64_t nbatch = (a.nsteps + U - 1) / U;
+  const int64_t nbatch = (a.nsteps + U - 1) / U, nfull = a.nsteps / U;
+  // the last RPC - 1 rows produced (newest last): what a batch leaves over for the next one's first chunk
+  T carry[RPC > 1 ? RPC - 1 : 1][D];
+#pragma unroll
+  for (int c = 0; c < (RPC > 1 ? RPC - 1 : 1); c++)
+#pragma unroll
+    for (int d = 0; d < D; d++) carry[c][d] = x[d];
   auto slow_batch = [&](int64_t it) {
     T dw[B::NZ];
     gen_batch<T, M, V>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
@@ -1757,33 +1741,116 @@ SDE_D void simulate_ref_tma_body(const sde_args &a) {
       const int64_t i = it * U + u;
       if (i < a.nsteps) {
         const T t = t0 + (T)i * dt;
-        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x);
-        emit_slow((int)i + 1);
+        Model::template step<SCHEME>(cst.c, t, dt, dw + u * M, x);
+        emit_row((int)i + 1, x);
+#pragma unroll
+        for (int c = 0; c + 1 < RPC - 1; c++)
+#pragma unroll
+          for (int d = 0; d < D; d++) carry[c][d] = carry[c + 1][d];
+        if (RPC > 1) {
+#pragma unroll
+          for (int d = 0; d < D; d++) carry[RPC - 2][d] = x[d];
+        }
       }
     }
   };
+  // PH rows of a batch (the newest ones) wait in `carry` for the next batch; chunk number of a batch's first chunk:
+  // cs(it) = it * NCB - mshift (q = cs * RPC is the ring row its first element lands on)
+  const int PH = (((1 - h) % RPC) + RPC) % RPC;
+  const int mshift = (PH - (1 - h)) / RPC;                         // 0, or 1 when h >= 2 (4-byte rows)
   int64_t it = 0;
-  for (; it < nbatch && it * U + 1 < hmax; it++) slow_batch(it);          // until every lane is inside its ring
-  {
-    // steady state: all U rows of a batch go into the ring for every lane; bookkeeping once per batch
-    const int64_t it_end = (qend - 1) / U;                                  // rows (it+1)*U <= qend - 1
-    uint32_t off = (uint32_t)(((int)(it * U) + 1 - h) * ROWB) & 255u;
-    for (; it < it_end; it++) {
-      const int i_last = (int)(it * U) + U;
-      begin_check(i_last);
-      T dw[B::NZ];
-      gen_batch<T, M, V>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
+  const int64_t it0 = (mshift + NCB - 1) / NCB;                     // first batch whose chunks are all ring rows (q >= 0)
+  for (; it < it0 && it < nbatch; it++) slow_batch(it);
+  // fast batches: it0 <= it < it1, all chunks inside full tiles and all U steps real
+  int64_t it1 = ((int64_t)ntile * 8 + mshift) / NCB;
+  if (it1 > nfull) it1 = nfull;
+  // one batch in the steady state, phase PHC: NCB aligned 16-byte stores, new carry.  Warp-uniform running state:
+  // cpos = chunk position inside the tile (0..7), kt = tile index, blk = Philox block of the batch, tb = first step
+  const T nv = (T)a.noise_var;
+  int cpos = 0, kt = 0, ks_ = 0;                                   // ks_ = kt % NSTG
+  uint32_t blk = 0;
+  int tb = 0;
+  auto fast_batch = [&](auto phc) {
+    constexpr int PHC = decltype(phc)::value;
+    if (cpos == 0) acquire(kt);
+    T dw[B::NZ];
+    gen_batch<T, M, V>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dw, pc.v);
+    T seq[PHC + U][D];                                             // carry rows, then the U new rows
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const T t = t0 + (T)(it * U + u) * dt;
-        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x);
-        put(off);
-        off = (off + ROWB) & 255u;
-      }
-      flush_check(i_last);
+    for (int c = 0; c < PHC; c++)
+#pragma unroll
+      for (int d = 0; d < D; d++) seq[c][d] = carry[(RPC - 1) - PHC + c][d];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const T t = t0 + (T)(tb + u) * dt;
+      Model::template step<SCHEME>(cst.c, t, dt, dw + u * M, x);
+#pragma unroll
+      for (int d = 0; d < D; d++) seq[PHC + u][d] = x[d];
     }
+    // 16-byte rows with several rows per batch (RPC == 1, NCB > 1: row r is chunk r, one past the batch grid) may cross a
+    // tile boundary INSIDE a batch: boundary checks per chunk there, once per batch everywhere else
+    constexpr bool PERCHUNK = (RPC == 1) && (NCB > 1);
+    if (!PERCHUNK) {
+      unsigned char *stage = trow + ks_ * 4096;
+#pragma unroll
+      for (int c = 0; c < NCB; c++) {
+        union { uint4 q4; T v[EPC]; } w;
+#pragma unroll
+        for (int e = 0; e < EPC; e++) w.v[e] = seq[(c * EPC + e) / D][(c * EPC + e) % D];
+        *(uint4 *)(stage + ((((uint32_t)(cpos + c)) ^ sw) << 4)) = w.q4;
+      }
+      cpos += NCB;
+      if (cpos == 8) {
+        flush(kt);
+        cpos = 0;
+        kt++;
+        ks_ = ks_ + 1 == NSTG ? 0 : ks_ + 1;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NCB; c++) {
+        if (c > 0 && cpos == 0) acquire(kt);
+        union { uint4 q4; T v[EPC]; } w;
+#pragma unroll
+        for (int e = 0; e < EPC; e++) w.v[e] = seq[(c * EPC + e) / D][(c * EPC + e) % D];
+        *(uint4 *)(trow + ks_ * 4096 + ((((uint32_t)cpos) ^ sw) << 4)) = w.q4;
+        if (++cpos == 8) {
+          flush(kt);
+          cpos = 0;
+          kt++;
+          ks_ = ks_ + 1 == NSTG ? 0 : ks_ + 1;
+        }
+      }
+    }
+    if (RPC > 1) {
+#pragma unroll
+      for (int c = 0; c < RPC - 1; c++)
+#pragma unroll
+        for (int d = 0; d < D; d++) carry[c][d] = seq[U + PHC - (RPC - 1) + c >= 0 ? U + PHC - (RPC - 1) + c : 0][d];
+    }
+    blk += (uint32_t)B::NB;
+    tb += U;
+  };
+  auto run_fast = [&](auto phc) {
+    constexpr int PHC = decltype(phc)::value;
+    const int64_t cs0 = it * NCB - mshift;                          // >= 0 by the choice of it0
+    cpos = (int)(cs0 & 7);
+    kt = (int)(cs0 >> 3);
+    ks_ = kt % NSTG;
+    blk = (uint32_t)(it * B::NB);
+    tb = (int)(it * U);
+    for (; it < it1; it++) fast_batch(phc);
+    // the newest PHC rows are still in registers only: rows it*U - PHC + 1 .. it*U (compile-time indices: no local memory)
+#pragma unroll
+    for (int c = 0; c < PHC; c++) emit_row((int)(it * U) - PHC + 1 + c, carry[(RPC - 1) - PHC + c]);
+  };
+  if (it < it1) {
+    if (PH == 0) run_fast(IntC<0>());
+    else if (PH == 1) run_fast(IntC<(RPC > 1 ? 1 : 0)>());
+    else if (PH == 2) run_fast(IntC<(RPC > 2 ? 2 : 0)>());
+    else run_fast(IntC<(RPC > 3 ? 3 : 0)>());
   }
-  for (; it < nbatch; it++) slow_batch(it);                                 // rows after the last full tile
+  for (; it < nbatch; it++) slow_batch(it);                          // partial last tile, tail rows
   if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the stores' reads
   __syncwarp();
   count_nonfinite(a, live, x, D);
@@ -1971,7 +2038,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_##SNAME##_##SUF(    \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, SCH, V>(a); }                  \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_##SNAME##_##SUF(      \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, SCH, V>(a); }
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma2_body<MODEL, T, SCH, V>(a); }
 #define SDE_KERNELS_WIENER(MODEL, TAG, SCH, SNAME, T, SUF)                                                       \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMW_MINBLOCKS) sdek_##TAG##_simw_##SNAME##_##SUF(   \
       const __grid_constant__ sde_args a) { sdeb200::simulate_wiener_body<MODEL, T, SCH>(a); }                  \
@@ -2000,7 +2067,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_exact_##PNAME(                 \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, T, 3>(a); }                      \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_exact_##PNAME(                  \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, T, 3>(a); }
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma2_body<MODEL, T, 3>(a); }
 
 #define SDE_KERNELS_EXACT_V2(MODEL, TAG)                                                                          \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_exact_f64v2(                      \
@@ -2012,7 +2079,7 @@ SDE_D void coef_eval_body(const sde_args &a) {
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMREF_MINB) sdek_##TAG##_simref_exact_f64v2(        \
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_body<MODEL, double, 3, 2>(a); }               \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, SDE_SIMRT_MINB) sdek_##TAG##_simrt_exact_f64v2(          \
-      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma_body<MODEL, double, 3, 2>(a); }
+      const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma2_body<MODEL, double, 3, 2>(a); }
 
 #define SDE_KERNELS_SCHEME(MODEL, TAG, SCH, SNAME)  \
   SDE_KERNELS(MODEL, TAG, SCH, SNAME, double, f64)  \

@@ -146,7 +146,9 @@ int sde_nvrtc_compile_only(const std::string &functor_src, int M, int slot, int 
   }
   const char *hdr_src[] = {sde_embedded_device_cuh, sde_embedded_args_h, sde_embedded_coeffs_inc};
   const char *hdr_name[] = {"sde_device.cuh", "sde_args.h", "sde_coeffs.inc"};
-  std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo",
+  // -default-device: the generic lambdas of the device code carry no execution-space annotation (nvcc infers it, JIT mode
+  // otherwise takes them for host functions)
+  std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device",
                                     math ? "-DSDE_STRICT=1" : "-DSDE_STRICT=0"};
   if (math) opts.push_back("--fmad=false");
   const std::string cpath = cache_path(src, opts);
@@ -245,4 +247,13 @@ extern "C" int sdeb200_debug_nvrtc_check(const char *functor_src, int M, int pre
   }
   if (log && logcap > 0) { strncpy(log, lg.c_str(), logcap - 1); log[logcap - 1] = 0; }
   return total;
+}
+
+// one family of one slot (CPU tests: every family must build under NVRTC, not only under nvcc)
+extern "C" int sdeb200_debug_nvrtc_check_family(const char *functor_src, int M, int slot, int math, int family, char *log, int logcap) {
+  std::vector<char> cubin;
+  std::string lg;
+  int rc = sde_nvrtc_compile_only(functor_src, M, slot, math, family, &cubin, &lg);
+  if (log && logcap > 0) { strncpy(log, lg.c_str(), logcap - 1); log[logcap - 1] = 0; }
+  return rc ? rc : (int)cubin.size();
 }

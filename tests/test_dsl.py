@@ -213,6 +213,25 @@ def test_generated_functor_compiles_for_sm100a(S, name):
         assert rc > 1000, log.value.decode()
 
 
+@pytest.mark.parametrize("name", ["BlackScholes", "Heston"])
+def test_every_kernel_family_builds_under_nvrtc(S, name):
+    """NVRTC (JIT mode) is stricter than nvcc: every kernel family — terminal, RNG-driven trajectories (incl. the TMA
+    store kernel), Wiener-driven, coefficient / logtransition — of every slot (f64 stream v1, f32, f64 stream v2) must
+    compile from the generated functor.  M = 1 covers EM / Milstein / RungeKutta, M = 2 the two-noise batches."""
+    L = S._lib.lib()
+    cls = build(S, name)
+    src = L.sdeb200_model_cuda_source(cls._handle)
+    fn = L.sdeb200_debug_nvrtc_check_family
+    fn.restype = C.c_int
+    log = C.create_string_buffer(1 << 16)
+    for slot in (0, 1, 2):
+        for family in (0, 1, 2, 3):
+            if slot == 2 and family in (2, 3) and name == "Heston":
+                continue     # no noise in these families: stream v2 compiles the same code as slot 0
+            rc = fn(src, cls._M, slot, 0, family, log, len(log))
+            assert rc > 1000, (slot, family, log.value.decode()[:2000])
+
+
 def test_cubin_cache_round_trip(S, tmp_path, monkeypatch):
     """A generated model's cubin is written to $SDEB200_CACHE_DIR and loaded back by the next compile of the same
     source / options; an empty variable turns the cache off; a corrupt entry is ignored."""

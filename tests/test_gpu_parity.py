@@ -3,6 +3,8 @@
 Tolerances (BASELINE.md §5 / north_star): FP64 trajectories on identical Wiener increments <= 1e-12 relative
 (bit-identical in STRICT math), FP32 <= 1e-5 relative; on-device RNG estimates within 3 standard errors.
 """
+import math
+
 import numpy as np
 import pytest
 
@@ -148,11 +150,15 @@ def test_wiener_driven_tma_tiles(gpu, O, name, npaths, nrows, precision, inplace
         assert np.array_equal(x_tma, ref)
 
 
-@pytest.mark.parametrize("npaths,nrows", [(257, 513), (1000, 253), (64, 40), (33, 512), (95, 37), (4097, 65), (32, 300)])
+@pytest.mark.parametrize("npaths,nrows", [(257, 513), (1000, 253), (64, 40), (33, 512), (95, 37), (4097, 65), (32, 300),
+                                          (130, 258), (70, 131), (999, 1027)])
 @pytest.mark.parametrize("precision", ["f64", "f32"])
-def test_reference_order_trajectories_with_tma_stores(gpu, npaths, nrows, precision):
-    """simulate / wiener! / the Exact sampler in the reference's [path][time][D] order: the TMA tensor-store kernels
-    (K2t) write bit for bit what the shared-memory-tile kernels (K2b) write, inside guard zones, for ragged shapes."""
+@pytest.mark.parametrize("rng", [1, 2])
+def test_reference_order_trajectories_with_tma_stores(gpu, npaths, nrows, precision, rng):
+    """simulate / wiener! / the Exact sampler in the reference's [path][time][D] order: the TMA tensor-store kernel (K2u:
+    one sub-path per warp, whole 16-byte chunks per Philox batch, rows of 4 / 8 / 16 bytes, both normal streams) writes bit
+    for bit what the shared-memory-tile kernel (K2b) writes, inside guard zones, for ragged shapes (every phase of the
+    16-byte grid: nrows mod 4, head rows, partial last tiles, leftover paths, partial warps)."""
     import torch
     S = gpu
     tdt = torch.float64 if precision == "f64" else torch.float32
@@ -170,11 +176,12 @@ def test_reference_order_trajectories_with_tma_stores(gpu, npaths, nrows, precis
 
     he, bs = S.Heston(*HESTON_P), S.BlackScholes(*BS_P)
     jobs = [
-        ("bs-milstein", 1, lambda v: S.simulate(bs, S.Milstein(dt), 0.0, 100.0, nsteps, npaths, seed=5, precision=precision, out=v, path_offset=3)),
-        ("heston-em", 2, lambda v: S.simulate(he, S.EulerMaruyama(dt), 0.0, [100.0, 0.4], nsteps, npaths, seed=6, precision=precision, out=v)),
-        ("bs-exact", 1, lambda v: S.simulate(bs, S.Exact(dt), 0.0, 100.0, nsteps, npaths, seed=7, precision=precision, out=v)),
-        ("wiener1", 1, lambda v: S.wiener_(v, dt, seed=8)),
-        ("wiener2", 2, lambda v: S.wiener_(v, dt, seed=9)),
+        ("bs-milstein", 1, lambda v: S.simulate(bs, S.Milstein(dt), 0.0, 100.0, nsteps, npaths, seed=5, precision=precision, out=v, path_offset=3, rng=rng)),
+        ("heston-em", 2, lambda v: S.simulate(he, S.EulerMaruyama(dt), 0.0, [100.0, 0.4], nsteps, npaths, seed=6, precision=precision, out=v, rng=rng)),
+        ("bs-exact", 1, lambda v: S.simulate(bs, S.Exact(dt), 0.0, 100.0, nsteps, npaths, seed=7, precision=precision, out=v, rng=rng)),
+        ("wiener1", 1, lambda v: S.wiener_(v, dt, seed=8, rng=rng)),
+        ("wiener2", 2, lambda v: S.wiener_(v, dt, seed=9, rng=rng)),
+        ("wiener4", 4, lambda v: S.wiener_(v, dt, seed=10, rng=rng)),
     ]
     for tag, D, fn in jobs:
         shape = (npaths, nrows, D) if D > 1 else (npaths, nrows)
@@ -191,7 +198,11 @@ def test_reference_order_trajectories_with_tma_stores(gpu, npaths, nrows, precis
             finally:
                 S.set_tma(True)
         rowb = D * (8 if precision == "f64" else 4)
-        assert res[1][1] == 0 and res[0][1] == (1 if rowb == 8 and nrows >= 2 * (128 // rowb) + 4 else 0), tag
+        M = D                                                       # every job here has as many Wiener processes as states
+        U = (8 // math.gcd(M, 8)) if (rng == 2 and precision == "f64") else ((2 if precision == "f64" else 4) // math.gcd(M, 2 if precision == "f64" else 4))
+        bb = U * rowb
+        takes_tma = 16 % rowb == 0 and bb % 16 == 0 and 128 % bb == 0 and nrows >= 2 * (128 // rowb) + 4 and npaths >= 32
+        assert res[1][1] == 0 and res[0][1] == (1 if takes_tma else 0), (tag, res[0][1], takes_tma)
         assert np.array_equal(res[0][0], res[1][0]), tag
         assert np.isfinite(res[0][0]).all(), tag
 

@@ -121,5 +121,7 @@ out["C4_heston_mlmc_call"] = {
     "cpu_fine_path_steps_per_s": cpu_steps / cpu_s, "cpu_cores": O.max_threads(), "cpu_sample": "levels 1..8 with 1/100 of the paths"}
 print(out["C4_heston_mlmc_call"], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
-print("wrote gpurun_out/configs.json")
+out["normal_stream"] = S.simulation.DEFAULT_RNG or 1
+name = "configs_v%d.json" % (S.simulation.DEFAULT_RNG or 1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
+print("wrote gpurun_out/" + name)
