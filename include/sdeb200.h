@@ -217,6 +217,13 @@ int sdeb200_mlmc_estimate(sdeb200_model *m, const sdeb200_opts *o, const double 
                           int64_t substeps, int64_t level_first, int nlevels, int64_t nsteps,
                           const int64_t *npaths, const sdeb200_payoff *payoff, double *result);
 
+/* sdeb200_mlmc_estimate with one path offset per level (path_offsets[nlevels], added to o->path_offset): the share of one
+ * rank of a multi-process run in which every level is sharded over all ranks. */
+int sdeb200_mlmc_estimate_sharded(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
+                                  int64_t substeps, int64_t level_first, int nlevels, int64_t nsteps,
+                                  const int64_t *npaths, const int64_t *path_offsets, const sdeb200_payoff *payoff,
+                                  double *result);
+
 /* ---- library-owned device buffers: results that stay on the GPU for callers without a device array type ---- */
 /* shape[ndim] in C order (last extent contiguous); pass sdeb200_buffer_ptr(b) wherever a driver takes a data pointer. */
 typedef struct sdeb200_buffer sdeb200_buffer;

@@ -87,6 +87,7 @@ SYMBOLS = {
     "sdeb200_buffer_copy_to_host": (_I, [_VP, _I64, _I64, _VP]),
     "sdeb200_buffer_copy_from_host": (_I, [_VP, _I64, _I64, _VP]),
     "sdeb200_buffer_free": (_I, [_VP]),
+    "sdeb200_mlmc_estimate_sharded": (_I, [_VP, _PO, _PD, _PD, _I64, _I64, _I, _I64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _PP, _PD]),
     "sdeb200_comm_unique_id": (_I, [_VP]),
     "sdeb200_comm_init": (_I, [_VP, _I, _I]),
     "sdeb200_comm_destroy": (_I, []),

@@ -1795,6 +1795,21 @@ extern "C" int sdeb200_mlmc_estimate(sdeb200_model *m, const sdeb200_opts *o, co
   return SDEB200_OK;
 }
 
+// The same with one path offset PER LEVEL: rank r of a multi-process run owns [offset_l, offset_l + npaths_l) of level l
+// (every level sharded over all ranks), so that the run equals the one-GPU run bit for bit.
+extern "C" int sdeb200_mlmc_estimate_sharded(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,
+                                             int64_t substeps, int64_t level_first, int nlevels, int64_t nsteps,
+                                             const int64_t *npaths, const int64_t *path_offsets, const sdeb200_payoff *payoff,
+                                             double *result) {
+  if (!path_offsets) return sdeb200_mlmc_estimate(m, o, params, x0, substeps, level_first, nlevels, nsteps, npaths, payoff, result);
+  if (g_ndev > 1) return fail(SDEB200_E_ARG, "per-level offsets belong to the one-process-per-GPU mode");
+  const int64_t *saved = tl_level_off;
+  tl_level_off = path_offsets;
+  const int rc = sdeb200_mlmc_estimate(m, o, params, x0, substeps, level_first, nlevels, nsteps, npaths, payoff, result);
+  tl_level_off = saved;
+  return rc;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // library-owned device buffers (hard part 4): a caller without a GPU array type of its own — plain Julia
 // without CUDA.jl — keeps large results (C3: 41 GB of trajectories) on the device, passes sdeb200_buffer_ptr(b) wherever

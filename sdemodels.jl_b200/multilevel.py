@@ -167,7 +167,7 @@ class MultilevelEstimate:
 
 
 def ml_estimate(model, s, payoff, t0, x0, nsteps, n, *, seed=0, precision="f64", math="fast", stream=0,
-                path_offset=0, rng=None):
+                path_offset=0, rng=None, level_offsets=None):
     """Multilevel estimator of E[payoff(X_T)]: all levels run concurrently on separate streams, each level ends
     in its own all-reduce.  `n`: this rank's paths per level."""
     from . import simulation as sim
@@ -179,10 +179,13 @@ def ml_estimate(model, s, payoff, t0, x0, nsteps, n, *, seed=0, precision="f64",
     res = np.zeros((nl, 8))
     o = sim._opts(s.scheme, t0, seed, precision, math, stream, path_offset, rng=rng)
     pay = sim._payoff(payoff)
-    _lib.check(L.sdeb200_mlmc_estimate(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
-                                       s.substeps, s.levels[0], nl, int(nsteps),
-                                       counts.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(pay),
-                                       res.ctypes.data_as(_PD)))
+    # level_offsets: this rank's first path of every level (multi-process runs: every level sharded over all ranks)
+    offs = None if level_offsets is None else np.ascontiguousarray(level_offsets, dtype=np.int64)
+    _lib.check(L.sdeb200_mlmc_estimate_sharded(model._handle, C.byref(o), p.ctypes.data_as(_PD), v0.ctypes.data_as(_PD),
+                                               s.substeps, s.levels[0], nl, int(nsteps),
+                                               counts.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               None if offs is None else offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               C.byref(pay), res.ctypes.data_as(_PD)))
     ntot, bad = res[:, 6], res[:, 7]
     good = np.maximum(ntot - bad, 1)
     m = res[:, 0] / good

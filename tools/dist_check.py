@@ -34,7 +34,7 @@ lvl = []
 for i, (a, b) in enumerate(offs):
     sub = S.MultilevelScheme(S.EulerMaruyama(1 / 16), 2, range(0, 5))
     out = np.zeros(8)
-    o = S.simulation._opts(S.subdivide(sub.scheme, 2 ** max(i - 1, 0)) if i else sub.scheme, 0.0, 6, "f64", "fast", i, a)
+    o = S.simulation._opts(S.subdivide(sub.scheme, 2 ** max(i - 1, 0)) if i else sub.scheme, 0.0, 6, "f64", "fast", S.level_stream(0, i), a)
     p = m.params
     PD = C.POINTER(C.c_double)
     x0 = np.array([100.0, 0.4])
