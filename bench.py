@@ -366,7 +366,21 @@ def main():
                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture of the same launch "
                                     "shape, read from profiles/r01d_tma_kernels_ncu_summary.csv; algorithmic 8.208 + 8.208 GB",
                     "workload": "BlackScholes EM FP64, simulate!(x, model, scheme, t0, x0, w) in place, 2e6 paths x 513 rows"}
-                del wbuf
+                # logtransition(model, EulerMaruyama, times, data) along the trajectories just written: the
+                # other streaming kernel of the path — D reads + 1 write per transition
+                lt = torch.empty((nw, rw - 1), dtype=torch.float64, device="cuda")
+                bestl = None
+                for rep in range(3):
+                    S.logtransition(bsm, S.EulerMaruyama(1.0 / (rw - 1)), 0.0, wbuf, out=lt)
+                    t = S.last_kernel_ms()
+                    bestl = t if bestl is None or (rep > 0 and t < bestl) else bestl
+                lbytes = wbuf.numel() * 8 + lt.numel() * 8
+                line["roofline_logtransition"] = {
+                    "kernel": "sdek_bs_f_logt_f64", "bound": "hbm", "achieved": lbytes / bestl / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": lbytes / bestl / 1e6 / hbm_peak, "kernel_ms": bestl, "algorithmic_bytes": lbytes,
+                    "traffic": ncu_traffic("r02c_secondary_ncu_summary.csv", "sdek_bs_f_logt_f64"),
+                    "workload": "BlackScholes FP64 logtransition over 2e6 paths x 513 rows (8.21 GB read, 8.19 GB written)"}
+                del wbuf, lt
             except Exception as err:  # the headline line must not depend on this extra
                 line["roofline_hbm_kernel"] = {"error": str(err)[:200]}
         if world == 1 and not args.no_cpu_baseline:

@@ -625,7 +625,9 @@ static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, 
 
 // reference-order trajectories with TMA tensor stores (simulate_ref_tma_body): per warp a ring of two 4 KB tiles
 static size_t simrt_smem(int precision) {
-  return (size_t)(SDE_BLOCK / 32) * (precision == SDEB200_F64 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32) * 4096 + 1024;
+  const bool manual = precision == SDEB200_F64 ? SDE_SIMRT2_MANUAL_F64 != 0 : SDE_SIMRT2_MANUAL_F32 != 0;
+  const int stages = manual ? 1 : (precision == SDEB200_F64 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32);
+  return (size_t)(SDE_BLOCK / 32) * stages * 4096 + 1024;
 }
 static int64_t simref_grid(int64_t npaths);
 static size_t simref_smem(int D, int precision);

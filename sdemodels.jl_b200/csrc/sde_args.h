@@ -90,6 +90,14 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb) {
 #ifndef SDE_SIMRT2_STAGES_F32
 #define SDE_SIMRT2_STAGES_F32 4
 #endif
+/* K2u: how a finished tile leaves shared memory — 0: one tensor store by lane 0 (asynchronous, STAGES deep ring),
+ * 1: 8 x (LDS.128 + STG.128) by the whole warp (synchronous, one stage) */
+#ifndef SDE_SIMRT2_MANUAL_F64
+#define SDE_SIMRT2_MANUAL_F64 0
+#endif
+#ifndef SDE_SIMRT2_MANUAL_F32
+#define SDE_SIMRT2_MANUAL_F32 0
+#endif
 #ifndef SDE_SIMWT_STAGES
 #define SDE_SIMWT_STAGES 6 /* ring depth of the TMA Wiener-driven kernel: 4 KB per stage and warp */
 #endif

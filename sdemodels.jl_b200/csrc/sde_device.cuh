@@ -457,7 +457,9 @@ SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, const float 
   const float u1 = fmaf(__uint2float_rn(ra), 0x1.0p-32f, 0x1.0p-33f);
 #if SDE_F32_MUFU
   // u1 <= 1 (the largest word rounds to exactly 1): log2 <= 0, so w >= 0 without a clamp; -0 passes through sqrt.approx
-  const float w = (-0x1.62e430p+0f /* 2 ln 2 */ * scale2) * __log2f(u1);
+  float l2;   // u1 >= 2^-33 is a normal number: the flush-to-zero form saves the denormal pre-scaling (3 instructions)
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  const float w = (-0x1.62e430p+0f /* 2 ln 2 */ * scale2) * l2;
   float g, sn, cs;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(w));
   const float ang = __int2float_rn((int32_t)rb) * 0x1.921fb6p-30f;   // 2 pi rb / 2^32 with rb read as signed: [-pi, pi)
@@ -1177,28 +1179,31 @@ SDE_D void simulate_soa_body(const sde_args &a) {
 #pragma unroll
   for (int v = 0; v < VEC; v++) philox_path_init(gpath + (uint64_t)v, a.stream, ks, pp[v], sizeof(T) == 8 && SDE_SOA_PP);
   PinnedCoef pc(a.lk, sizeof(T) == 8, V);
-  const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
-  for (int64_t it = 0; it < nbatch; it++) {
+  const int64_t nbatch = (a.nsteps + B::U - 1) / B::U, nfull = a.nsteps / B::U;
+  const T nv = (T)a.noise_var;
+  auto batch = [&](int64_t it, bool full) {
     T dw[VEC][B::NZ];
 #pragma unroll
     for (int v = 0; v < VEC; v++)
 #if SDE_SOA_PP
-      gen_batch<T, M, V>(pp[v], gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v], pc.v);
+      gen_batch<T, M, V>(pp[v], gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, nv, dw[v], pc.v);
 #else
-      gen_batch<T, M, V>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[v],
+      gen_batch<T, M, V>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, nv, dw[v],
                       sizeof(T) == 8 ? pc.v : nullptr);
 #endif
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t i = it * B::U + u;
-      if (i < a.nsteps) {
+      if (full || i < a.nsteps) {
         const T t = t0 + (T)i * dt;
 #pragma unroll
         for (int v = 0; v < VEC; v++) Model::template step<SCHEME>(cst.c, t, dt, dw[v] + u * (M > 0 ? M : 0), x[v]);
         store_row(i + 1);
       }
     }
-  }
+  };
+  for (int64_t it = 0; it < nfull; it++) batch(it, true);      // whole batches: no per-row bound checks
+  for (int64_t it = nfull; it < nbatch; it++) batch(it, false);
   unsigned bad = 0;
 #pragma unroll
   for (int v = 0; v < VEC; v++) bad += (v < nlive && !all_finite(x[v], D)) ? 1u : 0u;
@@ -1654,7 +1659,10 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   if (!OK) return;
   unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  constexpr int NSTG = sizeof(T) == 8 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32;   // ring depth: tiles in flight per warp
+  // MANUAL: a finished tile leaves through 8 LDS.128 + 8 STG.128 per warp (16-byte chunks, four 128-byte row segments per
+  // warp instruction) instead of a tensor store — synchronous, so one stage is enough
+  constexpr bool MANUAL = sizeof(T) == 8 ? (SDE_SIMRT2_MANUAL_F64 != 0) : (SDE_SIMRT2_MANUAL_F32 != 0);
+  constexpr int NSTG = MANUAL ? 1 : (sizeof(T) == 8 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32);   // ring depth: tiles in flight per warp
   unsigned char *tiles = smem + (size_t)wid * (NSTG * 4096);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
@@ -1688,12 +1696,27 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   const uint32_t sw = (uint32_t)(lane & 7);
 
   auto acquire = [&](int k) {   // about to write tile k: the tensor store of tile k - NSTG must have read its stage
-    if (k >= NSTG) {
-      if (lane == 0) bulk_wait_read<NSTG - 1>();
+    if (!MANUAL && k >= NSTG) {
+      if (lane == 0) bulk_wait_read<(NSTG > 1 ? NSTG - 1 : 0)>();
       __syncwarp();
     }
   };
   auto flush = [&](int k) {     // tile k is complete in shared memory
+    if (MANUAL) {
+      __syncwarp();
+      const unsigned char *src = tiles + (k % NSTG) * 4096;
+      unsigned char *gbase = (unsigned char *)a.out + ((int64_t)j * nrows + h + (int64_t)k * TS) * ROWB;   // sub-path j, first row of tile k
+      const int cc = lane & 7;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int r = 4 * i + (lane >> 3);                                 // tile row = map row br*32 + r
+        const uint4 v = *(const uint4 *)(src + r * 128 + ((cc ^ (r & 7)) << 4));
+        const int64_t mrr = br * 32 + r;
+        if (mrr < maprows) __stcs((uint4 *)(gbase + mrr * (int64_t)g * pitch + cc * 16), v);
+      }
+      __syncwarp();
+      return;
+    }
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -1851,7 +1874,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     else run_fast(IntC<(RPC > 3 ? 3 : 0)>());
   }
   for (; it < nbatch; it++) slow_batch(it);                          // partial last tile, tail rows
-  if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the stores' reads
+  if (!MANUAL && lane == 0) bulk_wait_read<0>();   // shared memory must outlive the stores' reads
   __syncwarp();
   count_nonfinite(a, live, x, D);
 }

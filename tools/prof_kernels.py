@@ -1,4 +1,5 @@
-"""One warm-up + one profiled launch of a secondary kernel (for ncu): mode in {sample32, simsoa64, simsoa32, simw64, mlmc64}."""
+"""One warm-up + one profiled launch of a secondary kernel (for ncu): mode in {sample32, simsoa64, simsoa32, simref64, simref32, simw64, mlmc64, logt64}.
+The normal stream follows SDEB200_RNG (0/1 = v1, 2 = v2)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg, torch
@@ -15,6 +16,18 @@ for rep in range(2):
         n, prec = 2_000_000, ("f64" if mode.endswith("64") else "f32")
         out = torch.empty((513, n), dtype=torch.float64 if prec == "f64" else torch.float32, device="cuda")
         S.simulate(bs, S.Milstein(1 / 512), 0.0, 100.0, 512, n, seed=rep, precision=prec, out=out, layout="soa")
+        work = n * 512
+    elif mode in ("simref64", "simref32"):
+        n, prec = 2_000_000, ("f64" if mode.endswith("64") else "f32")
+        out = torch.empty((n, 513), dtype=torch.float64 if prec == "f64" else torch.float32, device="cuda")
+        S.simulate(bs, S.Milstein(1 / 512), 0.0, 100.0, 512, n, seed=rep, precision=prec, out=out)
+        work = n * 512
+    elif mode == "logt64":
+        n = 2_000_000
+        w = torch.empty((n, 513), dtype=torch.float64, device="cuda")
+        S.simulate(bs, S.EulerMaruyama(1 / 512), 0.0, 100.0, 512, n, seed=rep, out=w)
+        lt = torch.empty((n, 512), dtype=torch.float64, device="cuda")
+        S.logtransition(bs, S.EulerMaruyama(1 / 512), 0.0, w, out=lt)
         work = n * 512
     elif mode == "simw64":
         n = 2_000_000
