@@ -66,7 +66,9 @@ template <int DIM> struct WienerN {
 #define XCOEFFILL2(T, TAG)                              \
   T.coef = (const void *)sdek_##TAG##_coef;             \
   T.logt[0] = (const void *)sdek_##TAG##_logt_f64;      \
-  T.logt[1] = (const void *)sdek_##TAG##_logt_f32;
+  T.logt[1] = (const void *)sdek_##TAG##_logt_f32;      \
+  T.logtt[0] = (const void *)sdek_##TAG##_logtt_f64;    \
+  T.logtt[1] = (const void *)sdek_##TAG##_logtt_f32;
 
 XSCHEME(BlackScholes, TAGGED(bs), 0, em)
 XSCHEME(BlackScholes, TAGGED(bs), 1, mil)

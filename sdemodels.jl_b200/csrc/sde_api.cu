@@ -607,27 +607,29 @@ static int tmap_encoder(tmap_encode_fn *out) {
 // (32/g map rows) x (128 bytes), 128-byte shared-memory swizzle.  npaths must be a multiple of g.
 static_assert(sizeof(sde_tmap) == sizeof(CUtensorMap) && alignof(sde_tmap) == alignof(CUtensorMap), "sde_tmap mirrors CUtensorMap");
 static int make_traj_tmap(sde_tmap *tm, const void *base, int precision, int D, int64_t nrows, int64_t npaths, int grp,
-                          int boxrows = 0) {
+                          int boxrows = 0, int rowbytes = 128) {   // rowbytes: 128 (128-byte swizzle) or 64 (64-byte swizzle)
   tmap_encode_fn enc = nullptr;
   int rc = tmap_encoder(&enc);
   if (rc) return rc;
   const size_t es = precision == SDEB200_F64 ? 8 : 4;
   const cuuint64_t dims[2] = {(cuuint64_t)grp * nrows * D, (cuuint64_t)(npaths / grp)};
   const cuuint64_t strides[1] = {(cuuint64_t)grp * nrows * D * es};
-  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)(boxrows > 0 ? boxrows : 32 / grp)};
+  const cuuint32_t box[2] = {(cuuint32_t)(rowbytes / es), (cuuint32_t)(boxrows > 0 ? boxrows : 32 / grp)};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc((CUtensorMap *)tm, precision == SDEB200_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                   (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   rowbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SDEB200_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
 }
 
 // reference-order trajectories with TMA tensor stores (simulate_ref_tma_body): per warp a ring of two 4 KB tiles
+static int simrt_rowbytes(int precision) { return precision == SDEB200_F64 ? SDE_SIMRT2_ROWB_F64 : SDE_SIMRT2_ROWB_F32; }
 static size_t simrt_smem(int precision) {
   const bool manual = precision == SDEB200_F64 ? SDE_SIMRT2_MANUAL_F64 != 0 : SDE_SIMRT2_MANUAL_F32 != 0;
   const int stages = manual ? 1 : (precision == SDEB200_F64 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32);
-  return (size_t)(SDE_BLOCK / 32) * stages * 4096 + 1024;
+  return (size_t)(SDE_BLOCK / 32) * stages * 32 * simrt_rowbytes(precision) + 1024;
 }
 static int64_t simref_grid(int64_t npaths);
 static size_t simref_smem(int D, int precision);
@@ -652,15 +654,17 @@ static int launch_simref(const void *k, const void *k_tma, int D, int M, int slo
   const int bb = batch_steps(M, slot) * rowb;
   int rc;
   int64_t done = 0;
-  if (k_tma && g_tma_enabled && M > 0 && 16 % rowb == 0 && bb % 16 == 0 && 128 % bb == 0 && ((uintptr_t)out % 16) == 0 &&
+  const int talign = SDE_SIMRT2_ALIGN(simrt_rowbytes(precision));
+  if (k_tma && g_tma_enabled && M > 0 && 16 % rowb == 0 && bb % 16 == 0 && simrt_rowbytes(precision) % bb == 0 &&
+      ((uintptr_t)out % talign) == 0 &&
       nrows >= 2 * (128 / rowb) + 4 && nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
-    const int grp = sde_tma_group(nrows * rowb);
+    const int grp = sde_tma_group(nrows * rowb, talign);
     const int64_t ncov = npaths - npaths % grp;
     if (ncov >= 32) {
       sde_args b = a;
       b.npaths = ncov;
       b.out = out;
-      if ((rc = make_traj_tmap(&b.tm_x, out, precision, D, nrows, ncov, grp, 32))) return rc;
+      if ((rc = make_traj_tmap(&b.tm_x, out, precision, D, nrows, ncov, grp, 32, simrt_rowbytes(precision)))) return rc;
       const int64_t units = (int64_t)grp * cdiv(ncov / grp, 32);     // warps: sub-path j of 32 map rows each
       if ((rc = launch(k_tma, cdiv(units, SDE_BLOCK / 32), &b, st, simrt_smem(precision)))) return rc;
       g.tma_launches++;
@@ -1159,6 +1163,39 @@ static size_t logt_smem(int D, int precision) {
   return (size_t)(SDE_BLOCK / 32) * 32 * (xld + old) * esize(precision);
 }
 
+static size_t logtt_smem() { return (size_t)(SDE_BLOCK / 32) * SDE_LOGTT_STAGES * (4096 + 8) + 1024; }
+// One launch over device buffers: the TMA-load kernel K7t where its tiles apply (D*sizeof(T) | 128, 16-byte aligned input,
+// paths of at least two tiles), the plain tile kernel K7 for everything else and for the npaths % g leftover paths.
+static int launch_logt(const sde_ktable *kt, const sdeb200_model *m, int precision, sde_args a, int64_t nrows, int64_t npaths,
+                       const void *x, void *out, cudaStream_t st) {
+  const size_t es = esize(precision);
+  const int D = m->D, rowb = (int)(D * es);
+  const void *k = kt->logt[precision], *k_tma = kt->logtt[precision];
+  int rc;
+  int64_t done = 0;
+  if (k_tma && g_tma_enabled && 128 % rowb == 0 && ((uintptr_t)x % 16) == 0 && nrows >= 2 * (128 / rowb) + 4 &&
+      nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
+    const int grp = sde_tma_group((int64_t)nrows * rowb);
+    const int64_t ncov = npaths - npaths % grp;
+    if (ncov >= 32) {
+      a.npaths = ncov;
+      a.out = out;
+      a.out2 = (void *)x;
+      if ((rc = make_traj_tmap(&a.tm_w, x, precision, D, nrows, ncov, grp))) return rc;
+      if ((rc = launch(k_tma, cdiv(ncov, SDE_BLOCK), &a, st, logtt_smem()))) return rc;
+      g.tma_launches++;
+      done = ncov;
+    }
+  }
+  if (done < npaths) {
+    a.npaths = npaths - done;
+    a.out = (char *)out + (size_t)done * (nrows - 1) * es;
+    a.out2 = (char *)x + (size_t)done * nrows * D * es;
+    if ((rc = launch(k, cdiv(npaths - done, SDE_BLOCK), &a, st, logt_smem(D, precision)))) return rc;
+  }
+  return 0;
+}
+
 extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, const double *params, int64_t nrows,
                                      int64_t npaths, const void *x, void *out) {
   if (!m || !o) return fail(SDEB200_E_ARG, "null argument");
@@ -1174,7 +1211,6 @@ extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, co
   const sde_ktable *kt;
   if ((rc = get_ktable(m, &oc, &kt, FAM_MISC))) return rc;
   if (npaths == 0 || nrows == 1) return SDEB200_OK;
-  const void *k = kt->logt[o->precision];
   const size_t es = esize(o->precision);
   const size_t xb = (size_t)nrows * m->D * es, ob = (size_t)(nrows - 1) * es;
   if (sharded_call(npaths) && is_host_or_null(x) && is_host_or_null(out))
@@ -1187,13 +1223,9 @@ extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, co
   fill_args(&a, m, &oc, params, x0);
   a.nsteps = nrows - 1;
   const bool xdev = is_device_ptr(x), odev = is_device_ptr(out);
-  const size_t smem = logt_smem(m->D, o->precision);
   if ((rc = timed_begin())) return rc;
   if (xdev && odev) {
-    a.npaths = npaths;
-    a.out = out;
-    a.out2 = (void *)x;
-    if ((rc = launch(k, cdiv(npaths, SDE_BLOCK), &a, st, smem))) return rc;
+    if ((rc = launch_logt(kt, m, o->precision, a, nrows, npaths, x, out, st))) return rc;
   } else {
     int64_t slab = (int64_t)((size_t)(128u << 20) / xb);
     slab = std::max<int64_t>(32, std::min<int64_t>(slab, npaths));
@@ -1210,11 +1242,7 @@ extern "C" int sdeb200_logtransition(sdeb200_model *m, const sdeb200_opts *o, co
       if (used[bi]) CU(cudaStreamWaitEvent(st, g.cdone[bi], 0));
       CU(cudaMemcpyAsync(g.win[bi].p, (const char *)x + (size_t)s0 * xb, (size_t)n * xb,
                          xdev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-      sde_args b = a;
-      b.npaths = n;
-      b.out = g.slab[bi].p;
-      b.out2 = g.win[bi].p;
-      if ((rc = launch(k, cdiv(n, SDE_BLOCK), &b, st, smem))) return rc;
+      if ((rc = launch_logt(kt, m, o->precision, a, nrows, n, g.win[bi].p, g.slab[bi].p, st))) return rc;
       CU(cudaEventRecord(g.kdone[bi], st));
       CU(cudaStreamWaitEvent(g.copy, g.kdone[bi], 0));
       CU(cudaMemcpyAsync((char *)out + (size_t)s0 * ob, g.slab[bi].p, (size_t)n * ob,

@@ -71,19 +71,29 @@ typedef struct {
 #else
 #define SDE_ARGS_HD static inline
 #endif
-SDE_ARGS_HD int sde_tma_group(int64_t pitch_bytes) {
+SDE_ARGS_HD int sde_tma_group(int64_t pitch_bytes, int align = 16) {
   int g = 1;
-  while ((g * pitch_bytes) % 16) g *= 2;
-  return g; /* the pitch is a multiple of sizeof(T) >= 4, hence g <= 4 */
+  while ((g * pitch_bytes) % align) g *= 2;
+  return g; /* the pitch is a multiple of sizeof(T) >= 4, hence g <= align / 4 */
 }
-SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb) {
+SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb, int align = 16) {
   int h = 0;
-  while (((int64_t)j * pitch_bytes + (int64_t)h * rowb) % 16) h++;
+  while (((int64_t)j * pitch_bytes + (int64_t)h * rowb) % align) h++;
   return h;
 }
-/* ring depth of the reference-order TMA store kernel K2u, 4 KB per stage and warp.  Measured on C3 (BlackScholes Milstein,
- * 10^7 x 512): FP64 2 / 3 / 4 stages 3.64 / 3.16 / 3.06 TB/s (114 registers: occupancy pays, not slack), FP32 2.35 / 2.62 / 2.86
- * TB/s (the warp waits on the tensor store of the tile that last used the stage: slack pays) */
+/* alignment K2u gives the row segments of its tiles: 16 bytes is what a tensor store needs; the 64-byte tiles align to the
+ * 32-byte DRAM sector (g <= 8 paths per map row, h_j <= 7), because a 64-byte segment that starts in the middle of a sector
+ * leaves two of its three sectors partial (measured on 513-row FP32 paths: 2.1 TB/s against 3.66 TB/s on 512-row paths) */
+#define SDE_SIMRT2_ALIGN(rowbytes) ((rowbytes) == 64 ? 32 : 16)
+/* bytes per path and tile of K2u (tile = 32 paths x this; 128: 128-byte swizzle, 64: 64-byte swizzle).  The FP32 kernel is bound
+ * by instruction issue, not by its stores (profiles/r02m: 6.91 ms with tensor stores, 6.62 ms with none at all, 6.79 ms with
+ * stores that stay in L2; 12 warps per SM at 16 KB of ring per warp): half-size tiles double the resident warps. */
+#ifndef SDE_SIMRT2_ROWB_F64
+#define SDE_SIMRT2_ROWB_F64 128
+#endif
+#ifndef SDE_SIMRT2_ROWB_F32
+#define SDE_SIMRT2_ROWB_F32 64
+#endif
 #ifndef SDE_SIMRT2_STAGES_F64
 #define SDE_SIMRT2_STAGES_F64 2
 #endif
@@ -97,6 +107,9 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb) {
 #endif
 #ifndef SDE_SIMRT2_MANUAL_F32
 #define SDE_SIMRT2_MANUAL_F32 0
+#endif
+#ifndef SDE_LOGTT_STAGES
+#define SDE_LOGTT_STAGES 4 /* ring depth of the TMA-load logtransition kernel K7t: 4 KB per stage and warp, 3 CTAs per SM */
 #endif
 #ifndef SDE_SIMWT_STAGES
 #define SDE_SIMWT_STAGES 6 /* ring depth of the TMA Wiener-driven kernel: 4 KB per stage and warp */

@@ -131,6 +131,9 @@ SDE_HD double sqrt_core(double v) { return sqrt_from_seed(v, rsqrt_seed(v)); }  
 #ifndef SDE_V2_ROT1
 #define SDE_V2_ROT1 1
 #endif
+#ifndef SDE_SIMRT2_DIAG
+#define SDE_SIMRT2_DIAG 0
+#endif
 #ifndef SDE_SQRT_FAST6
 #define SDE_SQRT_FAST6 1 /* six-operation form (sqrt_from_seed6, <= 1 ulp) instead of the seven-operation one */
 #endif
@@ -349,6 +352,54 @@ SDE_HD double sqrt_from_seed6(double v, double y) {
   const double d = fma(-g, g, v);
   return fma(d, h, g);
 }
+// ---------------------------------------------------------------------------------------------------
+// Natural logarithm and reciprocal for the log-density kernel (K7), built from the pieces of the normal generator:
+//   ln x = e ln2 - (T_j + r Q(r))/2 + 2^-51,  x = 2^e m, m in [1,2), r = m/c_j - 1, |r| <= 2^-8, T_j = 2 ln(1/c_j) + 2^-50
+// (the 128-entry table and the degree-4 Q of stream v1: |r Q(r) + 2 log1p(r)| <= 7.8e-17).  ABSOLUTE error <= 4e-16 for
+// |ln x| <= 1 and <= 1 ulp + 2e-16 beyond; no relative guarantee at x -> 1, which a log-determinant inside
+// -(D log 2π + log det Σ + q)/2 does not need.  9 FP64-pipe instructions instead of the ~30 + branches of the library
+// routine; everything that is not a positive normal number (0, subnormal, negative, inf, NaN) goes to the library routine.
+// 1/x: MUFU.RCP64H seed + two Newton steps (<= 1 ulp for normal x whose reciprocal is normal; library division otherwise).
+// ---------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)   // out of line: the library routines would otherwise be inlined once per unrolled tile row
+static __device__ __noinline__ double log_slow(double x) { return log(x); }
+static __device__ __noinline__ double rcp_slow(double x) { return 1.0 / x; }
+#else
+static inline double log_slow(double x) { return log(x); }
+static inline double rcp_slow(double x) { return 1.0 / x; }
+#endif
+SDE_HD bool log_fast_ok(double x) { return double2hi(x) - 0x00100000u < 0x7FE00000u; }      // positive normal number
+SDE_HD double log_fast_core(double x, const double *ltab /* SDE_LOG_TAB_INIT: {1/c_j, 2 ln(1/c_j) + 2^-50}, j < 128 */) {
+  const uint32_t h = double2hi(x);      // branch-free; garbage (but no fault: the index is masked) unless log_fast_ok(x)
+  const double m = hilo2double((h & 0x000FFFFFu) | 0x3FF00000u, double2lo(x));
+  const int j = (int)((h >> 13) & 0x7Fu);
+  const double kd = (double)((int)(h >> 20) - 1023);
+  const double inv_c = ltab[2 * j], tl = ltab[2 * j + 1];
+  const double rr = fma(m, inv_c, -1.0);
+  double q = SDE_K(SDE_LOG_C4);
+  q = fma(q, rr, SDE_K(SDE_LOG_C3));
+  q = fma(q, rr, SDE_K(SDE_LOG_C2));
+  q = fma(q, rr, SDE_K(SDE_LOG_C1));
+  q = fma(q, rr, -2.0);
+  const double w = fma(rr, q, tl);                                 // -2 ln m + 2^-50
+  return fma(kd, 0.5 * SDE_TWO_LN2_V, fma(w, -0.5, 0x1.0p-51));
+}
+SDE_HD double log_fast(double x, const double *ltab) { return log_fast_ok(x) ? log_fast_core(x, ltab) : log_slow(x); }
+SDE_HD bool rcp_fast_ok(double x) { return (double2hi(x) & 0x7FFFFFFFu) - 0x00200000u < 0x7FC00000u; }   // |x| in [2^-1021, 2^1021)
+SDE_HD double rcp_fast_core(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  double y = hilo2double(double2hi(1.0 / hilo2double(double2hi(x), 0)), 0);
+#endif
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);                                                // 2^-40
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+SDE_HD double rcp_fast(double x) { return rcp_fast_ok(x) ? rcp_fast_core(x) : rcp_slow(x); }
+
 //   lk (v2, fine) = noise_var * {Q2_0, Q2_1, Q2_2, Q2_3, -, 2 ln 2};  tab = [0, 2 LOGN): log pairs, then the rotation pairs
 SDE_HD void make_log_consts_v2(double dt, double *lk) {
 #if SDE_V2_FINE
@@ -1648,10 +1699,14 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   constexpr int U = B::U;
   constexpr int ROWB = D * (int)sizeof(T);
   constexpr int BB = U * ROWB;                                   // bytes per batch and lane
-  constexpr bool OK = (16 % ROWB == 0) && (BB % 16 == 0) && (128 % BB == 0) && M > 0;
+  constexpr int TROWB = sizeof(T) == 8 ? SDE_SIMRT2_ROWB_F64 : SDE_SIMRT2_ROWB_F32;   // bytes per path and tile (128 or 64)
+  static_assert(TROWB == 128 || TROWB == 64, "tile rows of 128 bytes (128-byte swizzle) or 64 bytes (64-byte swizzle)");
+  constexpr int NCH = TROWB / 16;                                // 16-byte chunks per tile row
+  constexpr int TILEB = 32 * TROWB;                              // bytes per tile
+  constexpr bool OK = (16 % ROWB == 0) && (BB % 16 == 0) && (TROWB % BB == 0) && M > 0;
   constexpr int RPC = OK ? 16 / ROWB : 1;                        // rows per 16-byte chunk
   constexpr int NCB = OK ? BB / 16 : 1;                          // chunks per batch
-  constexpr int TS = OK ? 128 / ROWB : 1;                        // rows per tile
+  constexpr int TS = OK ? TROWB / ROWB : 1;                      // rows per tile
   constexpr int EPC = 16 / (int)sizeof(T);                       // elements per chunk
   __shared__ double s_tab[TabSize<T, V>::value];
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -1663,7 +1718,8 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   // warp instruction) instead of a tensor store — synchronous, so one stage is enough
   constexpr bool MANUAL = sizeof(T) == 8 ? (SDE_SIMRT2_MANUAL_F64 != 0) : (SDE_SIMRT2_MANUAL_F32 != 0);
   constexpr int NSTG = MANUAL ? 1 : (sizeof(T) == 8 ? SDE_SIMRT2_STAGES_F64 : SDE_SIMRT2_STAGES_F32);   // ring depth: tiles in flight per warp
-  unsigned char *tiles = smem + (size_t)wid * (NSTG * 4096);
+  static_assert(!MANUAL || TROWB == 128, "the manual flush is written for 128-byte tile rows");
+  unsigned char *tiles = smem + (size_t)wid * (NSTG * TILEB);
   PhiloxKeys ks;
   philox_expand(a.seed_lo, a.seed_hi, ks);
   Consts<T> cst;
@@ -1675,7 +1731,8 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 
   const int nrows = (int)(a.nsteps + 1);
   const int64_t pitch = (int64_t)nrows * ROWB;
-  const int g = sde_tma_group(pitch);
+  constexpr int TALIGN = SDE_SIMRT2_ALIGN(TROWB);
+  const int g = sde_tma_group(pitch, TALIGN);
   const int64_t maprows = a.npaths / g;                           // a.npaths is a multiple of g
   const int64_t unit = (int64_t)blockIdx.x * (SDE_BLOCK / 32) + wid;
   const int j = (int)(unit % g);
@@ -1684,16 +1741,17 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   const int64_t mr = br * 32 + lane;
   const bool live = mr < maprows;
   const int64_t p = (live ? mr : maprows - 1) * g + j;            // dead lanes shadow a live path (their tile rows are clipped)
-  const int h = sde_tma_head(j, pitch, ROWB);                     // first 16-byte aligned row of this sub-path: warp-uniform
+  const int h = sde_tma_head(j, pitch, ROWB, TALIGN);             // first aligned row of this sub-path: warp-uniform
   const int ntile = nrows > h ? (nrows - h) / TS : 0;
   const int qend = ntile * TS;                                    // ring rows are q = row - h in [0, qend)
   const sde_tmap *tmx = &a.tm_x;
   T *xp = (T *)a.out + p * (int64_t)nrows * D;
-  unsigned char *trow = tiles + lane * 128;
+  unsigned char *trow = tiles + lane * TROWB;
   const uint32_t tiles_s = smem_u32(tiles);
   const int c0base = j * nrows * D + h * D, c1 = (int)(br * 32);
-  // chunk c (0..7) of this lane's 128-byte tile row under the 128-byte swizzle
-  const uint32_t sw = (uint32_t)(lane & 7);
+  // chunk c of this lane's tile row under the shared-memory swizzle: 128-byte mode XORs address bits 4-6 with bits 7-9
+  // (= lane & 7 for 128-byte rows), 64-byte mode bits 4-5 with bits 7-8 (= (lane >> 1) & 3 for 64-byte rows)
+  const uint32_t sw = TROWB == 128 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
 
   auto acquire = [&](int k) {   // about to write tile k: the tensor store of tile k - NSTG must have read its stage
     if (!MANUAL && k >= NSTG) {
@@ -1704,7 +1762,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   auto flush = [&](int k) {     // tile k is complete in shared memory
     if (MANUAL) {
       __syncwarp();
-      const unsigned char *src = tiles + (k % NSTG) * 4096;
+      const unsigned char *src = tiles + (k % NSTG) * TILEB;
       unsigned char *gbase = (unsigned char *)a.out + ((int64_t)j * nrows + h + (int64_t)k * TS) * ROWB;   // sub-path j, first row of tile k
       const int cc = lane & 7;
 #pragma unroll
@@ -1720,7 +1778,12 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tmx, c0base + k * TS * D, c1, tiles_s + (uint32_t)(k % NSTG) * 4096u);
+#if SDE_SIMRT2_DIAG == 1      /* timing experiment only (wrong results): no tensor store at all = the kernel's compute ceiling */
+#elif SDE_SIMRT2_DIAG == 2    /* timing experiment only: every warp rewrites its first two tiles = tensor stores that stay in L2 */
+      tma_store_2d(tmx, c0base + (k & 1) * TS * D, c1, tiles_s + (uint32_t)(k % NSTG) * (uint32_t)TILEB);
+#else
+      tma_store_2d(tmx, c0base + k * TS * D, c1, tiles_s + (uint32_t)(k % NSTG) * (uint32_t)TILEB);
+#endif
       bulk_commit();
     }
   };
@@ -1734,7 +1797,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
       const int k = q / TS, qq = q - k * TS;
       if (qq == 0) acquire(k);
       const uint32_t off = (uint32_t)qq * ROWB;
-      unsigned char *dst = trow + (k % NSTG) * 4096 + ((((off >> 4) ^ sw) << 4) | (off & 15u));
+      unsigned char *dst = trow + (k % NSTG) * TILEB + ((((off >> 4) ^ sw) << 4) | (off & 15u));
 #pragma unroll
       for (int d = 0; d < D; d++) ((T *)dst)[d] = v[d];
       if (qq == TS - 1) flush(k);
@@ -1785,7 +1848,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   const int64_t it0 = (mshift + NCB - 1) / NCB;                     // first batch whose chunks are all ring rows (q >= 0)
   for (; it < it0 && it < nbatch; it++) slow_batch(it);
   // fast batches: it0 <= it < it1, all chunks inside full tiles and all U steps real
-  int64_t it1 = ((int64_t)ntile * 8 + mshift) / NCB;
+  int64_t it1 = ((int64_t)ntile * NCH + mshift) / NCB;
   if (it1 > nfull) it1 = nfull;
   // one batch in the steady state, phase PHC: NCB aligned 16-byte stores, new carry.  Warp-uniform running state:
   // cpos = chunk position inside the tile (0..7), kt = tile index, blk = Philox block of the batch, tb = first step
@@ -1814,7 +1877,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     // tile boundary INSIDE a batch: boundary checks per chunk there, once per batch everywhere else
     constexpr bool PERCHUNK = (RPC == 1) && (NCB > 1);
     if (!PERCHUNK) {
-      unsigned char *stage = trow + ks_ * 4096;
+      unsigned char *stage = trow + ks_ * TILEB;
 #pragma unroll
       for (int c = 0; c < NCB; c++) {
         union { uint4 q4; T v[EPC]; } w;
@@ -1823,7 +1886,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
         *(uint4 *)(stage + ((((uint32_t)(cpos + c)) ^ sw) << 4)) = w.q4;
       }
       cpos += NCB;
-      if (cpos == 8) {
+      if (cpos == NCH) {
         flush(kt);
         cpos = 0;
         kt++;
@@ -1836,8 +1899,8 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
         union { uint4 q4; T v[EPC]; } w;
 #pragma unroll
         for (int e = 0; e < EPC; e++) w.v[e] = seq[(c * EPC + e) / D][(c * EPC + e) % D];
-        *(uint4 *)(trow + ks_ * 4096 + ((((uint32_t)cpos) ^ sw) << 4)) = w.q4;
-        if (++cpos == 8) {
+        *(uint4 *)(trow + ks_ * TILEB + ((((uint32_t)cpos) ^ sw) << 4)) = w.q4;
+        if (++cpos == NCH) {
           flush(kt);
           cpos = 0;
           kt++;
@@ -1857,8 +1920,8 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   auto run_fast = [&](auto phc) {
     constexpr int PHC = decltype(phc)::value;
     const int64_t cs0 = it * NCB - mshift;                          // >= 0 by the choice of it0
-    cpos = (int)(cs0 & 7);
-    kt = (int)(cs0 >> 3);
+    cpos = (int)(cs0 % NCH);
+    kt = (int)(cs0 / NCH);
     ks_ = kt % NSTG;
     blk = (uint32_t)(it * B::NB);
     tb = (int)(it * U);
@@ -1886,16 +1949,38 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 //     in double for both storage precisions (it is free next to the memory traffic).
 //       μ = x0 + drift Δt;  Σ = Δt σ σ';  z = μ - x1;  -0.5 (D log 2π + log det Σ + z' Σ⁻¹ z)
 // ---------------------------------------------------------------------------------------------------
-template <int D> SDE_D double gauss_logpdf_terms(const double (&S)[SDE_MAXD][SDE_MAXD], const double *z) {
+#ifndef SDE_LOGT_FASTMATH
+#define SDE_LOGT_FASTMATH 1 /* log_fast / rcp_fast instead of the library log and IEEE divisions for D <= 2 (ncu of the library form:
+                               FP64 pipe 42 %, issue slots 63 %, 2.7 TB/s — bound by those two, not by its loads) */
+#endif
+// Every operation of the D <= 2 forms is written with an explicit rounding (no contraction): the branch-free twin below,
+// the batched callers and the library fallback then agree bit for bit, and the order is the oracle's.
+template <int D> SDE_D double gauss_logpdf_terms(const double (&S)[SDE_MAXD][SDE_MAXD], const double *z, const double *ltab) {
   double logdet, q;
+  constexpr double LOG2PI = 0x1.d67f1c864beb5p+0;
   if (D == 1) {
+#if SDE_LOGT_FASTMATH
+    logdet = log_fast(S[0][0], ltab);
+    q = __dmul_rn(z[0], __dmul_rn(z[0], rcp_fast(S[0][0])));
+#else
     logdet = log(S[0][0]);
-    q = z[0] * (z[0] / S[0][0]);
+    q = __dmul_rn(z[0], z[0] / S[0][0]);
+#endif
+    return __dmul_rn(-0.5, __dadd_rn(__dadd_rn(LOG2PI, logdet), q));
   } else if (D == 2) {  // closed forms (StaticArrays: det = a11 a22 - a12 a21, Cramer solve)
-    const double det = S[0][0] * S[1][1] - S[0][1] * S[1][0];
-    const double y0 = (S[1][1] * z[0] - S[0][1] * z[1]) / det, y1 = (S[0][0] * z[1] - S[1][0] * z[0]) / det;
+    const double det = __dsub_rn(__dmul_rn(S[0][0], S[1][1]), __dmul_rn(S[0][1], S[1][0]));
+    const double n0 = __dsub_rn(__dmul_rn(S[1][1], z[0]), __dmul_rn(S[0][1], z[1]));
+    const double n1 = __dsub_rn(__dmul_rn(S[0][0], z[1]), __dmul_rn(S[1][0], z[0]));
+#if SDE_LOGT_FASTMATH
+    const double rd = rcp_fast(det);
+    const double y0 = __dmul_rn(n0, rd), y1 = __dmul_rn(n1, rd);
+    logdet = log_fast(det, ltab);
+#else
+    const double y0 = n0 / det, y1 = n1 / det;
     logdet = log(det);
-    q = z[0] * y0 + z[1] * y1;
+#endif
+    q = __dadd_rn(__dmul_rn(z[0], y0), __dmul_rn(z[1], y1));
+    return __dmul_rn(-0.5, __dadd_rn(__dadd_rn(2.0 * LOG2PI, logdet), q));
   } else {  // Cholesky
     double L[SDE_MAXD][SDE_MAXD], y[SDE_MAXD];
     double ld = 0.0;
@@ -1929,15 +2014,79 @@ template <int D> SDE_D double gauss_logpdf_terms(const double (&S)[SDE_MAXD][SDE
   }
   return -0.5 * (((double)D * 0x1.d67f1c864beb5p+0 /* log 2π */ + logdet) + q);
 }
+// The same values without a branch (D <= 2, fast math): `ok` is cleared when an argument leaves the range of log_fast_core /
+// rcp_fast_core and the caller then takes gauss_logpdf_terms for the whole batch.  Several independent transitions evaluated
+// side by side in one basic block give the FP64 pipe the instruction-level parallelism a single dependent chain does not.
+template <int D> SDE_D double gauss_logpdf_terms_nb(const double (&S)[SDE_MAXD][SDE_MAXD], const double *z, const double *ltab, bool &ok) {
+  constexpr double LOG2PI = 0x1.d67f1c864beb5p+0;
+#if SDE_LOGT_FASTMATH
+  if (D == 1) {
+    ok = ok && log_fast_ok(S[0][0]) && rcp_fast_ok(S[0][0]);
+    const double logdet = log_fast_core(S[0][0], ltab);
+    const double q = __dmul_rn(z[0], __dmul_rn(z[0], rcp_fast_core(S[0][0])));
+    return __dmul_rn(-0.5, __dadd_rn(__dadd_rn(LOG2PI, logdet), q));
+  } else if (D == 2) {
+    const double det = __dsub_rn(__dmul_rn(S[0][0], S[1][1]), __dmul_rn(S[0][1], S[1][0]));
+    const double n0 = __dsub_rn(__dmul_rn(S[1][1], z[0]), __dmul_rn(S[0][1], z[1]));
+    const double n1 = __dsub_rn(__dmul_rn(S[0][0], z[1]), __dmul_rn(S[1][0], z[0]));
+    ok = ok && log_fast_ok(det) && rcp_fast_ok(det);
+    const double rd = rcp_fast_core(det);
+    const double y0 = __dmul_rn(n0, rd), y1 = __dmul_rn(n1, rd);
+    const double logdet = log_fast_core(det, ltab);
+    const double q = __dadd_rn(__dmul_rn(z[0], y0), __dmul_rn(z[1], y1));
+    return __dmul_rn(-0.5, __dadd_rn(__dadd_rn(2.0 * LOG2PI, logdet), q));
+  }
+#endif
+  return gauss_logpdf_terms<D>(S, z, ltab);
+}
+// NB consecutive transitions of one path: xs[0 .. NB] are rows row1 - 1 .. row1 + NB - 1, res[i] the log-density of xs[i + 1]
+// given xs[i].  μ, Σ and z are formed once; the result of a transition does not depend on how rows are batched.
+template <class Model, int NB>
+SDE_D void logt_batch(const double *prm, double t0, double dt, int row1, const double (&xs)[NB + 1][SDE_MAXD], const double *ltab,
+                      double (&res)[NB]) {
+  constexpr int D = Model::D, M = Model::M;
+  double S[NB][SDE_MAXD][SDE_MAXD], z[NB][SDE_MAXD];
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    double mu[SDE_MAXD], sig[SDE_MAXD * SDE_MAXM];
+#pragma unroll
+    for (int q = 0; q < SDE_MAXD * SDE_MAXM; q++) sig[q] = 0.0;
+    Model::coefficients(prm, t0 + (double)(row1 + i - 1) * dt, xs[i], mu, sig);
+#pragma unroll
+    for (int p = 0; p < D; p++) z[i][p] = (xs[i][p] + mu[p] * dt) - xs[i + 1][p];
+#pragma unroll
+    for (int p = 0; p < D; p++)
+#pragma unroll
+      for (int q = 0; q < D; q++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          const double term = (dt * sig[p * SDE_MAXM + j]) * sig[q * SDE_MAXM + j];
+          acc = j == 0 ? term : acc + term;
+        }
+        S[i][p][q] = acc;
+      }
+  }
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < NB; i++) res[i] = gauss_logpdf_terms_nb<D>(S[i], z[i], ltab, ok);
+  if (!ok) {
+#pragma unroll
+    for (int i = 0; i < NB; i++) res[i] = gauss_logpdf_terms<D>(S[i], z[i], ltab);
+  }
+}
 
 template <class Model, typename T>
 SDE_D void logtransition_body(const sde_args &a) {
-  constexpr int D = Model::D, M = Model::M;
+  constexpr int D = Model::D;
   constexpr int TS = (SDE_SIMW_ROWBYTES / (int)sizeof(T)) / D;  // rows per tile
   constexpr int XROW = TS * D, XLD = XROW | 1, OLD = TS | 1;
   extern __shared__ __align__(16) unsigned char s_dyn[];   // [warps][32][XLD] then [warps][32][OLD]
   T (*s_x)[32 * XLD] = (T (*)[32 * XLD])s_dyn;
   T (*s_o)[32 * OLD] = (T (*)[32 * OLD])((T *)s_dyn + (SDE_BLOCK / 32) * 32 * XLD);
+  __shared__ double s_ltab[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ltab[i] = g_log_tab[i];
+  __syncthreads();
   double prm[SDE_MAXP];
 #pragma unroll
   for (int i = 0; i < SDE_MAXP; i++) prm[i] = a.params[i];
@@ -1952,38 +2101,40 @@ SDE_D void logtransition_body(const sde_args &a) {
   double xp[SDE_MAXD];
 #pragma unroll
   for (int d = 0; d < SDE_MAXD; d++) xp[d] = 0.0;
+  constexpr int NB = 4;   // transitions evaluated side by side (instruction-level parallelism for the FP64 pipe)
   for (int64_t row0 = 0; row0 < nrows; row0 += TS) {
     const int nr = (int)((nrows - row0) < TS ? (nrows - row0) : TS);
     tile_load<T, XROW, XLD>(tx, xin + (wbase * nrows + row0) * D, nrows * D, nlive, nr * D, lane);
     __syncwarp();
-    for (int i = 0; i < nr; i++) {
-      const int64_t row = row0 + i;
-      double xc[SDE_MAXD];
+    int i = 0;
+    if (row0 == 0) {   // row 0 starts the path: no transition ends there
 #pragma unroll
-      for (int d = 0; d < SDE_MAXD; d++) xc[d] = d < D ? (double)tx[lane * XLD + i * D + d] : 0.0;
-      if (row > 0) {
-        double mu[SDE_MAXD], sig[SDE_MAXD * SDE_MAXM], S[SDE_MAXD][SDE_MAXD], z[SDE_MAXD];
+      for (int d = 0; d < SDE_MAXD; d++) xp[d] = d < D ? (double)tx[lane * XLD + d] : 0.0;
+      i = 1;
+    }
+    if (lane >= nlive) i = nr;   // rows of paths past the end are zero-filled: nothing to evaluate
+    for (; i + NB <= nr; i += NB) {
+      double xs[NB + 1][SDE_MAXD], res[NB];
 #pragma unroll
-        for (int q = 0; q < SDE_MAXD * SDE_MAXM; q++) sig[q] = 0.0;
-        Model::coefficients(prm, a.t0 + (double)(row - 1) * a.dt, xp, mu, sig);
+      for (int d = 0; d < SDE_MAXD; d++) xs[0][d] = xp[d];
 #pragma unroll
-        for (int p = 0; p < D; p++) z[p] = (xp[p] + mu[p] * a.dt) - xc[p];
+      for (int b = 0; b < NB; b++)
 #pragma unroll
-        for (int p = 0; p < D; p++)
+        for (int d = 0; d < SDE_MAXD; d++) xs[b + 1][d] = d < D ? (double)tx[lane * XLD + (i + b) * D + d] : 0.0;
+      logt_batch<Model, NB>(prm, a.t0, a.dt, (int)row0 + i, xs, s_ltab, res);
 #pragma unroll
-          for (int q = 0; q < D; q++) {
-            double acc = 0.0;
+      for (int b = 0; b < NB; b++) to[lane * OLD + i + b] = (T)res[b];   // transition ending at tile row i + b
 #pragma unroll
-            for (int j = 0; j < M; j++) {
-              const double term = (a.dt * sig[p * SDE_MAXM + j]) * sig[q * SDE_MAXM + j];
-              acc = j == 0 ? term : acc + term;
-            }
-            S[p][q] = acc;
-          }
-        to[lane * OLD + i] = (T)gauss_logpdf_terms<D>(S, z);  // transition ending at tile row i
-      }
+      for (int d = 0; d < SDE_MAXD; d++) xp[d] = xs[NB][d];              // carried into the next tile as well
+    }
+    for (; i < nr; i++) {
+      double xs[2][SDE_MAXD], res[1];
 #pragma unroll
-      for (int d = 0; d < SDE_MAXD; d++) xp[d] = xc[d];  // carried into the next tile as well
+      for (int d = 0; d < SDE_MAXD; d++) { xs[0][d] = xp[d]; xs[1][d] = d < D ? (double)tx[lane * XLD + i * D + d] : 0.0; }
+      logt_batch<Model, 1>(prm, a.t0, a.dt, (int)row0 + i, xs, s_ltab, res);
+      to[lane * OLD + i] = (T)res[0];
+#pragma unroll
+      for (int d = 0; d < SDE_MAXD; d++) xp[d] = xs[1][d];
     }
     __syncwarp();
     // tile row i holds the transition (row0 + i - 1) -> (row0 + i): output column row0 + i - 1; row 0 has none
@@ -1991,6 +2142,184 @@ SDE_D void logtransition_body(const sde_args &a) {
     if (nr > i0)
       tile_store<T, TS, OLD>(to + i0, out + wbase * (nrows - 1) + (row0 - 1 + i0), nrows - 1, nlive, nr - i0, lane);
     __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K7t logtransition on TMA tensor LOADS (same results as K7, bit for bit): a warp owns 32 paths; lane 0 moves tiles of x
+//     global -> shared through a ring of SDE_LOGTT_STAGES stages (geometry of K3t: g paths per map row, head rows h_j,
+//     128-byte swizzle; NST - 1 loads in flight per warp), every lane walks its own path in the swizzled tile and leaves
+//     the log-density of the transition ENDING at tile row i in element slot i of its tile row (slot i lies at or before
+//     row i's own bytes, which are in registers by then), and the warp writes the TS results of two / one / ... paths
+//     per instruction as whole row segments of out [path][row-1].  The outputs' pitch (nrows-1) differs from the inputs',
+//     so their 16-byte phases differ too: plain coalesced stores, no tensor map.  Head rows (< h_j <= 3) are plain
+//     accesses, the rows after the last full tile go through one cooperative shared-memory tile like K3t's.
+//     Needs D*sizeof(T) | 128; the host routes everything else and the npaths % g leftover to K7.
+// ---------------------------------------------------------------------------------------------------
+template <class Model, typename T>
+SDE_D void logtransition_tma_body(const sde_args &a) {
+  constexpr int D = Model::D;
+  constexpr int ROWB = D * (int)sizeof(T);
+  constexpr bool OK = (128 % ROWB == 0);
+  if (!OK) return;
+  constexpr int NST = SDE_LOGTT_STAGES;
+  constexpr int TS = OK ? 128 / ROWB : 1;                 // rows per tile
+  constexpr int NB = TS < 4 ? TS : 4;                     // transitions evaluated side by side
+  constexpr int NQ = OK ? NB * ROWB / 16 : 1;             // 16-byte chunks per batch (ROWB >= 4, NB = 4 or ROWB >= 64)
+  constexpr int TILE = 32 * 128;
+  constexpr int HMAX = ROWB % 16 == 0 ? 0 : (ROWB % 8 == 0 ? 1 : 3);
+  constexpr int TOUT = TS + HMAX, TROW = TOUT * D, TLD = TROW | 1;   // the cooperative tail tile [32][TLD]
+  static_assert(!OK || NST < 2 || 32 * TLD * (int)sizeof(T) <= 2 * TILE, "tail tile does not fit");
+  __shared__ double s_ltab[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_ltab[i] = g_log_tab[i];
+  __syncthreads();
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *tiles = smem + (size_t)wid * (NST * TILE);
+  uint64_t *bars = (uint64_t *)(smem + (size_t)(SDE_BLOCK / 32) * (NST * TILE)) + wid * NST;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++) mbar_init(smem_u32(bars + s), 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const int64_t wbase = ((int64_t)blockIdx.x * (SDE_BLOCK / 32) + wid) * 32;   // a.npaths is a multiple of g
+  if (wbase >= a.npaths) return;
+  const int nrows = (int)(a.nsteps + 1);
+  const int64_t pitch = (int64_t)nrows * ROWB;
+  const int g = sde_tma_group(pitch), lg = g == 1 ? 0 : (g == 2 ? 1 : 2), rpb = 32 >> lg;
+  const int h0 = 0, h1 = g > 1 ? sde_tma_head(1, pitch, ROWB) : 0, h2 = g > 2 ? sde_tma_head(2, pitch, ROWB) : 0,
+            h3 = g > 2 ? sde_tma_head(3, pitch, ROWB) : 0;
+  auto hh = [&](int j) { return j == 0 ? h0 : (j == 1 ? h1 : (j == 2 ? h2 : h3)); };
+  const int h12 = h1 > h2 ? h1 : h2, hmax = h12 > h3 ? h12 : h3;
+  const int ntile = nrows > hmax ? (nrows - hmax) / TS : 0;
+  const int r = (lane & (rpb - 1)) * g + (lane >> (5 - lg));   // lane <-> tile row `lane` <-> path wbase + r
+  const int h = hh(lane >> (5 - lg));
+  const int64_t p = wbase + r;
+  const bool live = p < a.npaths;
+  const int c1 = (int)(wbase >> lg);
+  const sde_tmap *tmw = &a.tm_w;
+  auto issue_load = [&](int k) {  // lane 0
+    if (k < ntile) {
+      const int s = k % NST;
+      const uint32_t bar = smem_u32(bars + s);
+      mbar_expect_tx(bar, TILE);
+      for (int j = 0; j < g; j++)
+        tma_load_2d(smem_u32(tiles + s * TILE + j * rpb * 128), tmw, j * nrows * D + (hh(j) + k * TS) * D, c1, bar);
+    }
+  };
+  if (lane == 0)
+    for (int k = 0; k < NST - 1; k++) issue_load(k);
+
+  double prm[SDE_MAXP];
+#pragma unroll
+  for (int i = 0; i < SDE_MAXP; i++) prm[i] = a.params[i];
+  const T *xin = (const T *)a.out2 + p * (int64_t)nrows * D;
+  T *out = (T *)a.out;
+  T *op = out + p * (int64_t)(nrows - 1);
+  double xp[SDE_MAXD];
+#pragma unroll
+  for (int d = 0; d < SDE_MAXD; d++) xp[d] = 0.0;
+  // log-density of x[row] = xc given x[row - 1] = xp (row >= 1), the arithmetic of K7
+  auto transition = [&](int row, const double *xc) {
+    double xs[2][SDE_MAXD], res[1];
+#pragma unroll
+    for (int d = 0; d < SDE_MAXD; d++) { xs[0][d] = xp[d]; xs[1][d] = xc[d]; }
+    logt_batch<Model, 1>(prm, a.t0, a.dt, row, xs, s_ltab, res);
+    return res[0];
+  };
+  if (live)
+    for (int row = 0; row < h && row < nrows; row++) {   // head rows before the first aligned row (h <= 3)
+      double xc[SDE_MAXD];
+#pragma unroll
+      for (int d = 0; d < SDE_MAXD; d++) xc[d] = d < D ? (double)xin[(int64_t)row * D + d] : 0.0;
+      if (row > 0) op[row - 1] = (T)transition(row, xc);
+#pragma unroll
+      for (int d = 0; d < SDE_MAXD; d++) xp[d] = xc[d];
+    }
+  const int sw = lane & 7;
+  for (int k = 0; k < ntile; k++) {
+    if (lane == 0) issue_load(k + NST - 1);   // into the stage of tile k - 1: consumed and fenced at the end of that iteration
+    const int s = k % NST;
+    mbar_wait(smem_u32(bars + s), (uint32_t)((k / NST) & 1));
+    unsigned char *tile = tiles + s * TILE, *trow = tile + lane * 128;
+    if (live) {
+      const int row0 = h + k * TS;
+#pragma unroll
+      for (int bi = 0; bi < TS / NB; bi++) {   // NB rows = NQ 16-byte chunks of the lane's tile row, evaluated side by side
+        union { uint4 q[NQ]; T v[NB * D]; } u;
+#pragma unroll
+        for (int c = 0; c < NQ; c++) u.q[c] = *(const uint4 *)(trow + (((bi * NQ + c) ^ sw) << 4));
+        double xs[NB + 1][SDE_MAXD], res[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+#pragma unroll
+          for (int d = 0; d < SDE_MAXD; d++) xs[b + 1][d] = d < D ? (double)u.v[b * D + d] : 0.0;
+        const bool first = row0 + bi * NB == 0;   // row 0 starts the path: its slot is never stored; evaluate x0 -> x0 there
+#pragma unroll
+        for (int d = 0; d < SDE_MAXD; d++) xs[0][d] = first ? xs[1][d] : xp[d];
+        logt_batch<Model, NB>(prm, a.t0, a.dt, row0 + bi * NB, xs, s_ltab, res);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {   // slot qi lies at or before the bytes of row qi, which are in registers
+          const uint32_t off = (uint32_t)((bi * NB + b) * (int)sizeof(T));
+          *(T *)(trow + ((((off >> 4) ^ (uint32_t)sw) << 4) | (off & 15u))) = (T)res[b];
+        }
+#pragma unroll
+        for (int d = 0; d < SDE_MAXD; d++) xp[d] = xs[NB][d];
+      }
+    }
+    __syncwarp();
+    // the tile's results: element e = k2*32 + lane of the [32 tile rows][TS] block; tile row tr holds sub-path tr / rpb of map
+    // row tr % rpb, and its slot cc is the transition ending at row h_j + k TS + cc, i.e. output column ... - 1
+#pragma unroll
+    for (int k2 = 0; k2 < TS; k2++) {
+      const int e = k2 * 32 + lane, tr = e / TS, cc = e - tr * TS;
+      const uint32_t off = (uint32_t)(cc * (int)sizeof(T));
+      const T v = *(const T *)(tile + tr * 128 + ((((off >> 4) ^ (uint32_t)(tr & 7)) << 4) | (off & 15u)));
+      const int j = tr >> (5 - lg);
+      const int64_t pr = wbase + (tr & (rpb - 1)) * g + j;
+      const int col = hh(j) + k * TS + cc - 1;
+      if (pr < a.npaths && col >= 0) __stcs(out + pr * (int64_t)(nrows - 1) + col, v);
+    }
+    fence_async_smem();   // these generic-proxy reads come before the tensor load that refills the stage
+    __syncwarp();
+  }
+  // rows past the last full tile: one cooperative tile over rows [T0, nrows) of the warp's paths (natural order)
+  const int T0 = ntile * TS, ncols = (nrows - T0) * D;
+  const int64_t rem = a.npaths - wbase;
+  const int nlive = (int)(rem < 32 ? rem : 32);
+  T tv[TROW];
+  if (ncols > 0) {
+    const T *gw = (const T *)a.out2 + (wbase * nrows + T0) * D;
+#pragma unroll
+    for (int k = 0; k < TROW; k++) {
+      const int e = k * 32 + lane, rr = e / TROW, c = e - rr * TROW;
+      tv[k] = (rr < nlive && c < ncols) ? __ldcs(gw + (int64_t)rr * nrows * D + c) : (T)0;
+    }
+  }
+  __syncwarp();   // also a scheduling fence (see K3t)
+  if (ncols > 0) {
+    T *tt = (T *)tiles;
+#pragma unroll
+    for (int k = 0; k < TROW; k++) {
+      const int e = k * 32 + lane, rr = e / TROW, c = e - rr * TROW;
+      tt[rr * TLD + c] = tv[k];
+    }
+    __syncwarp();
+    if (live)
+      for (int row = T0 + h; row < nrows; row++) {
+        double xc[SDE_MAXD];
+#pragma unroll
+        for (int d = 0; d < SDE_MAXD; d++) xc[d] = d < D ? (double)tt[r * TLD + (row - T0) * D + d] : 0.0;
+        if (row > 0) tt[r * TLD + (row - T0)] = (T)transition(row, xc);   // slot i <= i*D: behind the rows still to be read
+#pragma unroll
+        for (int d = 0; d < SDE_MAXD; d++) xp[d] = xc[d];
+      }
+    __syncwarp();
+    // tail tile column i = transition ending at row T0 + i -> output column T0 + i - 1; the columns before h_j were written above
+    tail_tile_store<T, TOUT, TLD>(tt, out + wbase * (int64_t)(nrows - 1) + (T0 - 1), (int64_t)(nrows - 1), nlive, nrows - T0, h0, h1, h2, h3,
+                                  g - 1, lane);
   }
 }
 
@@ -2111,7 +2440,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
 
 #define SDE_KERNELS_LOGT(MODEL, TAG, T, PNAME)                                                                   \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 4) sdek_##TAG##_logt_##PNAME(                          \
-      const __grid_constant__ sde_args a) { sdeb200::logtransition_body<MODEL, T>(a); }
+      const __grid_constant__ sde_args a) { sdeb200::logtransition_body<MODEL, T>(a); }                              \
+  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, 3) sdek_##TAG##_logtt_##PNAME(                         \
+      const __grid_constant__ sde_args a) { sdeb200::logtransition_tma_body<MODEL, T>(a); }
 
 #define SDE_KERNELS_COEF(MODEL, TAG)                                                                             \
   extern "C" __global__ void sdek_##TAG##_coef(const __grid_constant__ sde_args a) {                            \

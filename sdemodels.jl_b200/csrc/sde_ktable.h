@@ -13,6 +13,7 @@ typedef struct {
   const void *simw[4][3];
   const void *simwt[4][3]; /* Wiener-driven on TMA tensor tiles (null: not applicable) */
   const void *logt[2]; /* [precision] */
+  const void *logtt[2]; /* logtransition on TMA tensor loads (null: not applicable) */
   const void *coef;
 } sde_ktable;
 #endif

@@ -221,6 +221,7 @@ int sde_nvrtc_compile(const std::string &functor_src, int D, int M, int slot, in
   }
   if (family == FAM_MISC && ok) {
     get(std::string("sdek_gen_logt_") + SUF, &kt->logt[slot == 1 ? 1 : 0]);
+    get(std::string("sdek_gen_logtt_") + SUF, &kt->logtt[slot == 1 ? 1 : 0]);
     get("sdek_gen_coef", &kt->coef);
   }
   if (!ok) {

@@ -72,8 +72,8 @@ extern "C" void h_pair_from_words_v2(const uint32_t *w3, double scale2, double *
 extern "C" double h_sqrt6(double v) { return sqrt_from_seed6(v, rsqrt_seed(v)); }
 extern "C" double h_sqrt7(double v) { return sqrt_core(v); }
 // geometry of the TMA trajectory tiles (sde_args.h): paths per tensor-map row and the first aligned row of a sub-path
-extern "C" int h_tma_group(int64_t pitch_bytes) { return sde_tma_group(pitch_bytes); }
-extern "C" int h_tma_head(int j, int64_t pitch_bytes, int rowb) { return sde_tma_head(j, pitch_bytes, rowb); }
+extern "C" int h_tma_group(int64_t pitch_bytes, int align) { return sde_tma_group(pitch_bytes, align); }
+extern "C" int h_tma_head(int j, int64_t pitch_bytes, int rowb, int align) { return sde_tma_head(j, pitch_bytes, rowb, align); }
 // the per-path form of the block function (round 0/1 invariants hoisted) must equal the plain one
 extern "C" void h_philox_path(uint64_t path, uint32_t stream, uint32_t blk, const uint32_t *key, uint32_t *out) {
   PhiloxKeys ks;
@@ -83,4 +83,11 @@ extern "C" void h_philox_path(uint64_t path, uint32_t stream, uint32_t blk, cons
   uint32_t r[4];
   philox4x32_10(pp, blk, ks, r);
   for (int i = 0; i < 4; i++) out[i] = r[i];
+}
+// the log-density kernel's logarithm and reciprocal (K7, sde_device.cuh: log_fast / rcp_fast)
+extern "C" void h_log_fast(const double *x, int64_t n, double *out) {
+  for (int64_t i = 0; i < n; i++) out[i] = log_fast(x[i], h_log_tab);
+}
+extern "C" void h_rcp_fast(const double *x, int64_t n, double *out) {
+  for (int64_t i = 0; i < n; i++) out[i] = rcp_fast(x[i]);
 }

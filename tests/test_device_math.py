@@ -74,23 +74,26 @@ def test_fp32_normal_transform_matches_the_specification(H, O):
 
 
 def test_tma_tile_geometry(H):
-    """sde_tma_group / sde_tma_head (sde_args.h): g consecutive paths make the tensor map's row stride a multiple of
-    16 bytes (TMA requirement), and the box of sub-path j starts at the first 16-byte-aligned time row."""
-    H.h_tma_group.argtypes = [C.c_int64]
-    H.h_tma_head.argtypes = [C.c_int, C.c_int64, C.c_int]
-    for es in (4, 8):
-        for D in (1, 2, 4):
-            rowb = D * es
-            for nrows in list(range(1, 70)) + [252, 253, 512, 513, 1024, 1025, 4097]:
-                pitch = nrows * rowb
-                g = H.h_tma_group(pitch)
-                assert g in (1, 2, 4) and (g * pitch) % 16 == 0 and (g == 1 or ((g // 2) * pitch) % 16 != 0)
-                heads = [H.h_tma_head(j, pitch, rowb) for j in range(g)]
-                assert heads[0] == 0
-                for j, h in enumerate(heads):
-                    assert (j * pitch + h * rowb) % 16 == 0                       # aligned box start
-                    assert all((j * pitch + k * rowb) % 16 != 0 for k in range(h))  # and the first such row
-                    assert h <= (0 if rowb % 16 == 0 else (1 if rowb % 8 == 0 else 3))  # HMAX of the kernels
+    """sde_tma_group / sde_tma_head (sde_args.h): g consecutive paths make the tensor map's row stride a multiple of the
+    alignment — 16 bytes (what TMA requires; K3t, K7t, K2u with 128-byte tiles) or 32 bytes (K2u with 64-byte tiles: whole
+    DRAM sectors) — and the box of sub-path j starts at the first aligned time row."""
+    H.h_tma_group.argtypes = [C.c_int64, C.c_int]
+    H.h_tma_head.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int]
+    for align in (16, 32):
+        for es in (4, 8):
+            for D in (1, 2, 4):
+                rowb = D * es
+                for nrows in list(range(1, 70)) + [252, 253, 512, 513, 1024, 1025, 4097]:
+                    pitch = nrows * rowb
+                    g = H.h_tma_group(pitch, align)
+                    assert g in (1, 2, 4, 8)[:3 if align == 16 else 4] and (g * pitch) % align == 0
+                    assert g == 1 or ((g // 2) * pitch) % align != 0
+                    heads = [H.h_tma_head(j, pitch, rowb, align) for j in range(g)]
+                    assert heads[0] == 0
+                    for j, h in enumerate(heads):
+                        assert (j * pitch + h * rowb) % align == 0                       # aligned box start
+                        assert all((j * pitch + k * rowb) % align != 0 for k in range(h))  # and the first such row
+                        assert h <= max(0, align // rowb - 1)                               # HMAX of the kernels
 
 
 def test_per_path_philox_form_is_bit_identical(H, O):
@@ -104,3 +107,35 @@ def test_per_path_philox_form_is_bit_identical(H, O):
         out = (C.c_uint32 * 4)()
         H.h_philox_path(path, stream, blk, (C.c_uint32 * 2)(*key), out)
         assert list(out) == O.philox4x32_10([path & 0xffffffff, path >> 32, blk, stream], key)
+
+
+def test_log_fast_and_rcp_fast(H):
+    """The log-density kernel's logarithm (table + degree-4 polynomial of the normal generator) and reciprocal (seed + two
+    Newton steps) against libm in extended precision: absolute error of the logarithm <= 4e-16 + 1 ulp, reciprocal <= 1 ulp;
+    zero, subnormal, negative, infinite and NaN arguments take the library routine."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 200000)), 1.0 + rng.uniform(-1e-3, 1e-3, 50000),
+                        rng.uniform(0.5, 2.0, 100000), [1.0, 2.0, 0.5, 2.2250738585072014e-308, 1.7976931348623157e308,
+                                                        1.0 - 2.0 ** -53, 1.0 + 2.0 ** -52]])
+    out = np.zeros_like(x)
+    H.h_log_fast(x.ctypes.data_as(C.c_void_p), C.c_int64(x.size), out.ctypes.data_as(C.c_void_p))
+    ref = np.log(x.astype(np.longdouble))
+    err = np.abs(out.astype(np.longdouble) - ref).astype(np.float64)
+    assert np.all(err <= 4e-16 + np.spacing(np.abs(ref).astype(np.float64))), float(err.max())
+    special = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310])
+    so = np.zeros_like(special)
+    H.h_log_fast(special.ctypes.data_as(C.c_void_p), C.c_int64(special.size), so.ctypes.data_as(C.c_void_p))
+    with np.errstate(all="ignore"):
+        want = np.log(special)
+    assert np.array_equal(so, want, equal_nan=True)
+    y = np.concatenate([x, -x[:1000], [1e-300, 1e300, 3.0, -7.0]])
+    ro = np.zeros_like(y)
+    H.h_rcp_fast(y.ctypes.data_as(C.c_void_p), C.c_int64(y.size), ro.ctypes.data_as(C.c_void_p))
+    rref = (np.longdouble(1.0) / y.astype(np.longdouble))
+    rerr = np.abs(ro.astype(np.longdouble) - rref).astype(np.float64)
+    assert np.all(rerr <= np.spacing(np.abs(rref).astype(np.float64))), float((rerr / np.abs(rref).astype(np.float64)).max())
+    sp = np.array([0.0, np.inf, -np.inf, 5e-324, 1e-309, 1.7e308])
+    spo = np.zeros_like(sp)
+    H.h_rcp_fast(sp.ctypes.data_as(C.c_void_p), C.c_int64(sp.size), spo.ctypes.data_as(C.c_void_p))
+    with np.errstate(all="ignore"):
+        assert np.array_equal(spo, 1.0 / sp)

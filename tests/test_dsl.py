@@ -208,6 +208,8 @@ def test_generated_functor_compiles_for_sm100a(S, name):
     fn.restype = C.c_int
     log = C.create_string_buffer(1 << 16)
     variants = [(0, 0)] if name not in ("Heston", "BlackScholes") else [(0, 0), (0, 1), (1, 0)]
+    if name in ("Lorenz", "TestModel"):
+        variants = [(0, 0), (1, 0)]   # D = 3: 24- and 12-byte rows, which the TMA kernel forms must compile around (as no-ops)
     for prec, math_ in variants:
         rc = fn(src, cls._M, prec, math_, log, len(log))
         assert rc > 1000, log.value.decode()

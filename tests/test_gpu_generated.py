@@ -218,3 +218,55 @@ def test_four_dimensional_model_on_tma_tiles(gpu, precision, npaths, nrows):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert np.array_equal(res[0][0], res[0][1]) and np.isfinite(res[0][0]).all()
     assert np.all(res[0][0][:, 0] == np.array([1.0, 0.5, 0.25, 0.0], dtype=res[0][0].dtype))
+
+
+LOGT_TMA_SHAPES = [  # (npaths, nsteps): head rows (odd pitch), leftover paths (npaths % g), partial warps, ragged tails, one tile short
+    (257, 512), (1000, 252), (64, 75), (33, 511), (95, 68), (130, 257), (4100, 70), (31, 300),
+]
+
+
+@pytest.mark.parametrize("name,params,x,t", [c for c in CASES if c[0] in
+                                             ("BlackScholes", "Heston", "CoxIngersollRoss", "FitzHughNagumo", "Lorenz")])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_logtransition_on_tma_tiles(gpu, O, name, params, x, t, precision):
+    """K7t (logtransition with TMA tensor loads, rows of 4 / 8 / 16 bytes; Lorenz' 12- / 24-byte rows stay on K7): bit for bit
+    what the plain tile kernel K7 writes, inside guard zones, and the oracle's values (fast logarithm / reciprocal: absolute
+    error of the log-determinant <= 4e-16 + 1 ulp, tests/test_device_math.py)."""
+    import torch
+    S = gpu
+    D, M, _ = O.dims(name)
+    es = 8 if precision == "f64" else 4
+    m = (getattr(S, name) if name in ("BlackScholes", "Heston") else gen(S, name))(*params)
+    tdt = torch.float64 if precision == "f64" else torch.float32
+    G = 1024
+    for npaths, nsteps in LOGT_TMA_SHAPES:
+        dt = 1.0 / 256
+        z = np.random.default_rng(5).standard_normal((npaths, nsteps, M))
+        paths = O.simulate_z(name, 0, params, t, dt, x, z)
+        data = np.ascontiguousarray((paths[..., 0] if D == 1 else paths).astype(np.float32 if precision == "f32" else np.float64))
+        ref = O.logtransition(name, params, t, dt, data.reshape(npaths, nsteps + 1, D).astype(np.float64))
+        nrows = nsteps + 1
+        expect_tma = 128 % (D * es) == 0 and nrows >= 2 * (128 // (D * es)) + 4 and npaths >= 32
+
+        def run(tma):
+            S.set_tma(tma)
+            try:
+                fin = torch.full((data.size + 2 * G,), -7.0, dtype=tdt, device="cuda")
+                fin[G:G + data.size].copy_(torch.from_numpy(data.reshape(-1)))
+                fout = torch.full((npaths * nsteps + 2 * G,), -7.0, dtype=tdt, device="cuda")
+                c0 = S.tma_launch_count()
+                got = S.logtransition(m, S.EulerMaruyama(dt), t, fin[G:G + data.size].view(*data.shape),
+                                      out=fout[G:G + npaths * nsteps].view(npaths, nsteps))
+                torch.cuda.synchronize()
+                assert bool((fout[:G] == -7.0).all() and (fout[-G:] == -7.0).all()), "guard zone overwritten"
+                assert bool((fin[:G] == -7.0).all() and (fin[-G:] == -7.0).all())
+                return got.cpu().numpy(), S.tma_launch_count() - c0
+            finally:
+                S.set_tma(True)
+
+        a, na = run(True)
+        b, nb = run(False)
+        assert nb == 0 and na == (1 if expect_tma else 0), (name, npaths, nsteps, na)
+        assert np.array_equal(a, b, equal_nan=True), (name, npaths, nsteps)
+        tol = 1e-11 if precision == "f64" else 2e-5
+        assert np.max(np.abs(a - ref) / np.maximum(1.0, np.abs(ref))) <= tol, (name, npaths, nsteps)
