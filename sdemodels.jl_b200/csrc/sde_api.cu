@@ -654,7 +654,7 @@ static int launch_simref(const void *k, const void *k_tma, int D, int M, int slo
   const int bb = batch_steps(M, slot) * rowb;
   int rc;
   int64_t done = 0;
-  const int talign = SDE_SIMRT2_ALIGN(simrt_rowbytes(precision));
+  const int talign = precision == SDEB200_F64 ? SDE_SIMRT2_ALIGN_F64 : SDE_SIMRT2_ALIGN_F32;
   if (k_tma && g_tma_enabled && M > 0 && 16 % rowb == 0 && bb % 16 == 0 && simrt_rowbytes(precision) % bb == 0 &&
       ((uintptr_t)out % talign) == 0 &&
       nrows >= 2 * (128 / rowb) + 4 && nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
@@ -1062,9 +1062,9 @@ static int launch_simw(const sde_ktable *kt, const sdeb200_model *m, const sdeb2
   const void *kt_tma = kt->simwt[o->scheme][kslot(o)], *k = kt->simw[o->scheme][kslot(o)];
   int rc;
   int64_t done = 0;
-  if (kt_tma && g_tma_enabled && D == MW && 128 % rowb == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)x % 16) == 0 &&
+  if (kt_tma && g_tma_enabled && D == MW && 128 % rowb == 0 && ((uintptr_t)w % SDE_SIMWT_ALIGN) == 0 && ((uintptr_t)x % SDE_SIMWT_ALIGN) == 0 &&
       nrows >= 2 * (128 / rowb) + 4 && nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
-    const int grp = sde_tma_group((int64_t)nrows * rowb);
+    const int grp = sde_tma_group((int64_t)nrows * rowb, SDE_SIMWT_ALIGN);
     const int64_t ncov = npaths - npaths % grp;
     if (ncov >= 32) {
       a.npaths = ncov;
@@ -1173,9 +1173,9 @@ static int launch_logt(const sde_ktable *kt, const sdeb200_model *m, int precisi
   const void *k = kt->logt[precision], *k_tma = kt->logtt[precision];
   int rc;
   int64_t done = 0;
-  if (k_tma && g_tma_enabled && 128 % rowb == 0 && ((uintptr_t)x % 16) == 0 && nrows >= 2 * (128 / rowb) + 4 &&
+  if (k_tma && g_tma_enabled && 128 % rowb == 0 && ((uintptr_t)x % SDE_SIMWT_ALIGN) == 0 && nrows >= 2 * (128 / rowb) + 4 &&
       nrows * D < (1 << 28) && npaths < ((int64_t)1 << 31)) {
-    const int grp = sde_tma_group((int64_t)nrows * rowb);
+    const int grp = sde_tma_group((int64_t)nrows * rowb, SDE_SIMWT_ALIGN);
     const int64_t ncov = npaths - npaths % grp;
     if (ncov >= 32) {
       a.npaths = ncov;

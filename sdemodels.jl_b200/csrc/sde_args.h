@@ -83,8 +83,8 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb, int align = 1
 }
 /* alignment K2u gives the row segments of its tiles: 16 bytes is what a tensor store needs; the 64-byte tiles align to the
  * 32-byte DRAM sector (g <= 8 paths per map row, h_j <= 7), because a 64-byte segment that starts in the middle of a sector
- * leaves two of its three sectors partial (measured on 513-row FP32 paths: 2.1 TB/s against 3.66 TB/s on 512-row paths) */
-#define SDE_SIMRT2_ALIGN(rowbytes) ((rowbytes) == 64 ? 32 : 16)
+ * leaves two of its three sectors partial (measured on 513-row FP32 paths: 2.1 TB/s against 3.66 TB/s on 512-row paths;
+ * 3.40 TB/s once aligned).  SDE_SIMRT2_ALIGN_F64 / _F32 below. */
 /* bytes per path and tile of K2u (tile = 32 paths x this; 128: 128-byte swizzle, 64: 64-byte swizzle).  The FP32 kernel is bound
  * by instruction issue, not by its stores (profiles/r02m: 6.91 ms with tensor stores, 6.62 ms with none at all, 6.79 ms with
  * stores that stay in L2; 12 warps per SM at 16 KB of ring per warp): half-size tiles double the resident warps. */
@@ -93,6 +93,12 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb, int align = 1
 #endif
 #ifndef SDE_SIMRT2_ROWB_F32
 #define SDE_SIMRT2_ROWB_F32 64
+#endif
+#ifndef SDE_SIMRT2_ALIGN_F64
+#define SDE_SIMRT2_ALIGN_F64 32 /* measured on C3: 3.63 -> 3.84 TB/s, wiener! 3.70 -> 4.13 (profiles/r02q_alignment_variants.txt) */
+#endif
+#ifndef SDE_SIMRT2_ALIGN_F32
+#define SDE_SIMRT2_ALIGN_F32 (SDE_SIMRT2_ROWB_F32 == 64 ? 32 : 16)
 #endif
 #ifndef SDE_SIMRT2_STAGES_F64
 #define SDE_SIMRT2_STAGES_F64 2
@@ -111,6 +117,12 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb, int align = 1
 #ifndef SDE_LOGTT_STAGES
 #define SDE_LOGTT_STAGES 4 /* ring depth of the TMA-load logtransition kernel K7t: 4 KB per stage and warp, 3 CTAs per SM */
 #endif
+/* alignment of the row segments of the K3t / K7t tiles: 16 bytes, TMA's own requirement.  Sector alignment (32 bytes, g <= 8
+ * sub-paths of 32/g map rows per tile) was built and measured on 513-row paths (profiles/r02q_alignment_variants.txt): FP64
+ * BlackScholes 5.57 vs 5.58, Heston 5.54 vs 5.37, FP32 BlackScholes 4.99 vs 5.62 TB/s, logtransition 4.40 vs 4.95 — twice the
+ * tensor operations of half the size cost more than the partial sectors of these load-dominated kernels, and one ragged test
+ * shape hung: not shipped, the geometry code below stays general in g. */
+#define SDE_SIMWT_ALIGN 16
 #ifndef SDE_SIMWT_STAGES
 #define SDE_SIMWT_STAGES 6 /* ring depth of the TMA Wiener-driven kernel: 4 KB per stage and warp */
 #endif

@@ -1502,12 +1502,11 @@ SDE_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::
 // Cooperative store of a warp's ragged tail tile [32 paths][ROW] (runs once per warp).  Row r is written only from
 // column cs_{r % g} on: the columns before belong to time rows that were already written by TMA stores.
 template <typename T, int ROW, int LD>
-SDE_D void tail_tile_store(const T *tile, T *g, int64_t gstride, int nlive, int ncols, int cs0, int cs1, int cs2, int cs3, int gm1,
-                           int lane) {
+SDE_D void tail_tile_store(const T *tile, T *g, int64_t gstride, int nlive, int ncols, uint32_t hpack, int mult, int gm1, int lane) {
 #pragma unroll 4
   for (int k = 0; k < ROW; k++) {
     const int e = k * 32 + lane, r = e / ROW, c = e - r * ROW, j = r & gm1;
-    const int cs = j == 0 ? cs0 : (j == 1 ? cs1 : (j == 2 ? cs2 : cs3));
+    const int cs = (int)((hpack >> (4 * j)) & 15u) * mult;   // head rows h_j, four bits each
     if (r < nlive && c < ncols && c >= cs) __stcs(g + r * gstride + c, tile[r * LD + c]);
   }
 }
@@ -1533,7 +1532,8 @@ SDE_D void simulate_wiener_tma_body(const sde_args &a) {
   constexpr int GB = ROWB > 16 ? ROWB : 16;               // bytes per register group
   constexpr int G = GB / ROWB > 0 ? GB / ROWB : 1, GQ = GB / 16, NG = 128 / GB;
   constexpr int TILE = 32 * 128;
-  constexpr int HMAX = ROWB % 16 == 0 ? 0 : (ROWB % 8 == 0 ? 1 : 3);   // bound on the head rows h_j
+  constexpr int TALIGN = SDE_SIMWT_ALIGN;                 // alignment of the tiles' row segments (16: what TMA needs)
+  constexpr int HMAX = TALIGN > ROWB ? TALIGN / ROWB - 1 : 0;   // bound on the head rows h_j
   constexpr int TROW = (TS + HMAX) * D, TLD = TROW | 1;   // the cooperative tail tile [32][TLD] (fits in two stages)
   static_assert(!OK || 32 * TLD * (int)sizeof(T) <= 2 * TILE, "tail tile does not fit");
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -1551,12 +1551,16 @@ SDE_D void simulate_wiener_tma_body(const sde_args &a) {
   if (wbase >= a.npaths) return;
   const int nrows = (int)(a.nsteps + 1);
   const int64_t pitch = (int64_t)nrows * ROWB;
-  const int g = sde_tma_group(pitch), rpb = 32 / g;
-  // head rows of the g sub-paths (scalars, not an indexed array: no local memory)
-  const int h0 = 0, h1 = g > 1 ? sde_tma_head(1, pitch, ROWB) : 0, h2 = g > 2 ? sde_tma_head(2, pitch, ROWB) : 0,
-            h3 = g > 2 ? sde_tma_head(3, pitch, ROWB) : 0;
-  auto hh = [&](int j) { return j == 0 ? h0 : (j == 1 ? h1 : (j == 2 ? h2 : h3)); };
-  const int h12 = h1 > h2 ? h1 : h2, hmax = h12 > h3 ? h12 : h3;
+  const int g = sde_tma_group(pitch, TALIGN), rpb = 32 / g;
+  // head rows of the g <= 8 sub-paths, four bits each in one word (not an indexed array: no local memory)
+  uint32_t hpack = 0;
+  int hmax = 0;
+  for (int j = 1; j < g; j++) {
+    const int hj = sde_tma_head(j, pitch, ROWB, TALIGN);
+    hpack |= (uint32_t)hj << (4 * j);
+    hmax = hj > hmax ? hj : hmax;
+  }
+  auto hh = [&](int j) { return (int)((hpack >> (4 * j)) & 15u); };
   const int ntile = nrows > hmax ? (nrows - hmax) / TS : 0;
   const int r = (lane % rpb) * g + lane / rpb;        // lane <-> tile row `lane` <-> path wbase + r
   const int h = hh(lane / rpb);
@@ -1672,8 +1676,7 @@ SDE_D void simulate_wiener_tma_body(const sde_args &a) {
     if (live)
       for (int row = T0 + h; row < nrows; row++) row_step(row, tt + r * TLD + (row - T0) * D);
     __syncwarp();
-    tail_tile_store<T, TROW, TLD>(tt, (T *)a.out + (wbase * nrows + T0) * D, (int64_t)nrows * D, nlive, ncols, h0 * D, h1 * D, h2 * D,
-                                  h3 * D, g - 1, lane);
+    tail_tile_store<T, TROW, TLD>(tt, (T *)a.out + (wbase * nrows + T0) * D, (int64_t)nrows * D, nlive, ncols, hpack, D, g - 1, lane);
   }
   __syncwarp();
   count_nonfinite(a, live, x, D);
@@ -1731,7 +1734,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 
   const int nrows = (int)(a.nsteps + 1);
   const int64_t pitch = (int64_t)nrows * ROWB;
-  constexpr int TALIGN = SDE_SIMRT2_ALIGN(TROWB);
+  constexpr int TALIGN = sizeof(T) == 8 ? SDE_SIMRT2_ALIGN_F64 : SDE_SIMRT2_ALIGN_F32;
   const int g = sde_tma_group(pitch, TALIGN);
   const int64_t maprows = a.npaths / g;                           // a.npaths is a multiple of g
   const int64_t unit = (int64_t)blockIdx.x * (SDE_BLOCK / 32) + wid;
@@ -1856,8 +1859,9 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   int cpos = 0, kt = 0, ks_ = 0;                                   // ks_ = kt % NSTG
   uint32_t blk = 0;
   int tb = 0;
-  auto fast_batch = [&](auto phc) {
+  auto fast_batch = [&](auto phc, auto msc) {
     constexpr int PHC = decltype(phc)::value;
+    constexpr int MS = decltype(msc)::value;   // mshift % NCB: chunks of a tile-crossing batch that still belong to the old tile
     if (cpos == 0) acquire(kt);
     T dw[B::NZ];
     gen_batch<T, M, V>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dw, pc.v);
@@ -1873,40 +1877,52 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 #pragma unroll
       for (int d = 0; d < D; d++) seq[PHC + u][d] = x[d];
     }
+    auto put = [&](int c, unsigned char *stage, int pos) {   // chunk c of the batch -> chunk position pos of the lane's tile row
+      union { uint4 q4; T v[EPC]; } w;
+#pragma unroll
+      for (int e = 0; e < EPC; e++) w.v[e] = seq[(c * EPC + e) / D][(c * EPC + e) % D];
+      *(uint4 *)(stage + ((((uint32_t)pos) ^ sw) << 4)) = w.q4;
+    };
+    auto next_tile = [&]() {
+      flush(kt);
+      kt++;
+      ks_ = ks_ + 1 == NSTG ? 0 : ks_ + 1;
+    };
     // 16-byte rows with several rows per batch (RPC == 1, NCB > 1: row r is chunk r, one past the batch grid) may cross a
-    // tile boundary INSIDE a batch: boundary checks per chunk there, once per batch everywhere else
+    // tile boundary INSIDE a batch at any chunk: boundary checks per chunk there.  Everywhere else the first chunk of a
+    // batch sits at cpos = -mshift (mod NCB): on the batch grid when MS == 0 (boundary check once per batch); off it when the
+    // head rows are h_j >= 2 (only the 32-byte alignment produces them), and then every NCH / NCB-th batch crosses into the
+    // next tile after exactly MS chunks — one warp-uniform branch per batch.
     constexpr bool PERCHUNK = (RPC == 1) && (NCB > 1);
-    if (!PERCHUNK) {
-      unsigned char *stage = trow + ks_ * TILEB;
-#pragma unroll
-      for (int c = 0; c < NCB; c++) {
-        union { uint4 q4; T v[EPC]; } w;
-#pragma unroll
-        for (int e = 0; e < EPC; e++) w.v[e] = seq[(c * EPC + e) / D][(c * EPC + e) % D];
-        *(uint4 *)(stage + ((((uint32_t)(cpos + c)) ^ sw) << 4)) = w.q4;
-      }
-      cpos += NCB;
-      if (cpos == NCH) {
-        flush(kt);
-        cpos = 0;
-        kt++;
-        ks_ = ks_ + 1 == NSTG ? 0 : ks_ + 1;
-      }
-    } else {
+    if (PERCHUNK) {
 #pragma unroll
       for (int c = 0; c < NCB; c++) {
         if (c > 0 && cpos == 0) acquire(kt);
-        union { uint4 q4; T v[EPC]; } w;
-#pragma unroll
-        for (int e = 0; e < EPC; e++) w.v[e] = seq[(c * EPC + e) / D][(c * EPC + e) % D];
-        *(uint4 *)(trow + ks_ * TILEB + ((((uint32_t)cpos) ^ sw) << 4)) = w.q4;
+        put(c, trow + ks_ * TILEB, cpos);
         if (++cpos == NCH) {
-          flush(kt);
+          next_tile();
           cpos = 0;
-          kt++;
-          ks_ = ks_ + 1 == NSTG ? 0 : ks_ + 1;
         }
       }
+    } else if (MS == 0 || cpos + NCB <= NCH) {
+      unsigned char *stage = trow + ks_ * TILEB;
+#pragma unroll
+      for (int c = 0; c < NCB; c++) put(c, stage, cpos + c);
+      cpos += NCB;
+      if (MS == 0 && cpos == NCH) {
+        next_tile();
+        cpos = 0;
+      }
+    } else {   // cpos == NCH - MS
+      unsigned char *stage = trow + ks_ * TILEB;
+#pragma unroll
+      for (int c = 0; c < MS; c++) put(c, stage, NCH - MS + c);
+      next_tile();
+      acquire(kt);
+      stage = trow + ks_ * TILEB;
+#pragma unroll
+      for (int c = MS; c < NCB; c++) put(c, stage, c - MS);
+      cpos = NCB - MS;
     }
     if (RPC > 1) {
 #pragma unroll
@@ -1917,6 +1933,8 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     blk += (uint32_t)B::NB;
     tb += U;
   };
+  constexpr int HMAXR = TALIGN > ROWB ? TALIGN / ROWB - 1 : 0;                       // bound on the head rows h_j
+  constexpr int MSMAX = (RPC > 1 && NCB > 1) ? ((HMAXR - 1 + RPC - 1) / RPC) : 0;    // bound on mshift where it matters
   auto run_fast = [&](auto phc) {
     constexpr int PHC = decltype(phc)::value;
     const int64_t cs0 = it * NCB - mshift;                          // >= 0 by the choice of it0
@@ -1925,7 +1943,14 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     ks_ = kt % NSTG;
     blk = (uint32_t)(it * B::NB);
     tb = (int)(it * U);
-    for (; it < it1; it++) fast_batch(phc);
+    const int ms = MSMAX > 0 ? mshift % NCB : 0;
+    if (MSMAX >= 1 && ms == 1) {
+      for (; it < it1; it++) fast_batch(phc, IntC<(MSMAX >= 1 && NCB > 1 ? 1 : 0)>());
+    } else if (MSMAX >= 2 && ms == 2) {
+      for (; it < it1; it++) fast_batch(phc, IntC<(MSMAX >= 2 && NCB > 2 ? 2 : 0)>());
+    } else {
+      for (; it < it1; it++) fast_batch(phc, IntC<0>());
+    }
     // the newest PHC rows are still in registers only: rows it*U - PHC + 1 .. it*U (compile-time indices: no local memory)
 #pragma unroll
     for (int c = 0; c < PHC; c++) emit_row((int)(it * U) - PHC + 1 + c, carry[(RPC - 1) - PHC + c]);
@@ -2167,7 +2192,8 @@ SDE_D void logtransition_tma_body(const sde_args &a) {
   constexpr int NB = TS < 4 ? TS : 4;                     // transitions evaluated side by side
   constexpr int NQ = OK ? NB * ROWB / 16 : 1;             // 16-byte chunks per batch (ROWB >= 4, NB = 4 or ROWB >= 64)
   constexpr int TILE = 32 * 128;
-  constexpr int HMAX = ROWB % 16 == 0 ? 0 : (ROWB % 8 == 0 ? 1 : 3);
+  constexpr int TALIGN = SDE_SIMWT_ALIGN;
+  constexpr int HMAX = TALIGN > ROWB ? TALIGN / ROWB - 1 : 0;
   constexpr int TOUT = TS + HMAX, TROW = TOUT * D, TLD = TROW | 1;   // the cooperative tail tile [32][TLD]
   static_assert(!OK || NST < 2 || 32 * TLD * (int)sizeof(T) <= 2 * TILE, "tail tile does not fit");
   __shared__ double s_ltab[256];
@@ -2188,11 +2214,15 @@ SDE_D void logtransition_tma_body(const sde_args &a) {
   if (wbase >= a.npaths) return;
   const int nrows = (int)(a.nsteps + 1);
   const int64_t pitch = (int64_t)nrows * ROWB;
-  const int g = sde_tma_group(pitch), lg = g == 1 ? 0 : (g == 2 ? 1 : 2), rpb = 32 >> lg;
-  const int h0 = 0, h1 = g > 1 ? sde_tma_head(1, pitch, ROWB) : 0, h2 = g > 2 ? sde_tma_head(2, pitch, ROWB) : 0,
-            h3 = g > 2 ? sde_tma_head(3, pitch, ROWB) : 0;
-  auto hh = [&](int j) { return j == 0 ? h0 : (j == 1 ? h1 : (j == 2 ? h2 : h3)); };
-  const int h12 = h1 > h2 ? h1 : h2, hmax = h12 > h3 ? h12 : h3;
+  const int g = sde_tma_group(pitch, TALIGN), lg = g == 1 ? 0 : (g == 2 ? 1 : (g == 4 ? 2 : 3)), rpb = 32 >> lg;
+  uint32_t hpack = 0;   // head rows of the g <= 8 sub-paths, four bits each
+  int hmax = 0;
+  for (int j = 1; j < g; j++) {
+    const int hj = sde_tma_head(j, pitch, ROWB, TALIGN);
+    hpack |= (uint32_t)hj << (4 * j);
+    hmax = hj > hmax ? hj : hmax;
+  }
+  auto hh = [&](int j) { return (int)((hpack >> (4 * j)) & 15u); };
   const int ntile = nrows > hmax ? (nrows - hmax) / TS : 0;
   const int r = (lane & (rpb - 1)) * g + (lane >> (5 - lg));   // lane <-> tile row `lane` <-> path wbase + r
   const int h = hh(lane >> (5 - lg));
@@ -2318,7 +2348,7 @@ SDE_D void logtransition_tma_body(const sde_args &a) {
       }
     __syncwarp();
     // tail tile column i = transition ending at row T0 + i -> output column T0 + i - 1; the columns before h_j were written above
-    tail_tile_store<T, TOUT, TLD>(tt, out + wbase * (int64_t)(nrows - 1) + (T0 - 1), (int64_t)(nrows - 1), nlive, nrows - T0, h0, h1, h2, h3,
+    tail_tile_store<T, TOUT, TLD>(tt, out + wbase * (int64_t)(nrows - 1) + (T0 - 1), (int64_t)(nrows - 1), nlive, nrows - T0, hpack, 1,
                                   g - 1, lane);
   }
 }

@@ -270,3 +270,37 @@ def test_logtransition_on_tma_tiles(gpu, O, name, params, x, t, precision):
         assert np.array_equal(a, b, equal_nan=True), (name, npaths, nsteps)
         tol = 1e-11 if precision == "f64" else 2e-5
         assert np.max(np.abs(a - ref) / np.maximum(1.0, np.abs(ref))) <= tol, (name, npaths, nsteps)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("rng", [1, 2])
+def test_reference_order_tma_stores_two_states_one_noise(gpu, precision, rng):
+    """D = 2, M = 1 on the TMA store kernel K2u: a Philox batch is several 16-byte chunks (FP32: 4 steps x 8 bytes, FP64
+    stream v2: 8 steps x 16 bytes) and, with tiles aligned to 32-byte sectors, its first chunk may sit off the batch grid
+    (head rows h_j >= 2), so that a batch straddles two tiles.  Bit for bit what the shared-memory-tile kernel K2b writes."""
+    import torch
+    S = gpu
+    cls = S.sde_model("TwoOne_g", "dX = a*X*dt + s*X*dW1\ndY = b*(X - Y)*dt")
+    assert (cls._D, cls._M) == (2, 1)
+    m = cls(0.05, 0.3, 1.5)
+    tdt = torch.float64 if precision == "f64" else torch.float32
+    G = 1024
+    for npaths, nrows in [(257, 513), (130, 259), (999, 131), (64, 77), (300, 1026), (97, 70)]:
+        nsteps = nrows - 1
+        res = []
+        for tma in (True, False):
+            S.set_tma(tma)
+            try:
+                n = npaths * nrows * 2
+                full = torch.full((n + 2 * G,), -7.0, dtype=tdt, device="cuda")
+                v = full[G:G + n].view(npaths, nrows, 2)
+                c0 = S.tma_launch_count()
+                S.simulate(m, S.EulerMaruyama(1.0 / nsteps), 0.0, [1.0, 0.5], nsteps, npaths, seed=3, precision=precision, out=v, rng=rng)
+                torch.cuda.synchronize()
+                assert bool((full[:G] == -7.0).all() and (full[-G:] == -7.0).all()), "guard zone overwritten"
+                res.append((v.cpu().numpy().copy(), S.tma_launch_count() - c0))
+            finally:
+                S.set_tma(True)
+        assert res[0][1] == 1 and res[1][1] == 0, (npaths, nrows, res[0][1])
+        assert np.array_equal(res[0][0], res[1][0]), (npaths, nrows)
+        assert np.isfinite(res[0][0]).all() and np.all(res[0][0][:, 0, :] == np.array([1.0, 0.5]))
