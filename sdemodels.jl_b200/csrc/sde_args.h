@@ -100,6 +100,11 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb, int align = 1
 #ifndef SDE_SIMRT2_ALIGN_F32
 #define SDE_SIMRT2_ALIGN_F32 (SDE_SIMRT2_ROWB_F32 == 64 ? 32 : 16)
 #endif
+#ifndef SDE_SIMRT2_PREFETCH
+#define SDE_SIMRT2_PREFETCH 0 /* K2u: generate the next batch's normals alongside the current batch's steps.  Measured on C3
+                                 (profiles/r02u_k2u_prefetch_ab.txt): FP32 6.00 vs 5.99 ms (ptxas keeps the two chains apart anyway),
+                                 FP64 14.9 vs 10.6 ms (eight more live doubles at the 128-register cap): off */
+#endif
 #ifndef SDE_SIMRT2_STAGES_F64
 #define SDE_SIMRT2_STAGES_F64 2
 #endif

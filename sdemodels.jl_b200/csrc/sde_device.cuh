@@ -1538,7 +1538,7 @@ SDE_D void simulate_wiener_tma_body(const sde_args &a) {
   static_assert(!OK || 32 * TLD * (int)sizeof(T) <= 2 * TILE, "tail tile does not fit");
   extern __shared__ __align__(16) unsigned char s_dyn[];
   unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);  // the swizzle is a function of the address
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for ptxas (see K2u)
   unsigned char *tiles = smem + (size_t)wid * (NST * TILE);
   uint64_t *bars = (uint64_t *)(smem + (size_t)(SDE_BLOCK / 32) * (NST * TILE)) + wid * NST;
   if (lane == 0) {
@@ -1716,7 +1716,9 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   load_tables<T, V>(s_tab, a.noise_var);
   if (!OK) return;
   unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // the warp index through a shuffle: ptxas then knows it is warp-uniform, and the tensor-store operands derived from it (tile
+  // address, coordinates) sit in uniform registers instead of being made uniform by a vote loop before every UTMASTG
+  const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   // MANUAL: a finished tile leaves through 8 LDS.128 + 8 STG.128 per warp (16-byte chunks, four 128-byte row segments per
   // warp instruction) instead of a tensor store — synchronous, so one stage is enough
   constexpr bool MANUAL = sizeof(T) == 8 ? (SDE_SIMRT2_MANUAL_F64 != 0) : (SDE_SIMRT2_MANUAL_F32 != 0);
@@ -1859,12 +1861,20 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   int cpos = 0, kt = 0, ks_ = 0;                                   // ks_ = kt % NSTG
   uint32_t blk = 0;
   int tb = 0;
+  T dwn[B::NZ];                                                    // SDE_SIMRT2_PREFETCH: the normals of the next batch
   auto fast_batch = [&](auto phc, auto msc) {
     constexpr int PHC = decltype(phc)::value;
     constexpr int MS = decltype(msc)::value;   // mshift % NCB: chunks of a tile-crossing batch that still belong to the old tile
-    if (cpos == 0) acquire(kt);
     T dw[B::NZ];
+#if SDE_SIMRT2_PREFETCH
+    // software pipeline: the normals of the NEXT batch are produced while this batch's steps run — the generator does not
+    // depend on the state, so the two chains interleave in one basic block (one path per lane has no other parallelism)
+#pragma unroll
+    for (int i = 0; i < B::NZ; i++) dw[i] = dwn[i];
+    gen_batch<T, M, V>(pp, gpath, blk + (uint32_t)B::NB, a.stream, ks, s_tab, a.lk, nv, dwn, pc.v);
+#else
     gen_batch<T, M, V>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dw, pc.v);
+#endif
     T seq[PHC + U][D];                                             // carry rows, then the U new rows
 #pragma unroll
     for (int c = 0; c < PHC; c++)
@@ -1883,10 +1893,11 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
       for (int e = 0; e < EPC; e++) w.v[e] = seq[(c * EPC + e) / D][(c * EPC + e) % D];
       *(uint4 *)(stage + ((((uint32_t)pos) ^ sw) << 4)) = w.q4;
     };
-    auto next_tile = [&]() {
+    auto next_tile = [&]() {   // the stage of the next tile is acquired right away (once per tile, not a check per batch)
       flush(kt);
       kt++;
       ks_ = ks_ + 1 == NSTG ? 0 : ks_ + 1;
+      acquire(kt);
     };
     // 16-byte rows with several rows per batch (RPC == 1, NCB > 1: row r is chunk r, one past the batch grid) may cross a
     // tile boundary INSIDE a batch at any chunk: boundary checks per chunk there.  Everywhere else the first chunk of a
@@ -1897,7 +1908,6 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     if (PERCHUNK) {
 #pragma unroll
       for (int c = 0; c < NCB; c++) {
-        if (c > 0 && cpos == 0) acquire(kt);
         put(c, trow + ks_ * TILEB, cpos);
         if (++cpos == NCH) {
           next_tile();
@@ -1918,7 +1928,6 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 #pragma unroll
       for (int c = 0; c < MS; c++) put(c, stage, NCH - MS + c);
       next_tile();
-      acquire(kt);
       stage = trow + ks_ * TILEB;
 #pragma unroll
       for (int c = MS; c < NCB; c++) put(c, stage, c - MS);
@@ -1943,13 +1952,19 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     ks_ = kt % NSTG;
     blk = (uint32_t)(it * B::NB);
     tb = (int)(it * U);
+    if (cpos == 0) acquire(kt);
+#if SDE_SIMRT2_PREFETCH
+    gen_batch<T, M, V>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dwn, pc.v);
+#endif
     const int ms = MSMAX > 0 ? mshift % NCB : 0;
+    int nb = (int)(it1 - it);                                       // 32-bit loop counter (nsteps < 2^28)
+    it = it1;
     if (MSMAX >= 1 && ms == 1) {
-      for (; it < it1; it++) fast_batch(phc, IntC<(MSMAX >= 1 && NCB > 1 ? 1 : 0)>());
+      for (; nb > 0; nb--) fast_batch(phc, IntC<(MSMAX >= 1 && NCB > 1 ? 1 : 0)>());
     } else if (MSMAX >= 2 && ms == 2) {
-      for (; it < it1; it++) fast_batch(phc, IntC<(MSMAX >= 2 && NCB > 2 ? 2 : 0)>());
+      for (; nb > 0; nb--) fast_batch(phc, IntC<(MSMAX >= 2 && NCB > 2 ? 2 : 0)>());
     } else {
-      for (; it < it1; it++) fast_batch(phc, IntC<0>());
+      for (; nb > 0; nb--) fast_batch(phc, IntC<0>());
     }
     // the newest PHC rows are still in registers only: rows it*U - PHC + 1 .. it*U (compile-time indices: no local memory)
 #pragma unroll
@@ -2201,7 +2216,7 @@ SDE_D void logtransition_tma_body(const sde_args &a) {
   __syncthreads();
   extern __shared__ __align__(16) unsigned char s_dyn[];
   unsigned char *smem = s_dyn + ((1024u - (smem_u32(s_dyn) & 1023u)) & 1023u);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for ptxas (see K2u)
   unsigned char *tiles = smem + (size_t)wid * (NST * TILE);
   uint64_t *bars = (uint64_t *)(smem + (size_t)(SDE_BLOCK / 32) * (NST * TILE)) + wid * NST;
   if (lane == 0) {
@@ -2269,6 +2284,27 @@ SDE_D void logtransition_tma_body(const sde_args &a) {
       for (int d = 0; d < SDE_MAXD; d++) xp[d] = xc[d];
     }
   const int sw = lane & 7;
+  const int nlive = (int)(a.npaths - wbase < 32 ? a.npaths - wbase : 32);
+  auto store_tile = [&](auto gc, int k, const unsigned char *tile) {
+    constexpr int GC = decltype(gc)::value;          // sub-paths per map row
+    constexpr int RPI = OK ? 32 / TS : 1, RPB = 32 / GC;   // tile rows per warp instruction, tile rows per sub-path
+    static_assert(!OK || (RPB % RPI == 0 && RPB >= RPI), "a warp instruction stays inside one sub-path");
+    const int cc = lane & (TS - 1), tr0 = lane / TS;
+    const uint32_t off = (uint32_t)(cc * (int)sizeof(T));
+#pragma unroll
+    for (int j = 0; j < GC; j++) {
+      const int hj = hh(j);
+      T *ptr = out + (wbase + (int64_t)tr0 * GC + j) * (int64_t)(nrows - 1) + (hj + k * TS + cc - 1);
+      const bool skip = k == 0 && hj + cc == 0;      // column -1: row 0 starts the path
+#pragma unroll
+      for (int q = 0; q < RPB / RPI; q++) {
+        const int tr = j * RPB + q * RPI + tr0;
+        const T v = *(const T *)(tile + tr * 128 + ((((off >> 4) ^ (uint32_t)(tr & 7)) << 4) | (off & 15u)));
+        if ((q * RPI + tr0) * GC + j < nlive && !skip) __stcs(ptr, v);
+        ptr += (int64_t)RPI * GC * (nrows - 1);
+      }
+    }
+  };
   for (int k = 0; k < ntile; k++) {
     if (lane == 0) issue_load(k + NST - 1);   // into the stage of tile k - 1: consumed and fenced at the end of that iteration
     const int s = k % NST;
@@ -2300,25 +2336,18 @@ SDE_D void logtransition_tma_body(const sde_args &a) {
       }
     }
     __syncwarp();
-    // the tile's results: element e = k2*32 + lane of the [32 tile rows][TS] block; tile row tr holds sub-path tr / rpb of map
-    // row tr % rpb, and its slot cc is the transition ending at row h_j + k TS + cc, i.e. output column ... - 1
-#pragma unroll
-    for (int k2 = 0; k2 < TS; k2++) {
-      const int e = k2 * 32 + lane, tr = e / TS, cc = e - tr * TS;
-      const uint32_t off = (uint32_t)(cc * (int)sizeof(T));
-      const T v = *(const T *)(tile + tr * 128 + ((((off >> 4) ^ (uint32_t)(tr & 7)) << 4) | (off & 15u)));
-      const int j = tr >> (5 - lg);
-      const int64_t pr = wbase + (tr & (rpb - 1)) * g + j;
-      const int col = hh(j) + k * TS + cc - 1;
-      if (pr < a.npaths && col >= 0) __stcs(out + pr * (int64_t)(nrows - 1) + col, v);
-    }
+    // the tile's results leave as whole row segments of out: one warp instruction covers 32 / TS tile rows; tile row tr holds
+    // sub-path tr / rpb of map row tr % rpb, and its slot cc is the transition ending at row h_j + k TS + cc, i.e. output
+    // column ... - 1.  g is a compile-time constant inside store_tile: what is left per instruction is one shared-memory
+    // address, one pointer bump and the bound check of a partial warp.
+    if (g == 1) store_tile(IntC<1>(), k, tile);
+    else if (g == 2) store_tile(IntC<2>(), k, tile);
+    else store_tile(IntC<4>(), k, tile);
     fence_async_smem();   // these generic-proxy reads come before the tensor load that refills the stage
     __syncwarp();
   }
   // rows past the last full tile: one cooperative tile over rows [T0, nrows) of the warp's paths (natural order)
   const int T0 = ntile * TS, ncols = (nrows - T0) * D;
-  const int64_t rem = a.npaths - wbase;
-  const int nlive = (int)(rem < 32 ? rem : 32);
   T tv[TROW];
   if (ncols > 0) {
     const T *gw = (const T *)a.out2 + (wbase * nrows + T0) * D;
