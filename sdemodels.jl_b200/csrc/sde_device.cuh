@@ -21,7 +21,7 @@
 #define SDE_HD __host__ __device__ __forceinline__
 #define SDE_D __device__ __forceinline__
 #else
-#define SDE_HD static inline
+#define SDE_HD inline
 #endif
 
 #ifndef SDE_PPT
@@ -418,8 +418,11 @@ SDE_HD void make_log_consts_v2(double dt, double *lk) {
   lk[5] = SDE_TWO_LN2_V * dt;
 #endif
 }
-SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double *tab, const double *lk, double &z0, double &z1,
-                               const double *kr = nullptr) {
+// Polar form of the pair: radius^2 `w` (already scaled by the step's variance) and the unit vector (ca, sb); the pair is
+// (sqrt(w) ca, sqrt(w) sb).  Models whose noise terms share a square-root factor (Heston: sqrt(V) dW) take this form and
+// fold the two square roots into one (Model::step_polar, sde_models_builtin.cuh).
+SDE_HD void normal_polar_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double *tab, const double *lk, double &w, double &ca,
+                                double &sb, const double *kr = nullptr) {
   const uint64_t X1 = ((uint64_t)b << 32) | a;
   const double d1 = (double)X1;
   const uint32_t h1 = double2hi(d1);
@@ -450,9 +453,8 @@ SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double 
   q = fma(q, rr, lk[0]);
   q = fma(q, rr, lk[4]);
 #endif
-  double w = fma(rr, q, tl);
+  w = fma(rr, q, tl);
   w = fma(kd, lk[5], w);
-  const double g = sqrt_from_seed6(w, rsqrt_seed(w));
 #if SDE_V2_FINE
   const double *rot = tab + 2 * SDE_V2_LOGN + 2 * (c >> 21);
   const double C = rot[0], S = rot[1];
@@ -471,10 +473,8 @@ SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double 
   // rotation with the cosine of the residual formed explicitly (1 + cm: one rounding at 2^-53 absolute): two of the
   // three-register FMAs become two-register multiplies, which dispatch faster (profiles/r01_mb_cost.txt)
   const double c1 = fma(cm, u, 1.0);
-  const double ca1 = fma(C, c1, -(S * sn));
-  const double sb1 = fma(S, c1, C * sn);
-  z0 = g * ca1;
-  z1 = g * sb1;
+  ca = fma(C, c1, -(S * sn));
+  sb = fma(S, c1, C * sn);
   return;
 #endif
 #else
@@ -488,8 +488,14 @@ SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double 
   double cm = fma(kr ? kr[2] : SDE_K(SDE_ROT2_C2), u, SDE_K(SDE_ROT2_C1));
 #endif
   cm = cm * u;
-  const double ca = fma(C, cm, fma(-S, sn, C));
-  const double sb = fma(S, cm, fma(C, sn, S));
+  ca = fma(C, cm, fma(-S, sn, C));
+  sb = fma(S, cm, fma(C, sn, S));
+}
+SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double *tab, const double *lk, double &z0, double &z1,
+                               const double *kr = nullptr) {
+  double w, ca, sb;
+  normal_polar_f64_v2(a, b, c, tab, lk, w, ca, sb, kr);
+  const double g = sqrt_from_seed6(w, rsqrt_seed(w));
   z0 = g * ca;
   z1 = g * sb;
 }
@@ -595,6 +601,58 @@ static inline void h_scaled_tables(double dt, double *tab) {  // tab[SDE_TAB_DOU
 }
 #endif
 
+// A batch of U steps' worth of increments for one path: dW[u*M + j] ~ N(0, dt), generated from the path's
+// sub-stream blocks [blk0, blk0 + NB).  Flat normal index q = step*M + j follows the reference's draw order
+// (path outer, step inner, M draws left to right: src/simulation.jl:4-11,42-46).
+// V = normal-stream version (sdeb200_opts.rng): 1 = two FP64 normals per Philox block; 2 = eight per three blocks
+// (FP64 only; the FP32 stream is the same in both versions).
+template <typename T, int M, int V = 1> struct Batch {
+  static constexpr bool V2 = (V == 2) && sizeof(T) == 8;
+  static constexpr int NPB = NPC<T>::value;                              // normals per Philox block (v1)
+  static constexpr int U = (M == 0) ? 1 : (V2 ? 8 / sde_gcd(M, 8) : NPB / sde_gcd(M, NPB));   // steps per batch
+  static constexpr int NB = (M == 0) ? 0 : (V2 ? (U * M * 3) / 8 : (U * M) / NPB);             // Philox blocks per batch
+  static constexpr int NZ = (M == 0) ? 1 : U * M;
+};
+
+// Does the model functor take the polar form of a pair (Model::POLAR, Model::step_polar)?  Only hand-written FAST functors
+// declare it; generated functors and the STRICT build go through step<SCHEME>(…, dw, …).
+template <class Model> struct PolarOf {
+  template <class U> static constexpr int f(decltype(U::POLAR) *) { return U::POLAR; }
+  template <class U> static constexpr int f(...) { return 0; }
+  static constexpr int value = f<Model>(nullptr);
+};
+// The noise of one step as the kernels hand it to the model: M increments, or — for POLAR models on stream v2 in FP64
+// (M == 2: one pair per step) — the triple (w, ca, sb) with dW = sqrt(w) (ca, sb).  EVERY kernel form takes the same
+// branch for a given (model, precision, stream), so terminal values, trajectories and the fine path of a coupled level
+// stay bit-identical to one another.
+template <class Model, typename T, int V> struct Noise {
+  typedef Batch<T, Model::M, V> B;
+  static constexpr bool POLAR = PolarOf<Model>::value != 0 && B::V2 && Model::M == 2 && !SDE_STRICT;
+  static constexpr int STRIDE = POLAR ? 3 : (Model::M > 0 ? Model::M : 0);
+  static constexpr int NV = POLAR ? 3 * B::U : B::NZ;   // values per batch
+};
+template <class Model, int SCHEME, bool POLAR> struct NoiseStep {
+  template <typename T> SDE_HD static void run(const T *c, T t, T dt, const T *nz, T *x) {
+    Model::template step<SCHEME>(c, t, dt, nz, x);
+  }
+  template <typename T> SDE_HD static void increments(const T *nz, T *dw) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < Model::M; j++) dw[j] = nz[j];
+  }
+};
+template <class Model, int SCHEME> struct NoiseStep<Model, SCHEME, true> {
+  template <typename T> SDE_HD static void run(const T *c, T t, T dt, const T *nz, T *x) {
+    Model::step_polar(c, t, dt, nz[0], nz[1], nz[2], x);
+  }
+  template <typename T> SDE_HD static void increments(const T *nz, T *dw) {   // the pair itself, as normal_pair_f64_v2 forms it
+    const double g = sqrt_from_seed6((double)nz[0], rsqrt_seed((double)nz[0]));
+    dw[0] = (T)(g * (double)nz[1]);
+    dw[1] = (T)(g * (double)nz[2]);
+  }
+};
+
 #if defined(__CUDACC__)
 // ===================================================================================================
 // Device-only part: kernels
@@ -631,19 +689,6 @@ template <typename T> struct Consts {
   T c[SDE_MAXC];
 };
 
-// A batch of U steps' worth of increments for one path: dW[u*M + j] ~ N(0, dt), generated from the path's
-// sub-stream blocks [blk0, blk0 + NB).  Flat normal index q = step*M + j follows the reference's draw order
-// (path outer, step inner, M draws left to right: src/simulation.jl:4-11,42-46).
-// V = normal-stream version (sdeb200_opts.rng): 1 = two FP64 normals per Philox block; 2 = eight per three blocks
-// (FP64 only; the FP32 stream is the same in both versions).
-template <typename T, int M, int V = 1> struct Batch {
-  static constexpr bool V2 = (V == 2) && sizeof(T) == 8;
-  static constexpr int NPB = NPC<T>::value;                              // normals per Philox block (v1)
-  static constexpr int U = (M == 0) ? 1 : (V2 ? 8 / sde_gcd(M, 8) : NPB / sde_gcd(M, NPB));   // steps per batch
-  static constexpr int NB = (M == 0) ? 0 : (V2 ? (U * M * 3) / 8 : (U * M) / NPB);             // Philox blocks per batch
-  static constexpr int NZ = (M == 0) ? 1 : U * M;
-};
-
 // normals of one batch from its Philox words (V2: w[4*NB] holds the NB blocks back to back)
 template <typename T, int M, int V>
 SDE_HD void normals_from_words_v2(const uint32_t *w, const double *s_tab, const double *lk, T *dw, const double *kr) {
@@ -659,7 +704,23 @@ SDE_HD void normals_from_words_v2(const uint32_t *w, const double *s_tab, const 
   }
 }
 
-template <typename T, int M, int V = 1>
+// the same pairs in polar form, one triple (w, ca, sb) per step (M == 2; see Noise<> below)
+template <typename T, int M, int V>
+SDE_HD void polar_from_words_v2(const uint32_t *w, const double *s_tab, const double *lk, T *nz, const double *kr) {
+  typedef Batch<T, M, V> B;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int P = 0; P < B::NZ / 2; P++) {
+    double rw, ca, sb;
+    normal_polar_f64_v2(w[3 * P], w[3 * P + 1], w[3 * P + 2], s_tab, lk, rw, ca, sb, kr);
+    nz[3 * P] = (T)rw;
+    nz[3 * P + 1] = (T)ca;
+    nz[3 * P + 2] = (T)sb;
+  }
+}
+
+template <typename T, int M, int V = 1, bool POL = false>
 SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const PhiloxKeys &ks, const double *s_tab,
                      const double *lk, T scale2, T *dw, const double *kr = nullptr) {
   typedef Batch<T, M, V> B;
@@ -676,7 +737,8 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const Philox
 #pragma unroll
       for (int i = 0; i < 4; i++) w[4 * b + i] = r[i];
     }
-    normals_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
+    if (POL) polar_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
+    else normals_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
   } else {
 #pragma unroll
     for (int b = 0; b < B::NB; b++) {
@@ -706,7 +768,7 @@ struct PinnedCoef {
 };
 
 // gen_batch for a path whose round-0/1 invariants are precomputed (philox_path_init)
-template <typename T, int M, int V = 1>
+template <typename T, int M, int V = 1, bool POL = false>
 SDE_D void gen_batch(const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, const double *s_tab, const double *lk, T scale2,
                      T *dw, const double *kr = nullptr) {
   typedef Batch<T, M, V> B;
@@ -723,7 +785,8 @@ SDE_D void gen_batch(const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, 
 #pragma unroll
       for (int i = 0; i < 4; i++) w[4 * b + i] = r[i];
     }
-    normals_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
+    if (POL) polar_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
+    else normals_from_words_v2<T, M, V>(w, s_tab, lk, dw, kr);
   } else {
 #pragma unroll
     for (int b = 0; b < B::NB; b++) {
@@ -736,11 +799,11 @@ SDE_D void gen_batch(const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, 
 
 // FP64 kernels take the per-path Philox form and the pinned coefficients, FP32 kernels the plain block function
 // (measured 0.45 % faster there: fewer live registers); `pp` is dead code in the FP32 instantiations.
-template <typename T, int M, int V = 1>
+template <typename T, int M, int V = 1, bool POL = false>
 SDE_D void gen_batch(const PhiloxPath &pp, uint64_t path, uint32_t blk0, uint32_t stream, const PhiloxKeys &ks, const double *s_tab,
                      const double *lk, T scale2, T *dw, const double *kr) {
-  if (sizeof(T) == 8) gen_batch<T, M, V>(pp, blk0, ks, s_tab, lk, scale2, dw, kr);
-  else gen_batch<T, M, V>(path, blk0, stream, ks, s_tab, lk, scale2, dw);
+  if (sizeof(T) == 8) gen_batch<T, M, V, POL>(pp, blk0, ks, s_tab, lk, scale2, dw, kr);
+  else gen_batch<T, M, V, POL>(path, blk0, stream, ks, s_tab, lk, scale2, dw);
 }
 
 // Stream v2, step by step: the normals of step u of a batch are produced just before the step needs them — pair P is
@@ -774,6 +837,24 @@ template <typename T, int M> struct LazyV2 {
         z[2 * P + 1] = (T)z1;
       }
     }
+  }
+  // M == 2, POLAR models: step u reads pair P = u; the triple (w, ca, sb) goes straight to the model, nothing is kept in z
+  SDE_D void produce_polar(int u, const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, const double *s_tab, const double *lk,
+                           const double *kr, T *nz) {
+#pragma unroll
+    for (int b = 0; b < B::NB; b++) {
+      if (b >= blocks_before(u) && b < blocks_before(u + 1)) {
+        uint32_t r[4];
+        philox4x32_10(pp, blk0 + (uint32_t)b, ks, r);
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[4 * b + i] = r[i];
+      }
+    }
+    double rw, ca, sb;
+    normal_polar_f64_v2(w[3 * u], w[3 * u + 1], w[3 * u + 2], s_tab, lk, rw, ca, sb, kr);
+    nz[0] = (T)rw;
+    nz[1] = (T)ca;
+    nz[2] = (T)sb;
   }
 };
 
@@ -841,6 +922,7 @@ template <class Model, typename T, int SCHEME, int PPT, int V = 1>
 SDE_D void sample_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   typedef Batch<T, M, V> B;
+  typedef Noise<Model, T, V> NS;
   // transform tables: static shared memory, except the 40 KB of stream v2's fine tables, which come from the launch's
   // dynamic shared memory (static + the one-path-per-thread form's staging arrays would pass the 48 KB static limit)
   constexpr bool DYN_TAB = B::V2 && SDE_V2_FINE;
@@ -893,8 +975,14 @@ SDE_D void sample_body(const sde_args &a) {
           const T t = t0 + (T)(it * B::U + u) * dt;
 #pragma unroll
           for (int p = 0; p < PPT; p++) {
-            lz[p].produce(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr);
-            Model::template step<SCHEME>(cst.c, t, dt, lz[p].z + u * (M > 0 ? M : 0), x[p]);
+            if (NS::POLAR) {
+              T nz[3];
+              lz[p].produce_polar(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr, nz);
+              NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, nz, x[p]);
+            } else {
+              lz[p].produce(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr);
+              NoiseStep<Model, SCHEME, false>::run(cst.c, t, dt, lz[p].z + u * (M > 0 ? M : 0), x[p]);
+            }
           }
         }
       }
@@ -1026,6 +1114,7 @@ template <class Model, typename T, int SCHEME, int V = 1>
 SDE_D void mlmc_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   typedef Batch<T, M, V> B;
+  typedef Noise<Model, T, V> NS;
   __shared__ double s_tab[TabSize<T, V>::value];
   __shared__ double s_red[(SDE_BLOCK / 32) * 2 * SDE_MAXF];
   load_tables<T, V>(s_tab, a.noise_var);
@@ -1066,18 +1155,21 @@ SDE_D void mlmc_body(const sde_args &a) {
     constexpr int G = (B::U % 2 == 0) ? B::U : 2 * B::U, NBG = G / B::U;
     const int64_t ngroups = a.nsteps / G;
     for (int64_t gi = 0; gi < ngroups; gi++) {
-      T dw[NBG][B::NZ];
+      T dw[NBG][NS::NV];
 #pragma unroll
       for (int b = 0; b < NBG; b++)
-        gen_batch<T, M, V>(pp, gpath, (uint32_t)((gi * NBG + b) * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[b], pc.v);
+        gen_batch<T, M, V, NS::POLAR>(pp, gpath, (uint32_t)((gi * NBG + b) * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[b],
+                                      pc.v);
 #pragma unroll
       for (int j = 0; j < G; j++) {
         const T tc = t0 + (T)(gi * (G / 2) + j / 2) * dtc;
         const T tf = tc + (T)(j & 1) * dtf;
-        const T *dwu = dw[j / B::U] + (j % B::U) * (M > 0 ? M : 0);
+        const T *nzu = dw[j / B::U] + (j % B::U) * NS::STRIDE;
+        T dwu[M > 0 ? M : 1];
+        NoiseStep<Model, SCHEME, NS::POLAR>::increments(nzu, dwu);
 #pragma unroll
         for (int q = 0; q < M; q++) DW[q] = ((j & 1) ? DW[q] : (T)0) + dwu[q];
-        Model::template step<SCHEME>(cf.c, tf, dtf, dwu, xf);
+        NoiseStep<Model, SCHEME, NS::POLAR>::run(cf.c, tf, dtf, nzu, xf);
         if (j & 1) Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
       }
     }
@@ -1087,18 +1179,20 @@ SDE_D void mlmc_body(const sde_args &a) {
     for (int q = 0; q < (M > 0 ? M : 1); q++) DW[q] = (T)0;
   }
   for (; it < nbatch; it++) {
-    T dw[B::NZ];
-    gen_batch<T, M, V>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
+    T dw[NS::NV];
+    gen_batch<T, M, V, NS::POLAR>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
       const int64_t fstep = it * B::U + u;
       if (fstep < a.nsteps) {
         const T tc = t0 + (T)ncoarse * dtc;
         const T tf = tc + (T)sub * dtf;
-        const T *dwu = dw + u * (M > 0 ? M : 0);
+        const T *nzu = dw + u * NS::STRIDE;
+        T dwu[M > 0 ? M : 1];
+        NoiseStep<Model, SCHEME, NS::POLAR>::increments(nzu, dwu);
 #pragma unroll
         for (int j = 0; j < M; j++) DW[j] = DW[j] + dwu[j];
-        Model::template step<SCHEME>(cf.c, tf, dtf, dwu, xf);
+        NoiseStep<Model, SCHEME, NS::POLAR>::run(cf.c, tf, dtf, nzu, xf);
         if (++sub == substeps) {
           Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
 #pragma unroll
@@ -1183,6 +1277,7 @@ template <class Model, typename T, int SCHEME, int V = 1>
 SDE_D void simulate_soa_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M, VEC = SDE_SOA_VEC;
   typedef Batch<T, M, V> B;
+  typedef Noise<Model, T, V> NS;
   __shared__ double s_tab[TabSize<T, V>::value];
   load_tables<T, V>(s_tab, a.noise_var);
   PhiloxKeys ks;
@@ -1233,13 +1328,13 @@ SDE_D void simulate_soa_body(const sde_args &a) {
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U, nfull = a.nsteps / B::U;
   const T nv = (T)a.noise_var;
   auto batch = [&](int64_t it, bool full) {
-    T dw[VEC][B::NZ];
+    T dw[VEC][NS::NV];
 #pragma unroll
     for (int v = 0; v < VEC; v++)
 #if SDE_SOA_PP
-      gen_batch<T, M, V>(pp[v], gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, nv, dw[v], pc.v);
+      gen_batch<T, M, V, NS::POLAR>(pp[v], gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, nv, dw[v], pc.v);
 #else
-      gen_batch<T, M, V>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, nv, dw[v],
+      gen_batch<T, M, V, NS::POLAR>(gpath + (uint64_t)v, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, nv, dw[v],
                       sizeof(T) == 8 ? pc.v : nullptr);
 #endif
 #pragma unroll
@@ -1248,7 +1343,7 @@ SDE_D void simulate_soa_body(const sde_args &a) {
       if (full || i < a.nsteps) {
         const T t = t0 + (T)i * dt;
 #pragma unroll
-        for (int v = 0; v < VEC; v++) Model::template step<SCHEME>(cst.c, t, dt, dw[v] + u * (M > 0 ? M : 0), x[v]);
+        for (int v = 0; v < VEC; v++) NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw[v] + u * NS::STRIDE, x[v]);
         store_row(i + 1);
       }
     }
@@ -1322,6 +1417,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   constexpr int ROW = TS * D;                 // elements per path per tile
   constexpr int LDS = ROW | 1;                // odd stride: conflict-free column writes
   typedef Batch<T, M, V> B;
+  typedef Noise<Model, T, V> NS;
   __shared__ double s_tab[TabSize<T, V>::value];
   extern __shared__ __align__(16) unsigned char s_dyn[];   // [warps][32 * PW rows][LDS]: sde_simref_smem_bytes()
   load_tables<T, V>(s_tab, a.noise_var);
@@ -1371,10 +1467,10 @@ SDE_D void simulate_ref_body(const sde_args &a) {
   PinnedCoef pc(a.lk, sizeof(T) == 8, V);
   const int64_t nbatch = (a.nsteps + B::U - 1) / B::U;
   for (int64_t it = 0; it < nbatch; it++) {
-    T dw[PW][B::NZ];
+    T dw[PW][NS::NV];
 #pragma unroll
     for (int p = 0; p < PW; p++)
-      gen_batch<T, M, V>(pp[p], gpath + (uint64_t)(32 * p), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[p],
+      gen_batch<T, M, V, NS::POLAR>(pp[p], gpath + (uint64_t)(32 * p), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw[p],
                       pc.v);
 #pragma unroll
     for (int u = 0; u < B::U; u++) {
@@ -1382,7 +1478,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
       if (i < a.nsteps) {
         const T t = t0 + (T)i * dt;
 #pragma unroll
-        for (int p = 0; p < PW; p++) Model::template step<SCHEME>(cst.c, t, dt, dw[p] + u * (M > 0 ? M : 0), x[p]);
+        for (int p = 0; p < PW; p++) NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw[p] + u * NS::STRIDE, x[p]);
         if (fill == TS) flush();
         stage();
       }
@@ -1699,6 +1795,7 @@ template <class Model, typename T, int SCHEME, int V = 1>
 SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   constexpr int D = Model::D, M = Model::M;
   typedef Batch<T, M, V> B;
+  typedef Noise<Model, T, V> NS;
   constexpr int U = B::U;
   constexpr int ROWB = D * (int)sizeof(T);
   constexpr int BB = U * ROWB;                                   // bytes per batch and lane
@@ -1825,14 +1922,14 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 #pragma unroll
     for (int d = 0; d < D; d++) carry[c][d] = x[d];
   auto slow_batch = [&](int64_t it) {
-    T dw[B::NZ];
-    gen_batch<T, M, V>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
+    T dw[NS::NV];
+    gen_batch<T, M, V, NS::POLAR>(pp, gpath, (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk, (T)a.noise_var, dw, pc.v);
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int64_t i = it * U + u;
       if (i < a.nsteps) {
         const T t = t0 + (T)i * dt;
-        Model::template step<SCHEME>(cst.c, t, dt, dw + u * M, x);
+        NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw + u * NS::STRIDE, x);
         emit_row((int)i + 1, x);
 #pragma unroll
         for (int c = 0; c + 1 < RPC - 1; c++)
@@ -1861,19 +1958,19 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
   int cpos = 0, kt = 0, ks_ = 0;                                   // ks_ = kt % NSTG
   uint32_t blk = 0;
   int tb = 0;
-  T dwn[B::NZ];                                                    // SDE_SIMRT2_PREFETCH: the normals of the next batch
+  T dwn[NS::NV];                                                    // SDE_SIMRT2_PREFETCH: the normals of the next batch
   auto fast_batch = [&](auto phc, auto msc) {
     constexpr int PHC = decltype(phc)::value;
     constexpr int MS = decltype(msc)::value;   // mshift % NCB: chunks of a tile-crossing batch that still belong to the old tile
-    T dw[B::NZ];
+    T dw[NS::NV];
 #if SDE_SIMRT2_PREFETCH
     // software pipeline: the normals of the NEXT batch are produced while this batch's steps run — the generator does not
     // depend on the state, so the two chains interleave in one basic block (one path per lane has no other parallelism)
 #pragma unroll
-    for (int i = 0; i < B::NZ; i++) dw[i] = dwn[i];
-    gen_batch<T, M, V>(pp, gpath, blk + (uint32_t)B::NB, a.stream, ks, s_tab, a.lk, nv, dwn, pc.v);
+    for (int i = 0; i < NS::NV; i++) dw[i] = dwn[i];
+    gen_batch<T, M, V, NS::POLAR>(pp, gpath, blk + (uint32_t)B::NB, a.stream, ks, s_tab, a.lk, nv, dwn, pc.v);
 #else
-    gen_batch<T, M, V>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dw, pc.v);
+    gen_batch<T, M, V, NS::POLAR>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dw, pc.v);
 #endif
     T seq[PHC + U][D];                                             // carry rows, then the U new rows
 #pragma unroll
@@ -1883,7 +1980,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const T t = t0 + (T)(tb + u) * dt;
-      Model::template step<SCHEME>(cst.c, t, dt, dw + u * M, x);
+      NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw + u * NS::STRIDE, x);
 #pragma unroll
       for (int d = 0; d < D; d++) seq[PHC + u][d] = x[d];
     }
@@ -1954,7 +2051,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
     tb = (int)(it * U);
     if (cpos == 0) acquire(kt);
 #if SDE_SIMRT2_PREFETCH
-    gen_batch<T, M, V>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dwn, pc.v);
+    gen_batch<T, M, V, NS::POLAR>(pp, gpath, blk, a.stream, ks, s_tab, a.lk, nv, dwn, pc.v);
 #endif
     const int ms = MSMAX > 0 ? mshift % NCB : 0;
     int nb = (int)(it1 - it);                                       // 32-bit loop counter (nsteps < 2^28)

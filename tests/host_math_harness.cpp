@@ -1,6 +1,6 @@
 // Compiles the math helpers of sde_device.cuh with g++ (no CUDA) so the Philox block function and the
 // fused normal transforms can be checked on the CPU against oracle/philox_spec.c.
-#include "../sdemodels.jl_b200/csrc/sde_device.cuh"
+#include "../sdemodels.jl_b200/csrc/sde_models_builtin.cuh"
 using namespace sdeb200;
 
 extern "C" void h_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
@@ -90,4 +90,24 @@ extern "C" void h_log_fast(const double *x, int64_t n, double *out) {
 }
 extern "C" void h_rcp_fast(const double *x, int64_t n, double *out) {
   for (int64_t i = 0; i < n; i++) out[i] = rcp_fast(x[i]);
+}
+// the polar form of the Heston step (FAST math, stream v2: one sqrt of V*w) beside the plain form on the pair sqrt(w) (ca, sb)
+extern "C" void h_heston_polar(const double *params, double dt, const uint32_t *w3, const double *x_in, double *x_polar, double *x_plain) {
+  static_assert(PolarOf<Heston>::value == 1 && PolarOf<BlackScholes>::value == 0, "only Heston declares the polar form");
+  static_assert(Noise<Heston, double, 2>::POLAR && !Noise<Heston, double, 1>::POLAR && !Noise<Heston, float, 2>::POLAR, "FP64 + stream v2 only");
+  static double tab[SDE_TAB2_DOUBLES];
+  double lk[6], c[SDE_MAXC], w, ca, sb, z[2];
+  h_scaled_tables_v2(dt, tab);
+  make_log_consts_v2(dt, lk);
+  Heston::prepare(params, dt, c);
+  normal_polar_f64_v2(w3[0], w3[1], w3[2], tab, lk, w, ca, sb);
+  normal_pair_f64_v2(w3[0], w3[1], w3[2], tab, lk, z[0], z[1]);
+  const double nz[3] = {w, ca, sb};
+  double dw[2];
+  NoiseStep<Heston, 0, true>::increments(nz, dw);
+  if (dw[0] != z[0] || dw[1] != z[1]) { x_polar[0] = x_polar[1] = -1.0; return; }   // increments() must be the pair itself
+  x_polar[0] = x_plain[0] = x_in[0];
+  x_polar[1] = x_plain[1] = x_in[1];
+  NoiseStep<Heston, 0, true>::run(c, 0.0, dt, nz, x_polar);
+  NoiseStep<Heston, 0, false>::run(c, 0.0, dt, z, x_plain);
 }
