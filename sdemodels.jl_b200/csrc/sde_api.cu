@@ -896,9 +896,6 @@ extern "C" int sdeb200_model_coefficients(sdeb200_model *m, const double *params
 // ---------------------------------------------------------------------------------------------------
 // sample
 // ---------------------------------------------------------------------------------------------------
-#ifndef SDE_PPT
-#define SDE_PPT 4
-#endif
 static int64_t sample_grid(int64_t npaths) { return cdiv(npaths, (int64_t)SDE_BLOCK * SDE_PPT); }
 // Terminal-value launch: chunks of SDE_BLOCK*SDE_PPT = 512 paths either way; launches too small to fill the GPU with
 // SDE_PPT paths per thread (148 SMs x ~32 warps x 32 lanes x 4 paths ~ 600 k) use the one-path-per-thread form,
@@ -913,7 +910,8 @@ static int launch_sample(const sdeb200_model *m, const sde_ktable *kt, const sde
   // stream v2's fine transform tables live in dynamic shared memory (sample_body)
   const size_t smem = (kslot(o) == 2 && SDE_V2_FINE) ? (size_t)SDE_TAB2_DOUBLES * 8 : 0;
   if (k1 && invariant && a->npaths <= g_sample1_max) return launch(k1, grid, a, st, smem, SDE_BLOCK * SDE_PPT);
-  return launch(kt->sample[o->scheme][kslot(o)], grid, a, st, smem);
+  // the FP64 kernel of stream v2 carries SDE_PPT_V2 paths per thread in correspondingly larger CTAs (same chunks)
+  return launch(kt->sample[o->scheme][kslot(o)], grid, a, st, smem, SDE_SAMPLE_THREADS(kslot(o) == 2));
 }
 
 extern "C" int sdeb200_sample(sdeb200_model *m, const sdeb200_opts *o, const double *params, const double *x0,

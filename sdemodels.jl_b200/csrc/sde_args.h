@@ -20,6 +20,15 @@ typedef long long int64_t;
 #ifndef SDE_BLOCK
 #define SDE_BLOCK 128     /* threads per CTA for every path kernel */
 #endif
+#ifndef SDE_PPT
+#define SDE_PPT 4         /* paths per thread in the terminal-value kernel (instruction-level parallelism); a CTA works on chunks
+                             of SDE_BLOCK * SDE_PPT = 512 consecutive paths, whose summation tree defines the payoff partials */
+#endif
+#ifndef SDE_PPT_V2
+#define SDE_PPT_V2 2      /* the same for the FP64 kernel of normal stream v2: the same 512-path chunks and summation tree with
+                             SDE_BLOCK * SDE_PPT / SDE_PPT_V2 = 256 threads per CTA (sample_body's staged form) */
+#endif
+#define SDE_SAMPLE_THREADS(v2_f64) ((v2_f64) ? SDE_BLOCK * SDE_PPT / SDE_PPT_V2 : SDE_BLOCK)
 #define SDE_TAB_DOUBLES 2304 /* FP64 transform tables in shared memory: 256 (log) + 2048 (rotation) */
 /* SDE_V2_FINE = 1 (default): normal stream v2 evaluates its transform on finer tables — 512 log cells (|r| <= 2^-10: three
  * FMAs instead of four) and 2048 rotation cells (|phi| <= pi/2048: one-term sine residual) — 40 KB of shared memory per

@@ -24,8 +24,8 @@
 #define SDE_HD inline
 #endif
 
-#ifndef SDE_PPT
-#define SDE_PPT 4 /* paths per thread in the terminal-value kernel (instruction-level parallelism) */
+#ifndef SDE_V2_UNROLL
+#define SDE_V2_UNROLL 1 /* batches per iteration of the stream-v2 terminal kernel's time loop */
 #endif
 #ifndef SDE_PHILOX_ROUNDS
 #define SDE_PHILOX_ROUNDS 10 /* Philox4x32-10, the Random123 / cuRAND default; other values are tuning experiments only */
@@ -967,25 +967,29 @@ SDE_D void sample_body(const sde_args &a) {
   if (B::V2 && M > 0) {
     // stream v2: step-major order inside a batch, normals produced lazily (LazyV2) — the same arithmetic per path
     LazyV2<T, (M > 0 ? M : 1)> lz[PPT];
-    for (int64_t it = 0; it <= nbatch; it++) {
-      if (it == nbatch && rem == 0) break;
+    auto one_step = [&](int64_t it, int u) {   // u is a constant after unrolling
+      const T t = t0 + (T)(it * B::U + u) * dt;
 #pragma unroll
-      for (int u = 0; u < B::U; u++) {
-        if (it < nbatch || u < rem) {
-          const T t = t0 + (T)(it * B::U + u) * dt;
-#pragma unroll
-          for (int p = 0; p < PPT; p++) {
-            if (NS::POLAR) {
-              T nz[3];
-              lz[p].produce_polar(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr, nz);
-              NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, nz, x[p]);
-            } else {
-              lz[p].produce(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr);
-              NoiseStep<Model, SCHEME, false>::run(cst.c, t, dt, lz[p].z + u * (M > 0 ? M : 0), x[p]);
-            }
-          }
+      for (int p = 0; p < PPT; p++) {
+        if (NS::POLAR) {
+          T nz[3];
+          lz[p].produce_polar(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr, nz);
+          NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, nz, x[p]);
+        } else {
+          lz[p].produce(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr);
+          NoiseStep<Model, SCHEME, false>::run(cst.c, t, dt, lz[p].z + u * (M > 0 ? M : 0), x[p]);
         }
       }
+    };
+#pragma unroll SDE_V2_UNROLL
+    for (int64_t it = 0; it < nbatch; it++) {   // whole batches: no per-step conditions
+#pragma unroll
+      for (int u = 0; u < B::U; u++) one_step(it, u);
+    }
+    if (rem > 0) {
+#pragma unroll
+      for (int u = 0; u < B::U; u++)
+        if (u < rem) one_step(nbatch, u);
     }
   } else {
   for (int64_t it = 0; it < nbatch; it++) {
@@ -2506,8 +2510,13 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #define SDE_SAMPLE_MINB 1
 #endif
 #ifndef SDE_SAMPLE_MINB_V2
-#define SDE_SAMPLE_MINB_V2 2 /* stream v2 terminal kernel: measured 245.6 (2 CTAs, 214 registers) vs 232.3 (3 CTAs, 164) vs 220.6 G path-steps/s (4 CTAs, 128): the same instruction count, better scheduled with more registers */
+#define SDE_SAMPLE_MINB_V2 2 /* stream v2 terminal kernel, SDE_PPT_V2 = 2 paths per thread in 256-thread CTAs (sde_args.h): two
+                                CTAs = 16 warps per SM at <= 128 registers.  Measured with the polar Heston step (G path-steps/s,
+                                profiles/r02x_ab_occupancy.txt): 4 paths per thread 270.6 (204 registers, 8 warps per SM; 168
+                                registers / 12 warps: the same), 2 paths per thread 275.9 (118 registers, 16 warps) / 269.7 (96,
+                                20 warps) / 256.1 (80, 24 warps), 1 path per thread 250.1 (75 registers) / 231.2 (64) */
 #endif
+#define SDE_PPT_OF(T, V) ((sizeof(T) == 8 && (V) == 2) ? SDE_PPT_V2 : SDE_PPT)
 #ifndef SDE_SAMPLE1_MINB
 #define SDE_SAMPLE1_MINB 0
 #endif
@@ -2530,9 +2539,9 @@ SDE_D void coef_eval_body(const sde_args &a) {
 // TRAJ = the RNG-driven trajectory kernels, WIENER = the Wiener-driven ones (no noise: no stream version).
 // The reference defines Milstein for M == 1 models only (milstein.jl:4): instantiate SCH = 1, 2 only there.
 #define SDE_KERNELS_TERMINAL(MODEL, TAG, SCH, SNAME, T, V, SUF)                                                  \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK, sizeof(T) == 8 ? (V == 2 ? SDE_SAMPLE_MINB_V2 : SDE_SAMPLE_MINB) : SDE_SAMPLE_MINB_F32) \
+  extern "C" __global__ void __launch_bounds__(SDE_SAMPLE_THREADS(sizeof(T) == 8 && V == 2), sizeof(T) == 8 ? (V == 2 ? SDE_SAMPLE_MINB_V2 : SDE_SAMPLE_MINB) : SDE_SAMPLE_MINB_F32) \
       sdek_##TAG##_sample_##SNAME##_##SUF(                                                                       \
-      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT, V>(a); }               \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, SDE_PPT_OF(T, V), V>(a); }      \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT, sizeof(T) == 8 ? SDE_SAMPLE1_MINB : 0)        \
       sdek_##TAG##_sample1_##SNAME##_##SUF(                                                                      \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, T, SCH, 1, V>(a); }                     \
@@ -2578,8 +2587,8 @@ SDE_D void coef_eval_body(const sde_args &a) {
       const __grid_constant__ sde_args a) { sdeb200::simulate_ref_tma2_body<MODEL, T, 3>(a); }
 
 #define SDE_KERNELS_EXACT_V2(MODEL, TAG)                                                                          \
-  extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_sample_exact_f64v2(                      \
-      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, 3, SDE_PPT, 2>(a); }            \
+  extern "C" __global__ void __launch_bounds__(SDE_SAMPLE_THREADS(1)) sdek_##TAG##_sample_exact_f64v2(          \
+      const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, 3, SDE_PPT_V2, 2>(a); }         \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK * SDE_PPT) sdek_##TAG##_sample1_exact_f64v2(           \
       const __grid_constant__ sde_args a) { sdeb200::sample_body<MODEL, double, 3, 1, 2>(a); }                  \
   extern "C" __global__ void __launch_bounds__(SDE_BLOCK) sdek_##TAG##_simsoa_exact_f64v2(                      \
