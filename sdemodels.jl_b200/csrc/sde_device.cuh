@@ -981,7 +981,8 @@ SDE_D void sample_body(const sde_args &a) {
         }
       }
     };
-#pragma unroll SDE_V2_UNROLL
+    constexpr int UNR = SDE_V2_UNROLL;   // (a macro is not expanded inside the pragma)
+#pragma unroll UNR
     for (int64_t it = 0; it < nbatch; it++) {   // whole batches: no per-step conditions
 #pragma unroll
       for (int u = 0; u < B::U; u++) one_step(it, u);
