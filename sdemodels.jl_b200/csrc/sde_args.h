@@ -25,8 +25,10 @@ typedef long long int64_t;
                              of SDE_BLOCK * SDE_PPT = 512 consecutive paths, whose summation tree defines the payoff partials */
 #endif
 #ifndef SDE_PPT_V2
-#define SDE_PPT_V2 2      /* the same for the FP64 kernel of normal stream v2: the same 512-path chunks and summation tree with
-                             SDE_BLOCK * SDE_PPT / SDE_PPT_V2 = 256 threads per CTA (sample_body's staged form) */
+#define SDE_PPT_V2 4      /* the same for the FP64 kernel of normal stream v2 as its own switch: with 2, the same 512-path chunks
+                             and summation tree run in SDE_BLOCK * SDE_PPT / SDE_PPT_V2 = 256-thread CTAs (sample_body's staged
+                             form): 118 registers / 16 warps per SM instead of 204 / 8.  Measured (profiles/r02y_ab_loop.txt):
+                             295.2 G path-steps/s with 4, 292.4 with 2 */
 #endif
 #define SDE_SAMPLE_THREADS(v2_f64) ((v2_f64) ? SDE_BLOCK * SDE_PPT / SDE_PPT_V2 : SDE_BLOCK)
 #define SDE_TAB_DOUBLES 2304 /* FP64 transform tables in shared memory: 256 (log) + 2048 (rotation) */

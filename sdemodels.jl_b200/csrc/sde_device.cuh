@@ -288,8 +288,9 @@ SDE_HD void make_log_consts(double dt, double *lk) {
 
 // kr (optional): register-resident copies of the three leading polynomial coefficients {lk[3], ROT_S2, ROT_C2}; a DFMA takes
 // one uniform-register operand only, so a leading coefficient read from constant memory costs two moves per use.
-SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const double *lk, double &z0, double &z1,
-                            const double *kr = nullptr) {
+// Polar form: radius^2 `w` (already scaled by the step's variance) and the unit vector (ca, sb); the pair is sqrt(w) (ca, sb).
+SDE_HD void normal_polar_f64(const uint32_t (&r)[4], const double *tab, const double *lk, double &w, double &ca, double &sb,
+                             const double *kr = nullptr) {
   const uint64_t X1 = ((uint64_t)r[1] << 32) | r[0];
   const double d1 = (double)X1;
   const uint32_t h1 = double2hi(d1);
@@ -310,9 +311,8 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const dou
   q = fma(q, rr, lk[1]);
   q = fma(q, rr, lk[0]);
   q = fma(q, rr, lk[4]);
-  double w = fma(rr, q, tl);
+  w = fma(rr, q, tl);
   w = fma(kd, lk[5], w);
-  const double g = sqrt_core(w);  // radius, already scaled by sqrt(dt)
   // angle = X2 / 2^64 turns = (i + 1/2 + d) / 1024: the top 10 bits pick {cos, sin} of the cell centre from a
   // 1024-entry table, the low 54 bits (re-centred) are the offset t = 2^54 d, |t| <= 2^53 (exact in a double);
   // the residual rotation |phi| <= pi/1024 needs two-term polynomials; no quadrant logic.
@@ -326,8 +326,14 @@ SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const dou
   const double sn = t * sp;                       // sin(phi)
   double cm = fma(kr ? kr[2] : SDE_K(SDE_ROT_C2), u, SDE_K(SDE_ROT_C1));
   cm = cm * u;                                    // cos(phi) - 1
-  const double ca = fma(C, cm, fma(-S, sn, C));   // cos(theta_i + phi) = C + C (cos phi - 1) - S sin phi
-  const double sb = fma(S, cm, fma(C, sn, S));    // sin(theta_i + phi) = S + S (cos phi - 1) + C sin phi
+  ca = fma(C, cm, fma(-S, sn, C));   // cos(theta_i + phi) = C + C (cos phi - 1) - S sin phi
+  sb = fma(S, cm, fma(C, sn, S));    // sin(theta_i + phi) = S + S (cos phi - 1) + C sin phi
+}
+SDE_HD void normal_pair_f64(const uint32_t (&r)[4], const double *tab, const double *lk, double &z0, double &z1,
+                            const double *kr = nullptr) {
+  double w, ca, sb;
+  normal_polar_f64(r, tab, lk, w, ca, sb, kr);
+  const double g = sqrt_core(w);  // radius, already scaled by sqrt(dt)
   z0 = g * ca;
   z1 = g * sb;
 }
@@ -621,17 +627,17 @@ template <class Model> struct PolarOf {
   template <class U> static constexpr int f(...) { return 0; }
   static constexpr int value = f<Model>(nullptr);
 };
-// The noise of one step as the kernels hand it to the model: M increments, or — for POLAR models on stream v2 in FP64
-// (M == 2: one pair per step) — the triple (w, ca, sb) with dW = sqrt(w) (ca, sb).  EVERY kernel form takes the same
+// The noise of one step as the kernels hand it to the model: M increments, or — for POLAR models in FP64 (M == 2: one
+// pair per step, on either normal stream) — the triple (w, ca, sb) with dW = sqrt(w) (ca, sb).  EVERY kernel form takes the same
 // branch for a given (model, precision, stream), so terminal values, trajectories and the fine path of a coupled level
 // stay bit-identical to one another.
 template <class Model, typename T, int V> struct Noise {
   typedef Batch<T, Model::M, V> B;
-  static constexpr bool POLAR = PolarOf<Model>::value != 0 && B::V2 && Model::M == 2 && !SDE_STRICT;
+  static constexpr bool POLAR = PolarOf<Model>::value != 0 && sizeof(T) == 8 && Model::M == 2 && !SDE_STRICT;
   static constexpr int STRIDE = POLAR ? 3 : (Model::M > 0 ? Model::M : 0);
   static constexpr int NV = POLAR ? 3 * B::U : B::NZ;   // values per batch
 };
-template <class Model, int SCHEME, bool POLAR> struct NoiseStep {
+template <class Model, int SCHEME, bool POLAR, int V = 1> struct NoiseStep {
   template <typename T> SDE_HD static void run(const T *c, T t, T dt, const T *nz, T *x) {
     Model::template step<SCHEME>(c, t, dt, nz, x);
   }
@@ -642,12 +648,12 @@ template <class Model, int SCHEME, bool POLAR> struct NoiseStep {
     for (int j = 0; j < Model::M; j++) dw[j] = nz[j];
   }
 };
-template <class Model, int SCHEME> struct NoiseStep<Model, SCHEME, true> {
+template <class Model, int SCHEME, int V> struct NoiseStep<Model, SCHEME, true, V> {
   template <typename T> SDE_HD static void run(const T *c, T t, T dt, const T *nz, T *x) {
     Model::step_polar(c, t, dt, nz[0], nz[1], nz[2], x);
   }
-  template <typename T> SDE_HD static void increments(const T *nz, T *dw) {   // the pair itself, as normal_pair_f64_v2 forms it
-    const double g = sqrt_from_seed6((double)nz[0], rsqrt_seed((double)nz[0]));
+  template <typename T> SDE_HD static void increments(const T *nz, T *dw) {   // the pair itself, as normal_pair_f64[_v2] forms it
+    const double g = V == 2 ? sqrt_from_seed6((double)nz[0], rsqrt_seed((double)nz[0])) : sqrt_core((double)nz[0]);
     dw[0] = (T)(g * (double)nz[1]);
     dw[1] = (T)(g * (double)nz[2]);
   }
@@ -704,6 +710,15 @@ SDE_HD void normals_from_words_v2(const uint32_t *w, const double *s_tab, const 
   }
 }
 
+// stream v1, FP64: the pair of one Philox block in polar form (M == 2: one block per step)
+template <typename T>
+SDE_HD void polar_from_block(const uint32_t (&r)[4], const double *tab, const double *lk, T *nz, const double *kr) {
+  double rw, ca, sb;
+  normal_polar_f64(r, tab, lk, rw, ca, sb, kr);
+  nz[0] = (T)rw;
+  nz[1] = (T)ca;
+  nz[2] = (T)sb;
+}
 // the same pairs in polar form, one triple (w, ca, sb) per step (M == 2; see Noise<> below)
 template <typename T, int M, int V>
 SDE_HD void polar_from_words_v2(const uint32_t *w, const double *s_tab, const double *lk, T *nz, const double *kr) {
@@ -744,7 +759,8 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const Philox
     for (int b = 0; b < B::NB; b++) {
       uint32_t r[4];
       philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, ks, r);
-      normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
+      if (POL) polar_from_block(r, s_tab, lk, dw + 3 * b, kr);
+      else normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
     }
   }
 }
@@ -792,7 +808,8 @@ SDE_D void gen_batch(const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, 
     for (int b = 0; b < B::NB; b++) {
       uint32_t r[4];
       philox4x32_10(pp, blk0 + (uint32_t)b, ks, r);
-      normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
+      if (POL) polar_from_block(r, s_tab, lk, dw + 3 * b, kr);
+      else normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
     }
   }
 }
@@ -974,7 +991,7 @@ SDE_D void sample_body(const sde_args &a) {
         if (NS::POLAR) {
           T nz[3];
           lz[p].produce_polar(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr, nz);
-          NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, nz, x[p]);
+          NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cst.c, t, dt, nz, x[p]);
         } else {
           lz[p].produce(u, pp[p], (uint32_t)(it * B::NB), ks, s_tab, a.lk, kr);
           NoiseStep<Model, SCHEME, false>::run(cst.c, t, dt, lz[p].z + u * (M > 0 ? M : 0), x[p]);
@@ -996,27 +1013,27 @@ SDE_D void sample_body(const sde_args &a) {
   for (int64_t it = 0; it < nbatch; it++) {
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
-      T dw[B::NZ];
-      gen_batch<T, M, V>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, ks, s_tab, a.lk,
-                      (T)a.noise_var, dw, kr);
+      T dw[NS::NV];
+      gen_batch<T, M, V, NS::POLAR>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(it * B::NB), a.stream, ks, s_tab,
+                                    a.lk, (T)a.noise_var, dw, kr);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         const T t = t0 + (T)(it * B::U + u) * dt;
-        Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x[p]);
+        NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cst.c, t, dt, dw + u * NS::STRIDE, x[p]);
       }
     }
   }
   if (rem > 0) {
 #pragma unroll
     for (int p = 0; p < PPT; p++) {
-      T dw[B::NZ];
-      gen_batch<T, M, V>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, ks, s_tab, a.lk,
-                      (T)a.noise_var, dw, kr);
+      T dw[NS::NV];
+      gen_batch<T, M, V, NS::POLAR>(pp[p], gpath0 + (uint64_t)(p * (int)blockDim.x), (uint32_t)(nbatch * B::NB), a.stream, ks, s_tab,
+                                    a.lk, (T)a.noise_var, dw, kr);
 #pragma unroll
       for (int u = 0; u < B::U; u++) {
         if (u < rem) {
           const T t = t0 + (T)(nbatch * B::U + u) * dt;
-          Model::template step<SCHEME>(cst.c, t, dt, dw + u * (M > 0 ? M : 0), x[p]);
+          NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cst.c, t, dt, dw + u * NS::STRIDE, x[p]);
         }
       }
     }
@@ -1171,10 +1188,10 @@ SDE_D void mlmc_body(const sde_args &a) {
         const T tf = tc + (T)(j & 1) * dtf;
         const T *nzu = dw[j / B::U] + (j % B::U) * NS::STRIDE;
         T dwu[M > 0 ? M : 1];
-        NoiseStep<Model, SCHEME, NS::POLAR>::increments(nzu, dwu);
+        NoiseStep<Model, SCHEME, NS::POLAR, V>::increments(nzu, dwu);
 #pragma unroll
         for (int q = 0; q < M; q++) DW[q] = ((j & 1) ? DW[q] : (T)0) + dwu[q];
-        NoiseStep<Model, SCHEME, NS::POLAR>::run(cf.c, tf, dtf, nzu, xf);
+        NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cf.c, tf, dtf, nzu, xf);
         if (j & 1) Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
       }
     }
@@ -1194,10 +1211,10 @@ SDE_D void mlmc_body(const sde_args &a) {
         const T tf = tc + (T)sub * dtf;
         const T *nzu = dw + u * NS::STRIDE;
         T dwu[M > 0 ? M : 1];
-        NoiseStep<Model, SCHEME, NS::POLAR>::increments(nzu, dwu);
+        NoiseStep<Model, SCHEME, NS::POLAR, V>::increments(nzu, dwu);
 #pragma unroll
         for (int j = 0; j < M; j++) DW[j] = DW[j] + dwu[j];
-        NoiseStep<Model, SCHEME, NS::POLAR>::run(cf.c, tf, dtf, nzu, xf);
+        NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cf.c, tf, dtf, nzu, xf);
         if (++sub == substeps) {
           Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
 #pragma unroll
@@ -1348,7 +1365,7 @@ SDE_D void simulate_soa_body(const sde_args &a) {
       if (full || i < a.nsteps) {
         const T t = t0 + (T)i * dt;
 #pragma unroll
-        for (int v = 0; v < VEC; v++) NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw[v] + u * NS::STRIDE, x[v]);
+        for (int v = 0; v < VEC; v++) NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cst.c, t, dt, dw[v] + u * NS::STRIDE, x[v]);
         store_row(i + 1);
       }
     }
@@ -1483,7 +1500,7 @@ SDE_D void simulate_ref_body(const sde_args &a) {
       if (i < a.nsteps) {
         const T t = t0 + (T)i * dt;
 #pragma unroll
-        for (int p = 0; p < PW; p++) NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw[p] + u * NS::STRIDE, x[p]);
+        for (int p = 0; p < PW; p++) NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cst.c, t, dt, dw[p] + u * NS::STRIDE, x[p]);
         if (fill == TS) flush();
         stage();
       }
@@ -1934,7 +1951,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
       const int64_t i = it * U + u;
       if (i < a.nsteps) {
         const T t = t0 + (T)i * dt;
-        NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw + u * NS::STRIDE, x);
+        NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cst.c, t, dt, dw + u * NS::STRIDE, x);
         emit_row((int)i + 1, x);
 #pragma unroll
         for (int c = 0; c + 1 < RPC - 1; c++)
@@ -1985,7 +2002,7 @@ SDE_D void simulate_ref_tma2_body(const sde_args &a) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const T t = t0 + (T)(tb + u) * dt;
-      NoiseStep<Model, SCHEME, NS::POLAR>::run(cst.c, t, dt, dw + u * NS::STRIDE, x);
+      NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cst.c, t, dt, dw + u * NS::STRIDE, x);
 #pragma unroll
       for (int d = 0; d < D; d++) seq[PHC + u][d] = x[d];
     }
@@ -2511,11 +2528,12 @@ SDE_D void coef_eval_body(const sde_args &a) {
 #define SDE_SAMPLE_MINB 1
 #endif
 #ifndef SDE_SAMPLE_MINB_V2
-#define SDE_SAMPLE_MINB_V2 2 /* stream v2 terminal kernel, SDE_PPT_V2 = 2 paths per thread in 256-thread CTAs (sde_args.h): two
-                                CTAs = 16 warps per SM at <= 128 registers.  Measured with the polar Heston step (G path-steps/s,
-                                profiles/r02x_ab_occupancy.txt): 4 paths per thread 270.6 (204 registers, 8 warps per SM; 168
-                                registers / 12 warps: the same), 2 paths per thread 275.9 (118 registers, 16 warps) / 269.7 (96,
-                                20 warps) / 256.1 (80, 24 warps), 1 path per thread 250.1 (75 registers) / 231.2 (64) */
+#define SDE_SAMPLE_MINB_V2 2 /* stream v2 terminal kernel: two CTAs per SM.  Measured with the polar Heston step, G path-steps/s
+                                (profiles/r02x_ab_occupancy.txt, BEFORE the time loop lost its per-step conditions): 4 paths per
+                                thread 270.6 (204 registers, 8 warps per SM; 168 registers / 12 warps: the same), 2 paths per
+                                thread 275.9 (118 registers, 16 warps) / 269.7 (96, 20 warps) / 256.1 (80, 24 warps), 1 path per
+                                thread 250.1 (75 registers) / 231.2 (64); with the unconditional loop (r02y_ab_loop.txt) 4 paths
+                                per thread lead again: 295.2 against 292.4 */
 #endif
 #define SDE_PPT_OF(T, V) ((sizeof(T) == 8 && (V) == 2) ? SDE_PPT_V2 : SDE_PPT)
 #ifndef SDE_SAMPLE1_MINB

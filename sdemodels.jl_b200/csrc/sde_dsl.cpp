@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <memory>
 #include <set>
@@ -777,6 +778,54 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
         out->milstein_error = e.what();
       }
     }
+    // Polar form of the step (M == 2): when every non-zero diffusion entry is a product that carries the same factor
+    // sqrt(A) with A depending on the state (Heston-type models: sqrt(V) in every noise term), the FP64 kernels hand the
+    // model a pair as (w, ca, sb) with dW = sqrt(w) (ca, sb), and the step takes ONE square root of A*w instead of the
+    // radius' and the model's (sde_device.cuh: Noise<>, PolarOf<>; the hand-written Heston functor does the same).
+    bool have_polar = false;
+    E polar_arg;
+    Mat prest(D, std::vector<E>(M > 0 ? M : 1));
+    if (M == 2) {
+      std::function<void(const E &, std::vector<E> &)> factors = [&](const E &e, std::vector<E> &f) {
+        if (e->kind == Expr::CALL && e->name == "*") for (auto &a : e->args) factors(a, f);
+        else f.push_back(e);
+      };
+      std::vector<std::vector<E>> fl;   // factor lists of the non-zero entries, row-major
+      for (int i = 0; i < D; i++)
+        for (int j = 0; j < M; j++)
+          if (!is_val(diffm[i][j], 0)) { fl.emplace_back(); factors(diffm[i][j], fl.back()); }
+      E cand;
+      if (!fl.empty())
+        for (auto &f : fl[0]) {
+          if (!(f->kind == Expr::CALL && f->name == "sqrt" && f->args.size() == 1 && depends_on(f->args[0], dyn))) continue;
+          bool all = true;
+          for (auto &g : fl) {
+            bool found = false;
+            for (auto &h : g) found = found || equal(h, f);
+            all = all && found;
+          }
+          if (all) { cand = f; break; }
+        }
+      if (cand) {
+        have_polar = true;
+        polar_arg = hoist(cand->args[0], dyn, hoisted);
+        size_t k = 0;
+        for (int i = 0; i < D; i++)
+          for (int j = 0; j < M; j++) {
+            if (is_val(diffm[i][j], 0)) continue;
+            std::vector<E> rest;
+            bool dropped = false;
+            for (auto &h : fl[k]) {
+              if (!dropped && equal(h, cand)) { dropped = true; continue; }   // one occurrence of the common factor
+              rest.push_back(h);
+            }
+            k++;
+            E r = rest.empty() ? mk_num(1, true) : (rest.size() == 1 ? rest[0] : mk_call("*", rest));
+            prest[i][j] = hoist(simplify(r), dyn, hoisted);
+          }
+      }
+    }
+    out->polar = have_polar;
     const int NP = (int)params.size();
     if (NP + (int)hoisted.size() > 32) throw std::runtime_error("too many hoisted constants");
 
@@ -857,6 +906,27 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
     }
     for (int i = 0; i < D; i++) o << "    x[" << i << "] = y" << i << ";\n";
     o << "  }\n";
+    if (have_polar) {
+      o << "  static constexpr int POLAR = 1;\n";
+      o << "  template <typename T> SDE_HD static void step_polar(const T *c, T t, T dt, T w, T ca, T sb, T *x) {\n";
+      o << "    (void)c; (void)t;\n";
+      for (int i = 0; i < D; i++) o << "    const T x" << i << " = x[" << i << "];  // " << vars[i] << "\n";
+      for (int i = 0; i < D; i++) o << "    const T mu" << i << " = " << em.ex(hdrift[i]) << ";\n";
+      o << "    const T G = SDE_SQRT(" << em.ex(polar_arg) << " * w);\n";
+      const char *uv[2] = {"ca", "sb"};
+      for (int i = 0; i < D; i++) {
+        std::string noise;
+        for (int j = 0; j < M; j++) {
+          if (is_val(diffm[i][j], 0)) continue;
+          std::string term = is_val(prest[i][j], 1) ? std::string(uv[j]) : em.ex(prest[i][j]) + " * " + uv[j];
+          noise = noise.empty() ? term : "(" + noise + " + " + term + ")";
+        }
+        o << "    x[" << i << "] = (x" << i << " + mu" << i << " * dt)";
+        if (!noise.empty()) o << " + G * (" << noise << ")";
+        o << ";\n";
+      }
+      o << "  }\n";
+    }
     // drift / diffusion at a point, double precision, un-hoisted
     {
       Emit ec;

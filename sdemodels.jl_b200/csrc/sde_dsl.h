@@ -12,6 +12,7 @@ struct sde_dsl_model {
   std::vector<std::string> drift_str;      // D entries
   std::vector<std::string> diffusion_str;  // D * max(M,1), row-major
   std::string cuda_source;                 // struct GenModel { ... } in namespace sdeb200
+  bool polar = false;                      // M == 2: every diffusion entry carries one sqrt(A) factor -> GenModel::step_polar is emitted
   std::string milstein_error;              // M == 1 only: non-empty when the diffusion could not be differentiated symbolically
 };
 

@@ -155,7 +155,7 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
 #endif
   }
 #if !SDE_STRICT
-  // Polar form of the step (FAST math, FP64, normal stream v2: sde_device.cuh, Noise<>): both noise terms carry
+  // Polar form of the step (FAST math, FP64, either normal stream: sde_device.cuh, Noise<>): both noise terms carry
   // sqrt(V) sqrt(w), so ONE square root of V*w replaces the radius' and the model's (7 FP64 operations and one MUFU fewer
   // per step; sqrt(V w) is rounded once, sqrt(V) sqrt(w) three times).  V < 0 still gives a non-finite state.
   static constexpr int POLAR = 1;

@@ -91,23 +91,34 @@ extern "C" void h_log_fast(const double *x, int64_t n, double *out) {
 extern "C" void h_rcp_fast(const double *x, int64_t n, double *out) {
   for (int64_t i = 0; i < n; i++) out[i] = rcp_fast(x[i]);
 }
-// the polar form of the Heston step (FAST math, stream v2: one sqrt of V*w) beside the plain form on the pair sqrt(w) (ca, sb)
-extern "C" void h_heston_polar(const double *params, double dt, const uint32_t *w3, const double *x_in, double *x_polar, double *x_plain) {
+// the polar form of the Heston step (FAST math, FP64: one sqrt of V*w) beside the plain form on the pair sqrt(w) (ca, sb);
+// version = normal stream (1: words r[0..3] of one Philox block, 2: words (3P, 3P+1, 3P+2))
+extern "C" void h_heston_polar(int version, const double *params, double dt, const uint32_t *words, const double *x_in, double *x_polar,
+                               double *x_plain) {
   static_assert(PolarOf<Heston>::value == 1 && PolarOf<BlackScholes>::value == 0, "only Heston declares the polar form");
-  static_assert(Noise<Heston, double, 2>::POLAR && !Noise<Heston, double, 1>::POLAR && !Noise<Heston, float, 2>::POLAR, "FP64 + stream v2 only");
-  static double tab[SDE_TAB2_DOUBLES];
-  double lk[6], c[SDE_MAXC], w, ca, sb, z[2];
-  h_scaled_tables_v2(dt, tab);
-  make_log_consts_v2(dt, lk);
+  static_assert(Noise<Heston, double, 2>::POLAR && Noise<Heston, double, 1>::POLAR && !Noise<Heston, float, 2>::POLAR, "FP64 only");
+  static_assert(Noise<Heston, double, 2>::NV == 12 && Noise<Heston, double, 1>::NV == 3 && Noise<BlackScholes, double, 2>::NV == 8, "");
+  static double tab[SDE_TAB2_DOUBLES > SDE_TAB_DOUBLES ? SDE_TAB2_DOUBLES : SDE_TAB_DOUBLES];
+  double lk[6], c[SDE_MAXC], w, ca, sb, z[2], dw[2];
   Heston::prepare(params, dt, c);
-  normal_polar_f64_v2(w3[0], w3[1], w3[2], tab, lk, w, ca, sb);
-  normal_pair_f64_v2(w3[0], w3[1], w3[2], tab, lk, z[0], z[1]);
+  if (version == 2) {
+    h_scaled_tables_v2(dt, tab);
+    make_log_consts_v2(dt, lk);
+    normal_polar_f64_v2(words[0], words[1], words[2], tab, lk, w, ca, sb);
+    normal_pair_f64_v2(words[0], words[1], words[2], tab, lk, z[0], z[1]);
+  } else {
+    const uint32_t r[4] = {words[0], words[1], words[2], words[3]};
+    h_scaled_tables(dt, tab);
+    make_log_consts(dt, lk);
+    normal_polar_f64(r, tab, lk, w, ca, sb);
+    normal_pair_f64(r, tab, lk, z[0], z[1]);
+  }
   const double nz[3] = {w, ca, sb};
-  double dw[2];
-  NoiseStep<Heston, 0, true>::increments(nz, dw);
+  if (version == 2) NoiseStep<Heston, 0, true, 2>::increments(nz, dw);
+  else NoiseStep<Heston, 0, true, 1>::increments(nz, dw);
   if (dw[0] != z[0] || dw[1] != z[1]) { x_polar[0] = x_polar[1] = -1.0; return; }   // increments() must be the pair itself
   x_polar[0] = x_plain[0] = x_in[0];
   x_polar[1] = x_plain[1] = x_in[1];
-  NoiseStep<Heston, 0, true>::run(c, 0.0, dt, nz, x_polar);
-  NoiseStep<Heston, 0, false>::run(c, 0.0, dt, z, x_plain);
+  NoiseStep<Heston, 0, true, 1>::run(c, 0.0, dt, nz, x_polar);
+  NoiseStep<Heston, 0, false, 1>::run(c, 0.0, dt, z, x_plain);
 }

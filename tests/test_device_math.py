@@ -141,22 +141,23 @@ def test_log_fast_and_rcp_fast(H):
         assert np.array_equal(spo, 1.0 / sp)
 
 
-def test_heston_polar_step_equals_the_plain_step(H):
-    """Heston's polar step (FAST math, FP64, stream v2: ONE square root of V*w instead of sqrt(V) and sqrt(w)) against the
-    plain step on the same pair: at most one ulp of the new state apart, equal at V = 0, non-finite for V < 0."""
+@pytest.mark.parametrize("version", [1, 2])
+def test_heston_polar_step_equals_the_plain_step(H, version):
+    """Heston's polar step (FAST math, FP64: ONE square root of V*w instead of sqrt(V) and sqrt(w)) against the plain step on
+    the same pair, on both normal streams: at most one ulp of the new state apart, equal at V = 0, non-finite for V < 0."""
     rng = np.random.default_rng(12)
     params = (C.c_double * 5)(0.01, 10.0, 0.3, 0.1, 0.4)
     dt, worst = 1.0 / 1024, 0.0
     xp, xq = (C.c_double * 2)(), (C.c_double * 2)()
     for i in range(4000):
-        w3 = (C.c_uint32 * 3)(*[int(v) for v in rng.integers(0, 2 ** 32, 3)])
+        w4 = (C.c_uint32 * 4)(*[int(v) for v in rng.integers(0, 2 ** 32, 4)])
         S, V = 100.0 * np.exp(rng.standard_normal()), (0.4 * rng.random() ** 4 if i % 50 else 0.0)
-        H.h_heston_polar(params, C.c_double(dt), w3, (C.c_double * 2)(S, V), xp, xq)
+        H.h_heston_polar(version, params, C.c_double(dt), w4, (C.c_double * 2)(S, V), xp, xq)
         assert xp[0] != -1.0
         for d in (0, 1):
             worst = max(worst, abs(xp[d] - xq[d]) / (2.0 ** -52 * abs(xq[d])) if xq[d] != 0 else abs(xp[d]))
         if V == 0.0:
             assert xp[0] == xq[0] and xp[1] == xq[1]
     assert worst <= 1.5, worst   # measured: 1.0 ulp of the new state
-    H.h_heston_polar(params, C.c_double(dt), (C.c_uint32 * 3)(1, 2, 3), (C.c_double * 2)(100.0, -0.01), xp, xq)
+    H.h_heston_polar(version, params, C.c_double(dt), (C.c_uint32 * 4)(1, 2, 3, 4), (C.c_double * 2)(100.0, -0.01), xp, xq)
     assert not np.isfinite(xp[0]) and not np.isfinite(xp[1])

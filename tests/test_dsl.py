@@ -259,3 +259,24 @@ def test_cubin_cache_round_trip(S, tmp_path, monkeypatch):
     assert fn(src, 2, 1, 0, log, len(log)) == n1 and sum(f.stat().st_size for f in files) == n1
     monkeypatch.setenv("SDEB200_CACHE_DIR", "")               # off
     assert fn(src, 2, 1, 1, log, len(log)) > 1000 and len(list((tmp_path / "cubins").glob("*.cubin"))) == 2
+
+
+def test_polar_step_is_emitted_for_a_common_sqrt_factor(S):
+    """M == 2 models whose non-zero diffusion entries all carry the same state-dependent factor sqrt(A) get
+    GenModel::step_polar (one square root of A*w per step instead of the radius' and the model's; the FP64 kernels take it
+    in FAST math, sde_device.cuh Noise<>); every other model keeps the plain step only."""
+    L = S._lib.lib()
+    L.sdeb200_model_cuda_source.restype = C.c_char_p
+    src = L.sdeb200_model_cuda_source(build(S, "Heston")._handle).decode()
+    body = src[src.index("static constexpr int POLAR = 1;"):src.index("static void coefficients")]
+    assert "const T G = SDE_SQRT(x1 * w);" in body and "G * (x0 * ca)" in body and "* ca + " in body and "* sb" in body
+    assert body.count("SDE_SQRT") == 1          # the only square root of the polar step
+    three_halves = S.sde_model("ThreeHalves", "dS = r*S*dt + sqrt(V)*S*dW1; dV = κ*V*(θ-V)*dt + σ*V*sqrt(V)*dW2")
+    src = L.sdeb200_model_cuda_source(three_halves._handle).decode()
+    assert "POLAR" in src and "G * ((c[3] * x1) * sb)" in src
+    for name, text in (("MixedVol", "dS = r*S*dt + σ*S*dW1; dV = κ*(θ-V)*dt + ξ*sqrt(V)*dW2"),       # one entry without the factor
+                       ("ParamRoot", "dS = r*S*dt + sqrt(a)*S*dW1; dV = κ*(θ-V)*dt + sqrt(a)*V*dW2"),  # parameter-only root: hoisted instead
+                       ("TwoRoots", "dS = r*S*dt + sqrt(V)*S*dW1; dV = κ*(θ-V)*dt + sqrt(S)*dW2")):      # different arguments
+        assert "POLAR" not in L.sdeb200_model_cuda_source(S.sde_model(name, text)._handle).decode(), name
+    for name in ("BlackScholes", "CoxIngersollRoss", "Lorenz"):   # M == 1 / M == 3: never
+        assert "POLAR" not in L.sdeb200_model_cuda_source(build(S, name)._handle).decode()

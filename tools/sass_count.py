@@ -15,7 +15,7 @@ PPT = 4
 # kernel -> path-steps per iteration of its main loop (PPT paths x U steps per Philox batch)
 KERNELS = {
     "heston_sample_em_f64": ("sdek_heston_f_sample_em_f64", PPT * 1, "D"),
-    "heston_sample_em_f64v2": ("sdek_heston_f_sample_em_f64v2", 2 * 4, "D"),   # SDE_PPT_V2 = 2 paths x 4 steps per batch
+    "heston_sample_em_f64v2": ("sdek_heston_f_sample_em_f64v2", PPT * 4, "D"),   # SDE_PPT_V2 = 4 paths x 4 steps per batch
     "heston_sample_em_f32": ("sdek_heston_f_sample_em_f32", PPT * 2, "F"),
     "bs_sample_em_f64": ("sdek_bs_f_sample_em_f64", PPT * 2, "D"),
     "bs_simsoa_mil_f64": ("sdek_bs_f_simsoa_mil_f64", 4 * 2, "D"),
