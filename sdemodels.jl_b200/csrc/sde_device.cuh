@@ -515,47 +515,55 @@ SDE_HD void normal_pair_f64_v2(uint32_t a, uint32_t b, uint32_t c, const double 
                           ~2^-21) instead of the 256-entry table + residual rotation: 10 instructions fewer per pair; the
                           full-trajectory FP32 kernels are issue-bound (profiles/README.md) */
 #endif
-SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, const float *rotf, float &z0, float &z1) {
+// radius of an FP32 pair from its square (one MUFU.SQRT on the device; -0 passes through)
+SDE_HD float radius_f32(float w) {
+#if defined(__CUDA_ARCH__)
+  float g;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(w));
+  return g;
+#else
+  return sqrtf(w);
+#endif
+}
+// polar form: radius^2 `w` (scaled by scale2) and the unit vector (cs, sn); the pair is radius_f32(w) (cs, sn)
+SDE_HD void normal_polar_f32(uint32_t ra, uint32_t rb, float scale2, const float *rotf, float &w, float &cs, float &sn) {
 #if defined(__CUDA_ARCH__)
   const float u1 = fmaf(__uint2float_rn(ra), 0x1.0p-32f, 0x1.0p-33f);
 #if SDE_F32_MUFU
   // u1 <= 1 (the largest word rounds to exactly 1): log2 <= 0, so w >= 0 without a clamp; -0 passes through sqrt.approx
   float l2;   // u1 >= 2^-33 is a normal number: the flush-to-zero form saves the denormal pre-scaling (3 instructions)
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
-  const float w = (-0x1.62e430p+0f /* 2 ln 2 */ * scale2) * l2;
-  float g, sn, cs;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(w));
+  w = (-0x1.62e430p+0f /* 2 ln 2 */ * scale2) * l2;
   const float ang = __int2float_rn((int32_t)rb) * 0x1.921fb6p-30f;   // 2 pi rb / 2^32 with rb read as signed: [-pi, pi)
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
   (void)rotf;
-  z0 = g * cs;
-  z1 = g * sn;
   return;
 #else
-  float w = -0x1.62e430p+0f /* 2 ln 2 */ * __log2f(u1);
+  w = -0x1.62e430p+0f /* 2 ln 2 */ * __log2f(u1);
 #endif
 #else
   const float u1 = fmaf((float)ra, 0x1.0p-32f, 0x1.0p-33f);
-  float w = -0x1.62e430p+0f * log2f(u1);
+  w = -0x1.62e430p+0f * log2f(u1);
 #endif
 #if !(defined(__CUDA_ARCH__) && SDE_F32_MUFU)
   w = fmaxf(w * scale2, 0.0f);
-#if defined(__CUDA_ARCH__)
-  float g;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(w));
-#else
-  const float g = sqrtf(w);
-#endif
   const float *rot = rotf + 2 * (rb >> 24);
   const float C = rot[0], S = rot[1];
   const float t = (float)((int32_t)(rb & 0x00FFFFFFu) - 0x00800000);
   const float u = t * t;
-  const float sn = t * fmaf(SDE_ROTF_S1, u, SDE_ROTF_S0);
+  const float sr = t * fmaf(SDE_ROTF_S1, u, SDE_ROTF_S0);
   const float cm = u * fmaf(SDE_ROTF_C2, u, SDE_ROTF_C1);
-  z0 = g * fmaf(C, cm, fmaf(-S, sn, C));
-  z1 = g * fmaf(S, cm, fmaf(C, sn, S));
+  cs = fmaf(C, cm, fmaf(-S, sr, C));
+  sn = fmaf(S, cm, fmaf(C, sr, S));
 #endif
+}
+SDE_HD void normal_pair_f32(uint32_t ra, uint32_t rb, float scale2, const float *rotf, float &z0, float &z1) {
+  float w, cs, sn;
+  normal_polar_f32(ra, rb, scale2, rotf, w, cs, sn);
+  const float g = radius_f32(w);
+  z0 = g * cs;
+  z1 = g * sn;
 }
 
 // Normals per Philox block for each precision.
@@ -627,13 +635,13 @@ template <class Model> struct PolarOf {
   template <class U> static constexpr int f(...) { return 0; }
   static constexpr int value = f<Model>(nullptr);
 };
-// The noise of one step as the kernels hand it to the model: M increments, or — for POLAR models in FP64 (M == 2: one
-// pair per step, on either normal stream) — the triple (w, ca, sb) with dW = sqrt(w) (ca, sb).  EVERY kernel form takes the same
+// The noise of one step as the kernels hand it to the model: M increments, or — for POLAR models (M == 2: one pair per
+// step; FAST math, either precision, either normal stream) — the triple (w, ca, sb) with dW = sqrt(w) (ca, sb).  EVERY kernel form takes the same
 // branch for a given (model, precision, stream), so terminal values, trajectories and the fine path of a coupled level
 // stay bit-identical to one another.
 template <class Model, typename T, int V> struct Noise {
   typedef Batch<T, Model::M, V> B;
-  static constexpr bool POLAR = PolarOf<Model>::value != 0 && sizeof(T) == 8 && Model::M == 2 && !SDE_STRICT;
+  static constexpr bool POLAR = PolarOf<Model>::value != 0 && Model::M == 2 && !SDE_STRICT;
   static constexpr int STRIDE = POLAR ? 3 : (Model::M > 0 ? Model::M : 0);
   static constexpr int NV = POLAR ? 3 * B::U : B::NZ;   // values per batch
 };
@@ -652,10 +660,16 @@ template <class Model, int SCHEME, int V> struct NoiseStep<Model, SCHEME, true, 
   template <typename T> SDE_HD static void run(const T *c, T t, T dt, const T *nz, T *x) {
     Model::step_polar(c, t, dt, nz[0], nz[1], nz[2], x);
   }
-  template <typename T> SDE_HD static void increments(const T *nz, T *dw) {   // the pair itself, as normal_pair_f64[_v2] forms it
-    const double g = V == 2 ? sqrt_from_seed6((double)nz[0], rsqrt_seed((double)nz[0])) : sqrt_core((double)nz[0]);
-    dw[0] = (T)(g * (double)nz[1]);
-    dw[1] = (T)(g * (double)nz[2]);
+  // the pair itself, exactly as normal_pair_f64 / normal_pair_f64_v2 / normal_pair_f32 form it
+  SDE_HD static void increments(const double *nz, double *dw) {
+    const double g = V == 2 ? sqrt_from_seed6(nz[0], rsqrt_seed(nz[0])) : sqrt_core(nz[0]);
+    dw[0] = g * nz[1];
+    dw[1] = g * nz[2];
+  }
+  SDE_HD static void increments(const float *nz, float *dw) {
+    const float g = radius_f32(nz[0]);
+    dw[0] = g * nz[1];
+    dw[1] = g * nz[2];
   }
 };
 
@@ -711,13 +725,17 @@ SDE_HD void normals_from_words_v2(const uint32_t *w, const double *s_tab, const 
 }
 
 // stream v1, FP64: the pair of one Philox block in polar form (M == 2: one block per step)
-template <typename T>
-SDE_HD void polar_from_block(const uint32_t (&r)[4], const double *tab, const double *lk, T *nz, const double *kr) {
-  double rw, ca, sb;
-  normal_polar_f64(r, tab, lk, rw, ca, sb, kr);
-  nz[0] = (T)rw;
-  nz[1] = (T)ca;
-  nz[2] = (T)sb;
+SDE_HD void polar_from_block(const uint32_t (&r)[4], const double *tab, const double *lk, double scale2, double *nz, const double *kr) {
+  (void)scale2;
+  normal_polar_f64(r, tab, lk, nz[0], nz[1], nz[2], kr);
+}
+// FP32: the two pairs of a block, one triple per step
+SDE_HD void polar_from_block(const uint32_t (&r)[4], const double *tab, const double *lk, float scale2, float *nz, const double *kr) {
+  (void)lk;
+  (void)kr;
+  const float *rotf = (const float *)tab;
+  normal_polar_f32(r[0], r[1], scale2, rotf, nz[0], nz[1], nz[2]);
+  normal_polar_f32(r[2], r[3], scale2, rotf, nz[3], nz[4], nz[5]);
 }
 // the same pairs in polar form, one triple (w, ca, sb) per step (M == 2; see Noise<> below)
 template <typename T, int M, int V>
@@ -759,7 +777,7 @@ SDE_D void gen_batch(uint64_t path, uint32_t blk0, uint32_t stream, const Philox
     for (int b = 0; b < B::NB; b++) {
       uint32_t r[4];
       philox4x32_10((uint32_t)path, (uint32_t)(path >> 32), blk0 + (uint32_t)b, stream, ks, r);
-      if (POL) polar_from_block(r, s_tab, lk, dw + 3 * b, kr);
+      if (POL) polar_from_block(r, s_tab, lk, scale2, dw + b * (3 * B::NPB / 2), kr);
       else normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
     }
   }
@@ -808,7 +826,7 @@ SDE_D void gen_batch(const PhiloxPath &pp, uint32_t blk0, const PhiloxKeys &ks, 
     for (int b = 0; b < B::NB; b++) {
       uint32_t r[4];
       philox4x32_10(pp, blk0 + (uint32_t)b, ks, r);
-      if (POL) polar_from_block(r, s_tab, lk, dw + 3 * b, kr);
+      if (POL) polar_from_block(r, s_tab, lk, scale2, dw + b * (3 * B::NPB / 2), kr);
       else normals_from_block(r, s_tab, lk, scale2, dw + b * B::NPB, kr);
     }
   }

@@ -96,8 +96,9 @@ extern "C" void h_rcp_fast(const double *x, int64_t n, double *out) {
 extern "C" void h_heston_polar(int version, const double *params, double dt, const uint32_t *words, const double *x_in, double *x_polar,
                                double *x_plain) {
   static_assert(PolarOf<Heston>::value == 1 && PolarOf<BlackScholes>::value == 0, "only Heston declares the polar form");
-  static_assert(Noise<Heston, double, 2>::POLAR && Noise<Heston, double, 1>::POLAR && !Noise<Heston, float, 2>::POLAR, "FP64 only");
-  static_assert(Noise<Heston, double, 2>::NV == 12 && Noise<Heston, double, 1>::NV == 3 && Noise<BlackScholes, double, 2>::NV == 8, "");
+  static_assert(Noise<Heston, double, 2>::POLAR && Noise<Heston, double, 1>::POLAR && Noise<Heston, float, 2>::POLAR, "both precisions, both streams");
+  static_assert(Noise<Heston, double, 2>::NV == 12 && Noise<Heston, double, 1>::NV == 3 && Noise<Heston, float, 1>::NV == 6 &&
+                Noise<BlackScholes, double, 2>::NV == 8 && !Noise<BlackScholes, float, 1>::POLAR, "values per batch");
   static double tab[SDE_TAB2_DOUBLES > SDE_TAB_DOUBLES ? SDE_TAB2_DOUBLES : SDE_TAB_DOUBLES];
   double lk[6], c[SDE_MAXC], w, ca, sb, z[2], dw[2];
   Heston::prepare(params, dt, c);
@@ -121,4 +122,18 @@ extern "C" void h_heston_polar(int version, const double *params, double dt, con
   x_polar[1] = x_plain[1] = x_in[1];
   NoiseStep<Heston, 0, true, 1>::run(c, 0.0, dt, nz, x_polar);
   NoiseStep<Heston, 0, false, 1>::run(c, 0.0, dt, z, x_plain);
+}
+// the same in FP32 (host twin of the FP32 stream: table rotation, sqrtf): words (ra, rb) of one pair
+extern "C" void h_heston_polar_f32(const float *params, float dt, const uint32_t *words, const float *x_in, float *x_polar, float *x_plain) {
+  float c[SDE_MAXC], w, cs, sn, z[2], dw[2];
+  Heston::prepare(params, dt, c);
+  normal_polar_f32(words[0], words[1], dt, h_rotf_tab, w, cs, sn);
+  normal_pair_f32(words[0], words[1], dt, h_rotf_tab, z[0], z[1]);
+  const float nz[3] = {w, cs, sn};
+  NoiseStep<Heston, 0, true, 1>::increments(nz, dw);
+  if (dw[0] != z[0] || dw[1] != z[1]) { x_polar[0] = x_polar[1] = -1.0f; return; }
+  x_polar[0] = x_plain[0] = x_in[0];
+  x_polar[1] = x_plain[1] = x_in[1];
+  NoiseStep<Heston, 0, true, 1>::run(c, 0.0f, dt, nz, x_polar);
+  NoiseStep<Heston, 0, false, 1>::run(c, 0.0f, dt, z, x_plain);
 }

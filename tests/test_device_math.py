@@ -161,3 +161,24 @@ def test_heston_polar_step_equals_the_plain_step(H, version):
     assert worst <= 1.5, worst   # measured: 1.0 ulp of the new state
     H.h_heston_polar(version, params, C.c_double(dt), (C.c_uint32 * 4)(1, 2, 3, 4), (C.c_double * 2)(100.0, -0.01), xp, xq)
     assert not np.isfinite(xp[0]) and not np.isfinite(xp[1])
+
+
+def test_heston_polar_step_fp32(H):
+    """The FP32 polar step against the plain FP32 step on the same pair (host twin of the FP32 stream): within two float
+    ulps of the new state, equal at V = 0, non-finite for V < 0."""
+    rng = np.random.default_rng(13)
+    params = (C.c_float * 5)(0.01, 10.0, 0.3, 0.1, 0.4)
+    dt, worst = 1.0 / 1024, 0.0
+    xp, xq = (C.c_float * 2)(), (C.c_float * 2)()
+    for i in range(4000):
+        w2 = (C.c_uint32 * 2)(*[int(v) for v in rng.integers(0, 2 ** 32, 2)])
+        S, V = 100.0 * np.exp(rng.standard_normal()), (0.4 * rng.random() ** 4 if i % 50 else 0.0)
+        H.h_heston_polar_f32(params, C.c_float(dt), w2, (C.c_float * 2)(S, V), xp, xq)
+        assert xp[0] != -1.0
+        for d in (0, 1):
+            worst = max(worst, abs(xp[d] - xq[d]) / (2.0 ** -23 * abs(xq[d])) if xq[d] != 0 else abs(xp[d]))
+        if V == 0.0:
+            assert xp[0] == xq[0] and xp[1] == xq[1]
+    assert worst <= 2.0, worst
+    H.h_heston_polar_f32(params, C.c_float(dt), (C.c_uint32 * 2)(1, 2), (C.c_float * 2)(100.0, -0.01), xp, xq)
+    assert not np.isfinite(xp[0]) and not np.isfinite(xp[1])
