@@ -2,7 +2,10 @@
 # round 2, final measurement set (polar Heston step, unconditional v2 time loop): the driver's round-end sequence, every
 # configuration on both streams, ncu captures, launch list.  Files land in gpurun_out/ with the prefix r02z.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_r2z.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_r2z.log; tail -n 3 gpurun_out/pytest_r2z.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_r2z.log 2>&1; rc=$?; echo "pytest rc=$rc" >> gpurun_out/pytest_r2z.log; tail -n 3 gpurun_out/pytest_r2z.log
+if [ $rc -ne 0 ]; then tail -n 60 gpurun_out/pytest_r2z.log; exit 1; fi
+# FP32 terminal kernel: polar step (cur) against the build before it (prev)
+VARIANTS="cur prev" MODE=bench PREC=f32 SDEB200_RNG=2 bash tools/gpu_ab.sh 2>&1 | tee gpurun_out/r02z_ab_f32_polar.txt
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_r2z.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke_r2z.log; tail -n 2 gpurun_out/smoke_r2z.log
 timeout 600 python bench.py --impl reference > gpurun_out/bench_reference_r2z.log 2>&1; echo "reference rc=$?" >> gpurun_out/bench_reference_r2z.log; tail -n 2 gpurun_out/bench_reference_r2z.log | cut -c1-300
 timeout 900 python bench.py > gpurun_out/bench_r2z.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench_r2z.log; tail -n 2 gpurun_out/bench_r2z.log | cut -c1-400
