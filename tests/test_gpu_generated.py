@@ -304,3 +304,48 @@ def test_reference_order_tma_stores_two_states_one_noise(gpu, precision, rng):
         assert res[0][1] == 1 and res[1][1] == 0, (npaths, nrows, res[0][1])
         assert np.array_equal(res[0][0], res[1][0]), (npaths, nrows)
         assert np.isfinite(res[0][0]).all() and np.all(res[0][0][:, 0, :] == np.array([1.0, 0.5]))
+
+
+POLAR_MODELS = [
+    # the 3/2 stochastic-volatility model: both noise terms carry sqrt(V), the second one V*sqrt(V)
+    ("ThreeHalves", "dS = r*S*dt + sqrt(V)*S*dW1\ndV = κ*V*(θ-V)*dt + σ*V*sqrt(V)*dW2", (0.02, 2.0, 0.3, 0.5), [100.0, 0.3]),
+    # a correlated Heston-type model under other names, the root's argument a sum of states
+    ("RootOfSum", "dX = a*X*dt + b*sqrt(X+Y)*dW1\ndY = c*(d-Y)*dt + e*sqrt(X+Y)*dW2\ndW1*dW2 = f*dt", (0.05, 0.2, 1.5, 0.4, 0.1, -0.3), [1.0, 0.4]),
+]
+
+
+@pytest.mark.parametrize("name,text,params,x0", POLAR_MODELS)
+def test_generated_polar_step_matches_the_independent_twin(gpu, O, name, text, params, x0):
+    """Models for which the code generator emits the polar step (one square root of A*w per step, sde_dsl.cpp) against
+    oracle/twin.py — an independent parser / evaluator of the same equation text: Wiener-driven strict math bit for bit (no
+    polar step there), RNG-driven `sample` on both normal streams path by path (the polar step in FAST math; the plain
+    step in STRICT math), every kernel form with the same bits, the fine path of a coupled level included."""
+    import twin as T
+    S = gpu
+    m = S.sde_model(name + "_polar", text)(*params)
+    L = S._lib.lib()
+    L.sdeb200_model_cuda_source.restype = __import__("ctypes").c_char_p
+    assert b"step_polar" in L.sdeb200_model_cuda_source(type(m)._handle)
+    tm = T.Model(name, text)
+    nsteps, npaths, dt = 48, 40, 1.0 / 96
+    z = np.random.default_rng(8).standard_normal((npaths, nsteps, 2))
+    w = O.wiener_z(dt, z)
+    ref = np.array(T.simulate_wiener(tm, EM, params, 0.0, dt, x0, w.tolist()))
+    out = np.empty_like(ref)
+    S.simulate_(out, m, S.EulerMaruyama(dt), 0.0, x0, w, math="strict")
+    assert np.array_equal(out, ref)
+    for rng in (1, 2):
+        zz = O.normals_paths(21, 3, 1000, npaths, nsteps, 2, rng=rng)
+        ref = np.array(T.sample_z(tm, EM, params, 0.0, dt, x0, zz.tolist()))
+        for mth in ("fast", "strict"):
+            got = S.sample(m, S.EulerMaruyama(dt), 0.0, x0, nsteps, npaths, seed=21, stream=3, path_offset=1000, rng=rng, math=mth)
+            assert rel_err(got, ref) <= 1e-11, (rng, mth)
+        term = S.sample(m, S.EulerMaruyama(dt), 0.0, x0, nsteps, 700, seed=21, rng=rng)
+        xr, _ = S.simulate(m, S.EulerMaruyama(dt), 0.0, x0, nsteps, 700, seed=21, rng=rng)
+        xs, _ = S.simulate(m, S.EulerMaruyama(dt), 0.0, x0, nsteps, 700, seed=21, rng=rng, layout="soa")
+        assert np.array_equal(xr[:, -1], term) and np.array_equal(np.moveaxis(xs, -1, 0)[:, -1].reshape(term.shape), term)
+        xc, xf = S.multilevel_sample_level(m, S.EulerMaruyama(2 * dt), S.EulerMaruyama(dt), 2, 0.0, x0, nsteps // 2, 700, seed=21, rng=rng)
+        assert np.array_equal(xf, term)
+    t32 = S.sample(m, S.EulerMaruyama(dt), 0.0, x0, nsteps, 700, seed=21, precision="f32")
+    t64 = S.sample(m, S.EulerMaruyama(dt), 0.0, x0, nsteps, 700, seed=21)
+    assert np.all(np.isfinite(t32)) and abs(float(t32[:, 0].mean()) / float(t64[:, 0].mean()) - 1) < 0.02   # FP32 stream differs: same law
