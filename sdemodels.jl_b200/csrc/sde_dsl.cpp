@@ -783,8 +783,7 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
     // model a pair as (w, ca, sb) with dW = sqrt(w) (ca, sb), and the step takes ONE square root of A*w instead of the
     // radius' and the model's (sde_device.cuh: Noise<>, PolarOf<>; the hand-written Heston functor does the same).
     bool have_polar = false;
-    E polar_arg;
-    Mat prest(D, std::vector<E>(M > 0 ? M : 1));
+    E polar_arg, polar_raw;
     if (M == 2) {
       std::function<void(const E &, std::vector<E> &)> factors = [&](const E &e, std::vector<E> &f) {
         if (e->kind == Expr::CALL && e->name == "*") for (auto &a : e->args) factors(a, f);
@@ -808,24 +807,106 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
         }
       if (cand) {
         have_polar = true;
+        polar_raw = cand->args[0];
         polar_arg = hoist(cand->args[0], dyn, hoisted);
-        size_t k = 0;
-        for (int i = 0; i < D; i++)
-          for (int j = 0; j < M; j++) {
-            if (is_val(diffm[i][j], 0)) continue;
-            std::vector<E> rest;
-            bool dropped = false;
-            for (auto &h : fl[k]) {
-              if (!dropped && equal(h, cand)) { dropped = true; continue; }   // one occurrence of the common factor
-              rest.push_back(h);
-            }
-            k++;
-            E r = rest.empty() ? mk_num(1, true) : (rest.size() == 1 ? rest[0] : mk_call("*", rest));
-            prest[i][j] = hoist(simplify(r), dyn, hoisted);
-          }
       }
     }
     out->polar = have_polar;
+    // FAST-math forms of the Euler–Maruyama update (SDE_STRICT = 0 only; STRICT keeps the reference's literal operation
+    // order).  Same algebra, fewer operations: (1) every term — drift_i*dt, sigma_ij*dw_j — is a product whose
+    // parameter-only factors, Δt included, are folded into ONE constant computed in prepare(); (2) when every term of row i
+    // carries the state x_i itself (geometric rows: r*S*dt + sigma*S*dW), x_i is factored out: x_i + x_i*A, one FMA.
+    // The same for the polar step, whose noise of row i is G * (rest_i0*ca + rest_i1*sb).
+    std::set<std::string> dyn2 = dyn;   // symbols that vary per step: states, t and the noise of the step
+    for (const char *n : {"__dw0", "__dw1", "__dw2", "__dw3", "__ca", "__sb", "__G"}) dyn2.insert(n);
+    auto flat = [&](const E &e) {
+      std::vector<E> f;
+      std::function<void(const E &)> go = [&](const E &x) {
+        if (x->kind == Expr::CALL && x->name == "*") for (auto &a : x->args) go(a);
+        else f.push_back(x);
+      };
+      go(e);
+      return f;
+    };
+    auto product = [&](const std::vector<E> &f) { return f.empty() ? mk_num(1, true) : (f.size() == 1 ? f[0] : mk_call("*", f)); };
+    // term -> c * (dynamic factors), the constant hoisted (dt is visible in prepare)
+    auto fold_term = [&](const std::vector<E> &f) {
+      std::vector<E> st, dy;
+      for (auto &x : f) (depends_on(x, dyn2) ? dy : st).push_back(x);
+      E c = simplify(product(st));
+      if (c->kind == Expr::CALL || (c->kind == Expr::SYM && c->name == "dt")) c = hoist(c, dyn2, hoisted);
+      if (dy.empty()) return c;
+      if (is_val(c, 1)) return product(dy);
+      std::vector<E> all{c};
+      for (auto &x : dy) all.push_back(x);
+      return mk_call("*", all);
+    };
+    // row i: x_i + sum(terms)  or  x_i * A + x_i
+    auto fast_row = [&](int i, const std::vector<std::vector<E>> &terms) {
+      const E xi = mk_sym(vars[i]);
+      bool common = !terms.empty();
+      for (auto &f : terms) {
+        bool has = false;
+        for (auto &x : f) has = has || equal(x, xi);
+        common = common && has;
+      }
+      std::vector<E> sum;
+      for (auto f : terms) {
+        if (common)
+          for (size_t k = 0; k < f.size(); k++)
+            if (equal(f[k], xi)) { f.erase(f.begin() + k); break; }
+        sum.push_back(fold_term(f));
+      }
+      if (sum.empty()) return xi;
+      E a = sum.size() == 1 ? sum[0] : mk_call("+", sum);
+      if (common) return mk_call("+", {mk_call("*", {xi, a}), xi});
+      std::vector<E> all{xi};
+      for (auto &x : sum) all.push_back(x);
+      return mk_call("+", all);
+    };
+    std::vector<E> fast_em(D), fast_polar(D);
+    for (int i = 0; i < D; i++) {
+      std::vector<std::vector<E>> terms;
+      if (!is_val(drift[i], 0)) { auto f = flat(drift[i]); f.push_back(mk_sym("dt")); terms.push_back(f); }
+      for (int j = 0; j < M; j++)
+        if (!is_val(diffm[i][j], 0)) { auto f = flat(diffm[i][j]); f.push_back(mk_sym("__dw" + std::to_string(j))); terms.push_back(f); }
+      fast_em[i] = fast_row(i, terms);
+      if (have_polar) {
+        // the noise of the row as ONE term G * N_i; x_i is common only if it is a factor of every rest_ij
+        const E xi = mk_sym(vars[i]);
+        std::vector<std::vector<E>> pt;
+        if (!is_val(drift[i], 0)) { auto f = flat(drift[i]); f.push_back(mk_sym("dt")); pt.push_back(f); }
+        std::vector<std::vector<E>> rest;
+        for (int j = 0; j < M; j++)
+          if (!is_val(diffm[i][j], 0)) {
+            // un-hoisted rest: the entry's factors without one occurrence of the common root
+            auto f = flat(diffm[i][j]);
+            for (size_t k = 0; k < f.size(); k++)
+              if (f[k]->kind == Expr::CALL && f[k]->name == "sqrt" && equal(f[k]->args[0], polar_raw)) { f.erase(f.begin() + k); break; }
+            f.push_back(mk_sym(j == 0 ? "__ca" : "__sb"));
+            rest.push_back(f);
+          }
+        if (!rest.empty()) {
+          bool common = true;
+          for (auto &f : rest) {
+            bool has = false;
+            for (auto &x : f) has = has || equal(x, xi);
+            common = common && has;
+          }
+          std::vector<E> ns;
+          for (auto f : rest) {
+            if (common)
+              for (size_t k = 0; k < f.size(); k++)
+                if (equal(f[k], xi)) { f.erase(f.begin() + k); break; }
+            ns.push_back(fold_term(f));
+          }
+          std::vector<E> nf{mk_sym("__G"), ns.size() == 1 ? ns[0] : mk_call("+", ns)};
+          if (common) nf.push_back(xi);
+          pt.push_back(nf);
+        }
+        fast_polar[i] = fast_row(i, pt);
+      }
+    }
     const int NP = (int)params.size();
     if (NP + (int)hoisted.size() > 32) throw std::runtime_error("too many hoisted constants");
 
@@ -843,7 +924,8 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
     o << "  template <typename T> SDE_HD static void prepare(const T *p, T dt, T *c) {\n    (void)dt; (void)p;\n";
     for (int i = 0; i < NP; i++) o << "    c[" << i << "] = p[" << i << "];  // " << params[i] << "\n";
     {
-      Emit ep = em;  // hoisted expressions only see parameters (and earlier hoisted constants do not nest)
+      Emit ep = em;  // hoisted expressions only see parameters and dt (and earlier hoisted constants do not nest)
+      ep.sym["dt"] = "dt";
       for (size_t i = 0; i < hoisted.size(); i++)
         o << "    c[" << NP + (int)i << "] = " << ep.ex(hoisted[i]) << ";  // " << to_str(hoisted[i]) << "\n";
     }
@@ -855,9 +937,18 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
       for (int i = 0; i < D; i++) o << "    s[" << i << "] = " << es.ex(hdiff[i][0]) << ";\n";
       o << "  }\n";
     }
+    Emit ef = em;   // FAST forms: the step's noise symbols
+    ef.sym["dt"] = "dt";
+    for (int j = 0; j < 4; j++) ef.sym["__dw" + std::to_string(j)] = "dw[" + std::to_string(j) + "]";
+    ef.sym["__ca"] = "ca";
+    ef.sym["__sb"] = "sb";
+    ef.sym["__G"] = "G";
     o << "  template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {\n";
     o << "    (void)c; (void)t; (void)dw;\n";
     for (int i = 0; i < D; i++) o << "    const T x" << i << " = x[" << i << "];  // " << vars[i] << "\n";
+    o << "#if !SDE_STRICT\n    if (SCHEME == 0) {  // FAST math: folded constants, common state factor (same algebra as below)\n";
+    for (int i = 0; i < D; i++) o << "      x[" << i << "] = " << ef.ex(fast_em[i]) << ";\n";
+    o << "      return;\n    }\n#endif\n";
     for (int i = 0; i < D; i++) o << "    const T mu" << i << " = " << em.ex(hdrift[i]) << ";\n";
     for (int i = 0; i < D; i++)
       for (int j = 0; j < M; j++)
@@ -909,22 +1000,10 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
     if (have_polar) {
       o << "  static constexpr int POLAR = 1;\n";
       o << "  template <typename T> SDE_HD static void step_polar(const T *c, T t, T dt, T w, T ca, T sb, T *x) {\n";
-      o << "    (void)c; (void)t;\n";
+      o << "    (void)c; (void)t; (void)dt;\n";
       for (int i = 0; i < D; i++) o << "    const T x" << i << " = x[" << i << "];  // " << vars[i] << "\n";
-      for (int i = 0; i < D; i++) o << "    const T mu" << i << " = " << em.ex(hdrift[i]) << ";\n";
       o << "    const T G = SDE_SQRT(" << em.ex(polar_arg) << " * w);\n";
-      const char *uv[2] = {"ca", "sb"};
-      for (int i = 0; i < D; i++) {
-        std::string noise;
-        for (int j = 0; j < M; j++) {
-          if (is_val(diffm[i][j], 0)) continue;
-          std::string term = is_val(prest[i][j], 1) ? std::string(uv[j]) : em.ex(prest[i][j]) + " * " + uv[j];
-          noise = noise.empty() ? term : "(" + noise + " + " + term + ")";
-        }
-        o << "    x[" << i << "] = (x" << i << " + mu" << i << " * dt)";
-        if (!noise.empty()) o << " + G * (" << noise << ")";
-        o << ";\n";
-      }
+      for (int i = 0; i < D; i++) o << "    x[" << i << "] = " << ef.ex(fast_polar[i]) << ";\n";
       o << "  }\n";
     }
     // drift / diffusion at a point, double precision, un-hoisted

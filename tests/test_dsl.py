@@ -269,14 +269,30 @@ def test_polar_step_is_emitted_for_a_common_sqrt_factor(S):
     L.sdeb200_model_cuda_source.restype = C.c_char_p
     src = L.sdeb200_model_cuda_source(build(S, "Heston")._handle).decode()
     body = src[src.index("static constexpr int POLAR = 1;"):src.index("static void coefficients")]
-    assert "const T G = SDE_SQRT(x1 * w);" in body and "G * (x0 * ca)" in body and "* ca + " in body and "* sb" in body
+    assert "const T G = SDE_SQRT(x1 * w);" in body and "(G * ca)" in body and "* ca) + " in body and "* sb)" in body
+    assert "x[0] = ((x0 * (c[6] + (G * ca))) + x0);" in body    # geometric row: x0 factored out, r*dt folded into one constant
     assert body.count("SDE_SQRT") == 1          # the only square root of the polar step
     three_halves = S.sde_model("ThreeHalves", "dS = r*S*dt + sqrt(V)*S*dW1; dV = κ*V*(θ-V)*dt + σ*V*sqrt(V)*dW2")
     src = L.sdeb200_model_cuda_source(three_halves._handle).decode()
-    assert "POLAR" in src and "G * ((c[3] * x1) * sb)" in src
+    assert "POLAR" in src and "x[1] = ((x1 * ((c[5] * (c[2] - x1)) + (G * (c[3] * sb)))) + x1);" in src   # V factored out of κ*V*(θ-V)*dt and σ*V*sqrt(V)*dW2
     for name, text in (("MixedVol", "dS = r*S*dt + σ*S*dW1; dV = κ*(θ-V)*dt + ξ*sqrt(V)*dW2"),       # one entry without the factor
                        ("ParamRoot", "dS = r*S*dt + sqrt(a)*S*dW1; dV = κ*(θ-V)*dt + sqrt(a)*V*dW2"),  # parameter-only root: hoisted instead
                        ("TwoRoots", "dS = r*S*dt + sqrt(V)*S*dW1; dV = κ*(θ-V)*dt + sqrt(S)*dW2")):      # different arguments
         assert "POLAR" not in L.sdeb200_model_cuda_source(S.sde_model(name, text)._handle).decode(), name
     for name in ("BlackScholes", "CoxIngersollRoss", "Lorenz"):   # M == 1 / M == 3: never
         assert "POLAR" not in L.sdeb200_model_cuda_source(build(S, name)._handle).decode()
+
+
+def test_fast_forms_of_the_generated_update(S):
+    """FAST math (SDE_STRICT = 0) emits the Euler-Maruyama update with parameter-only factors and Δt folded into one
+    constant per term and the state factored out of geometric rows; STRICT keeps the reference's literal order below it."""
+    L = S._lib.lib()
+    L.sdeb200_model_cuda_source.restype = C.c_char_p
+    src = L.sdeb200_model_cuda_source(build(S, "BlackScholes")._handle).decode()
+    fast = src[src.index("#if !SDE_STRICT"):src.index("#endif", src.index("#if !SDE_STRICT"))]
+    assert "c[2] = (c[0] * dt);  // r * dt" in src and "x[0] = ((x0 * (c[2] + (c[1] * dw[0]))) + x0);" in fast
+    assert "T y0 = (x0 + mu0 * dt) + (s0_0 * dw[0]);" in src          # the literal form: euler_maruyama.jl:4
+    src = L.sdeb200_model_cuda_source(build(S, "CoxIngersollRoss")._handle).decode()
+    assert "x[0] = ((x0 + (c[3] * (c[1] - x0))) + ((c[2] * SDE_SQRT(x0)) * dw[0]));" in src   # no common factor: sum of folded terms
+    src = L.sdeb200_model_cuda_source(build(S, "TimeDependent")._handle).decode()
+    assert "(c[2] * t)" in src                                       # t stays a per-step factor
