@@ -841,28 +841,78 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
       for (auto &x : dy) all.push_back(x);
       return mk_call("*", all);
     };
-    // row i: x_i + sum(terms)  or  x_i * A + x_i
+    // row i:  x_i + sum(terms)  ->  x_i * (c' + A) + (cB + B)
+    //   terms whose only dynamic factor is affine in x_i with parameter-only other parts (a - x_i, x_i + a, ...: mean
+    //   reversion) are expanded first; then c' = 1 + (sum of parameter-only coefficients of x_i), A = the coefficients of
+    //   x_i that vary per step, cB = the sum of the parameter-only terms, B = the remaining terms.  Geometric rows come out
+    //   as x*A + x, mean-reverting ones as x*c' + (cB + noise): one FMA each.
     auto fast_row = [&](int i, const std::vector<std::vector<E>> &terms) {
       const E xi = mk_sym(vars[i]);
-      bool common = !terms.empty();
+      auto dynamic = [&](const E &e) { return depends_on(e, dyn2); };
+      std::vector<std::vector<E>> ex;
       for (auto &f : terms) {
-        bool has = false;
-        for (auto &x : f) has = has || equal(x, xi);
-        common = common && has;
+        int idx = -1, ndyn = 0;
+        for (size_t k = 0; k < f.size(); k++)
+          if (dynamic(f[k])) { ndyn++; idx = (int)k; }
+        bool done = false;
+        if (ndyn == 1 && f[idx]->kind == Expr::CALL && (f[idx]->name == "+" || (f[idx]->name == "-" && f[idx]->args.size() == 2))) {
+          const E &g = f[idx];
+          std::vector<E> st;
+          int sx = 0;
+          bool ok = true;
+          for (size_t q = 0; q < g->args.size(); q++) {
+            const int sign = (g->name == "-" && q == 1) ? -1 : 1;
+            if (equal(g->args[q], xi)) { ok = ok && sx == 0; sx = sign; }
+            else if (!dynamic(g->args[q])) st.push_back(sign > 0 ? g->args[q] : mk_call("-", {g->args[q]}));
+            else ok = false;
+          }
+          if (ok && sx != 0) {
+            std::vector<E> others;
+            for (size_t k = 0; k < f.size(); k++)
+              if ((int)k != idx) others.push_back(f[k]);
+            if (!st.empty()) {
+              auto t = others;
+              t.push_back(st.size() == 1 ? st[0] : mk_call("+", st));
+              ex.push_back(t);
+            }
+            auto t2 = others;
+            if (sx < 0) t2.push_back(mk_num(-1, true));
+            t2.push_back(xi);
+            ex.push_back(t2);
+            done = true;
+          }
+        }
+        if (!done) ex.push_back(f);
       }
-      std::vector<E> sum;
-      for (auto f : terms) {
-        if (common)
-          for (size_t k = 0; k < f.size(); k++)
-            if (equal(f[k], xi)) { f.erase(f.begin() + k); break; }
-        sum.push_back(fold_term(f));
+      std::vector<E> Kp{mk_num(1, true)}, Ap, Bs, Bd;
+      for (auto f : ex) {
+        int kx = -1;
+        for (size_t k = 0; k < f.size() && kx < 0; k++)
+          if (equal(f[k], xi)) kx = (int)k;
+        if (kx >= 0) f.erase(f.begin() + kx);
+        bool dyn_rest = false;
+        for (auto &x : f) dyn_rest = dyn_rest || dynamic(x);
+        if (kx >= 0) (dyn_rest ? Ap : Kp).push_back(dyn_rest ? fold_term(f) : simplify(product(f)));
+        else (dyn_rest ? Bd : Bs).push_back(dyn_rest ? fold_term(f) : simplify(product(f)));
       }
-      if (sum.empty()) return xi;
-      E a = sum.size() == 1 ? sum[0] : mk_call("+", sum);
-      if (common) return mk_call("+", {mk_call("*", {xi, a}), xi});
-      std::vector<E> all{xi};
-      for (auto &x : sum) all.push_back(x);
-      return mk_call("+", all);
+      auto constant = [&](const std::vector<E> &parts) {   // the sum of parameter-only parts as one prepared constant
+        E c = simplify(parts.size() == 1 ? parts[0] : mk_call("+", parts));
+        return (c->kind == Expr::CALL || (c->kind == Expr::SYM && c->name == "dt")) ? hoist(c, dyn2, hoisted) : c;
+      };
+      auto sum_of = [&](std::vector<E> v) { return v.size() == 1 ? v[0] : mk_call("+", v); };
+      E core;
+      if (Ap.empty()) core = Kp.size() == 1 ? xi : mk_call("*", {xi, constant(Kp)});   // x * (1 + K): mean reversion, growth
+      else {   // x*(K + A) + x: one FMA after A, and the small increment is not rounded against 1
+        std::vector<E> in;
+        if (Kp.size() > 1) in.push_back(constant(std::vector<E>(Kp.begin() + 1, Kp.end())));
+        for (auto &x : Ap) in.push_back(x);
+        core = mk_call("+", {mk_call("*", {xi, sum_of(in)}), xi});
+      }
+      std::vector<E> rest;
+      if (!Bs.empty()) rest.push_back(constant(Bs));
+      for (auto &x : Bd) rest.push_back(x);
+      if (rest.empty()) return core;
+      return mk_call("+", {core, sum_of(rest)});
     };
     std::vector<E> fast_em(D), fast_polar(D);
     for (int i = 0; i < D; i++) {
@@ -887,6 +937,7 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
             rest.push_back(f);
           }
         if (!rest.empty()) {
+          // x_i is taken out of the noise term only if it is a factor of every rest_ij (then G * N_i * x_i is an x_i-term)
           bool common = true;
           for (auto &f : rest) {
             bool has = false;

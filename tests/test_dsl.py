@@ -271,6 +271,7 @@ def test_polar_step_is_emitted_for_a_common_sqrt_factor(S):
     body = src[src.index("static constexpr int POLAR = 1;"):src.index("static void coefficients")]
     assert "const T G = SDE_SQRT(x1 * w);" in body and "(G * ca)" in body and "* ca) + " in body and "* sb)" in body
     assert "x[0] = ((x0 * (c[6] + (G * ca))) + x0);" in body    # geometric row: x0 factored out, r*dt folded into one constant
+    assert "x[1] = ((x1 * c[9]) + (c[10] + (G * ((c[7] * ca) + (c[8] * sb)))));" in body   # mean reversion expanded: V*(1 - κΔt) + (κθΔt + noise)
     assert body.count("SDE_SQRT") == 1          # the only square root of the polar step
     three_halves = S.sde_model("ThreeHalves", "dS = r*S*dt + sqrt(V)*S*dW1; dV = κ*V*(θ-V)*dt + σ*V*sqrt(V)*dW2")
     src = L.sdeb200_model_cuda_source(three_halves._handle).decode()
@@ -293,6 +294,7 @@ def test_fast_forms_of_the_generated_update(S):
     assert "c[2] = (c[0] * dt);  // r * dt" in src and "x[0] = ((x0 * (c[2] + (c[1] * dw[0]))) + x0);" in fast
     assert "T y0 = (x0 + mu0 * dt) + (s0_0 * dw[0]);" in src          # the literal form: euler_maruyama.jl:4
     src = L.sdeb200_model_cuda_source(build(S, "CoxIngersollRoss")._handle).decode()
-    assert "x[0] = ((x0 + (c[3] * (c[1] - x0))) + ((c[2] * SDE_SQRT(x0)) * dw[0]));" in src   # no common factor: sum of folded terms
+    assert "c[3] = ((T)1 + (((T)(-1) * c[0]) * dt));" in src and "c[4] = ((c[0] * dt) * c[1]);" in src
+    assert "x[0] = ((x0 * c[3]) + (c[4] + ((c[2] * SDE_SQRT(x0)) * dw[0])));" in src   # mean reversion: x*(1 - κΔt) + (κθΔt + noise)
     src = L.sdeb200_model_cuda_source(build(S, "TimeDependent")._handle).decode()
     assert "(c[2] * t)" in src                                       # t stays a per-step factor
