@@ -642,6 +642,7 @@ template <class Model> struct PolarOf {
 template <class Model, typename T, int V> struct Noise {
   typedef Batch<T, Model::M, V> B;
   static constexpr bool POLAR = PolarOf<Model>::value != 0 && Model::M == 2 && !SDE_STRICT;
+  static constexpr bool POLAR2 = POLAR && PolarOf<Model>::value >= 2;   // Model::step_polar2: a coarse step from two triples
   static constexpr int STRIDE = POLAR ? 3 : (Model::M > 0 ? Model::M : 0);
   static constexpr int NV = POLAR ? 3 * B::U : B::NZ;   // values per batch
 };
@@ -649,6 +650,7 @@ template <class Model, int SCHEME, bool POLAR, int V = 1> struct NoiseStep {
   template <typename T> SDE_HD static void run(const T *c, T t, T dt, const T *nz, T *x) {
     Model::template step<SCHEME>(c, t, dt, nz, x);
   }
+  template <typename T> SDE_HD static void run2(const T *, T, T, const T *, const T *, T *) {}   // never taken (POLAR2 false)
   template <typename T> SDE_HD static void increments(const T *nz, T *dw) {
 #if defined(__CUDACC__)
 #pragma unroll
@@ -659,6 +661,9 @@ template <class Model, int SCHEME, bool POLAR, int V = 1> struct NoiseStep {
 template <class Model, int SCHEME, int V> struct NoiseStep<Model, SCHEME, true, V> {
   template <typename T> SDE_HD static void run(const T *c, T t, T dt, const T *nz, T *x) {
     Model::step_polar(c, t, dt, nz[0], nz[1], nz[2], x);
+  }
+  template <typename T> SDE_HD static void run2(const T *c, T t, T dt, const T *na, const T *nb, T *x) {
+    Model::step_polar2(c, t, dt, na, nb, x);
   }
   // the pair itself, exactly as normal_pair_f64 / normal_pair_f64_v2 / normal_pair_f32 form it
   SDE_HD static void increments(const double *nz, double *dw) {
@@ -1205,12 +1210,19 @@ SDE_D void mlmc_body(const sde_args &a) {
         const T tc = t0 + (T)(gi * (G / 2) + j / 2) * dtc;
         const T tf = tc + (T)(j & 1) * dtf;
         const T *nzu = dw[j / B::U] + (j % B::U) * NS::STRIDE;
-        T dwu[M > 0 ? M : 1];
-        NoiseStep<Model, SCHEME, NS::POLAR, V>::increments(nzu, dwu);
+        if (NS::POLAR2) {
+          // the coarse step straight from the two polar triples of its fine steps (Model::step_polar2): no increments,
+          // no sum ΔW, one square root per fine increment instead of radius + radius + model root
+          NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cf.c, tf, dtf, nzu, xf);
+          if (j & 1) NoiseStep<Model, SCHEME, NS::POLAR2, V>::run2(cc.c, tc, dtc, dw[(j - 1) / B::U] + ((j - 1) % B::U) * NS::STRIDE, nzu, xc);
+        } else {
+          T dwu[M > 0 ? M : 1];
+          NoiseStep<Model, SCHEME, NS::POLAR, V>::increments(nzu, dwu);
 #pragma unroll
-        for (int q = 0; q < M; q++) DW[q] = ((j & 1) ? DW[q] : (T)0) + dwu[q];
-        NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cf.c, tf, dtf, nzu, xf);
-        if (j & 1) Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
+          for (int q = 0; q < M; q++) DW[q] = ((j & 1) ? DW[q] : (T)0) + dwu[q];
+          NoiseStep<Model, SCHEME, NS::POLAR, V>::run(cf.c, tf, dtf, nzu, xf);
+          if (j & 1) Model::template step<SCHEME>(cc.c, tc, dtc, DW, xc);
+        }
       }
     }
     it = ngroups * NBG;

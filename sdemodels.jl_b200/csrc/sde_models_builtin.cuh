@@ -158,7 +158,19 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
   // Polar form of the step (FAST math, FP64, either normal stream: sde_device.cuh, Noise<>): both noise terms carry
   // sqrt(V) sqrt(w), so ONE square root of V*w replaces the radius' and the model's (7 FP64 operations and one MUFU fewer
   // per step; sqrt(V w) is rounded once, sqrt(V) sqrt(w) three times).  V < 0 still gives a non-finite state.
-  static constexpr int POLAR = 1;
+  static constexpr int POLAR = 2;   // 1: step_polar; 2: step_polar2 as well
+  // One step over the SUM of two increments given as polar triples a, b (the coarse step of a coupled level with two
+  // substeps, multilevel.jl:79-86): sqrt(V)(dWa + dWb) = sqrt(V wa)(ca, sb)_a + sqrt(V wb)(ca, sb)_b — two roots instead
+  // of the two radii plus sqrt(V), and the sum ΔW is never formed.  c = the constants of the coarse Δt.
+  template <typename T> SDE_HD static void step_polar2(const T *c, T t, T dt, const T *a, const T *b, T *x) {
+    (void)t;
+    (void)dt;
+    const T S = x[0], V = x[1];
+    const T Ga = sqrt_fast(V * a[0]), Gb = sqrt_fast(V * b[0]);
+    x[0] = sde_fma(S, sde_fma(Gb, b[1], sde_fma(Ga, a[1], c[0])), S);
+    const T na = sde_fma(c[4], a[2], c[3] * a[1]), nb = sde_fma(c[4], b[2], c[3] * b[1]);
+    x[1] = sde_fma(Gb, nb, sde_fma(Ga, na, sde_fma(V, c[1], c[2])));
+  }
   template <typename T> SDE_HD static void step_polar(const T *c, T t, T dt, T w, T ca, T sb, T *x) {
     (void)t;
     (void)dt;

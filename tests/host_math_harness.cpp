@@ -95,7 +95,8 @@ extern "C" void h_rcp_fast(const double *x, int64_t n, double *out) {
 // version = normal stream (1: words r[0..3] of one Philox block, 2: words (3P, 3P+1, 3P+2))
 extern "C" void h_heston_polar(int version, const double *params, double dt, const uint32_t *words, const double *x_in, double *x_polar,
                                double *x_plain) {
-  static_assert(PolarOf<Heston>::value == 1 && PolarOf<BlackScholes>::value == 0, "only Heston declares the polar form");
+  static_assert(PolarOf<Heston>::value == 2 && PolarOf<BlackScholes>::value == 0, "only Heston declares the polar forms");
+  static_assert(Noise<Heston, double, 2>::POLAR2 && Noise<Heston, float, 1>::POLAR2 && !Noise<BlackScholes, double, 2>::POLAR2, "");
   static_assert(Noise<Heston, double, 2>::POLAR && Noise<Heston, double, 1>::POLAR && Noise<Heston, float, 2>::POLAR, "both precisions, both streams");
   static_assert(Noise<Heston, double, 2>::NV == 12 && Noise<Heston, double, 1>::NV == 3 && Noise<Heston, float, 1>::NV == 6 &&
                 Noise<BlackScholes, double, 2>::NV == 8 && !Noise<BlackScholes, float, 1>::POLAR, "values per batch");
@@ -136,4 +137,23 @@ extern "C" void h_heston_polar_f32(const float *params, float dt, const uint32_t
   x_polar[1] = x_plain[1] = x_in[1];
   NoiseStep<Heston, 0, true, 1>::run(c, 0.0f, dt, nz, x_polar);
   NoiseStep<Heston, 0, false, 1>::run(c, 0.0f, dt, z, x_plain);
+}
+// the coarse step of a coupled level with two substeps from the two polar triples (Heston::step_polar2) beside the reference
+// form: increments summed from zero, then one plain step (multilevel.jl:79-86); stream v2 words of the two fine pairs
+extern "C" void h_heston_polar2(const double *params, double dt_fine, const uint32_t *wa, const uint32_t *wb, const double *x_in,
+                                double *x_p2, double *x_plain) {
+  static double tab[SDE_TAB2_DOUBLES];
+  double lk[6], c[SDE_MAXC], na[3], nb[3], za[2], zb[2];
+  h_scaled_tables_v2(dt_fine, tab);
+  make_log_consts_v2(dt_fine, lk);
+  Heston::prepare(params, 2.0 * dt_fine, c);
+  normal_polar_f64_v2(wa[0], wa[1], wa[2], tab, lk, na[0], na[1], na[2]);
+  normal_polar_f64_v2(wb[0], wb[1], wb[2], tab, lk, nb[0], nb[1], nb[2]);
+  NoiseStep<Heston, 0, true, 2>::increments(na, za);
+  NoiseStep<Heston, 0, true, 2>::increments(nb, zb);
+  const double DW[2] = {(0.0 + za[0]) + zb[0], (0.0 + za[1]) + zb[1]};
+  x_p2[0] = x_plain[0] = x_in[0];
+  x_p2[1] = x_plain[1] = x_in[1];
+  NoiseStep<Heston, 0, true, 2>::run2(c, 0.0, 2.0 * dt_fine, na, nb, x_p2);
+  NoiseStep<Heston, 0, false, 2>::run(c, 0.0, 2.0 * dt_fine, DW, x_plain);
 }

@@ -182,3 +182,25 @@ def test_heston_polar_step_fp32(H):
     assert worst <= 2.0, worst
     H.h_heston_polar_f32(params, C.c_float(dt), (C.c_uint32 * 2)(1, 2), (C.c_float * 2)(100.0, -0.01), xp, xq)
     assert not np.isfinite(xp[0]) and not np.isfinite(xp[1])
+
+
+def test_heston_coarse_step_from_two_polar_triples(H):
+    """Heston::step_polar2 (the coarse step of a coupled level with two substeps taken straight from the two polar triples
+    of its fine steps) against the reference form — the increments summed from zero, then one plain step: a few ulps of
+    the new state apart, equal at V = 0, non-finite for V < 0."""
+    rng = np.random.default_rng(14)
+    params = (C.c_double * 5)(0.01, 10.0, 0.3, 0.1, 0.4)
+    dtf, worst = 1.0 / 1024, 0.0
+    xp, xq = (C.c_double * 2)(), (C.c_double * 2)()
+    for i in range(4000):
+        wa = (C.c_uint32 * 3)(*[int(v) for v in rng.integers(0, 2 ** 32, 3)])
+        wb = (C.c_uint32 * 3)(*[int(v) for v in rng.integers(0, 2 ** 32, 3)])
+        S, V = 100.0 * np.exp(rng.standard_normal()), (0.4 * rng.random() ** 4 if i % 50 else 0.0)
+        H.h_heston_polar2(params, C.c_double(dtf), wa, wb, (C.c_double * 2)(S, V), xp, xq)
+        for d in (0, 1):
+            worst = max(worst, abs(xp[d] - xq[d]) / (2.0 ** -52 * abs(xq[d])) if xq[d] != 0 else abs(xp[d]))
+        if V == 0.0:
+            assert xp[0] == xq[0] and xp[1] == xq[1]
+    assert worst <= 4.0, worst
+    H.h_heston_polar2(params, C.c_double(dtf), (C.c_uint32 * 3)(1, 2, 3), (C.c_uint32 * 3)(4, 5, 6), (C.c_double * 2)(100.0, -0.01), xp, xq)
+    assert not np.isfinite(xp[0]) and not np.isfinite(xp[1])
