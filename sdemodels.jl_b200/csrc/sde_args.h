@@ -116,11 +116,15 @@ SDE_ARGS_HD int sde_tma_head(int j, int64_t pitch_bytes, int rowb, int align = 1
                                  (profiles/r02u_k2u_prefetch_ab.txt): FP32 6.00 vs 5.99 ms (ptxas keeps the two chains apart anyway),
                                  FP64 14.9 vs 10.6 ms (eight more live doubles at the 128-register cap): off */
 #endif
+/* K2u ring depth (tiles in flight per warp).  Measured on C3 after the sector-aligned tiles (profiles/r02zz_c3_ring_depth_*.txt):
+ * FP32 (2 KB tiles) 2 / 3 / 4 / 5 / 6 / 8 stages: 3.31 / 3.32 / 3.43 / 3.51 / 3.67 / 3.39 TB/s — 6 stages = 48 KB per CTA, 16
+ * warps per SM; FP64 (4 KB tiles) 2 / 3 / 4 / 6 stages: 3.89 / 3.24 / 3.18 / 2.33 — the FP64 form needs its warps more than
+ * stores in flight */
 #ifndef SDE_SIMRT2_STAGES_F64
 #define SDE_SIMRT2_STAGES_F64 2
 #endif
 #ifndef SDE_SIMRT2_STAGES_F32
-#define SDE_SIMRT2_STAGES_F32 4
+#define SDE_SIMRT2_STAGES_F32 6
 #endif
 /* K2u: how a finished tile leaves shared memory — 0: one tensor store by lane 0 (asynchronous, STAGES deep ring),
  * 1: 8 x (LDS.128 + STG.128) by the whole warp (synchronous, one stage) */

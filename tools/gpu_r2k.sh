@@ -1,11 +1,11 @@
 #!/bin/bash
+# per-instruction stall sampling of the reference-order FP32 trajectory kernel (K2u) and the [time][path] FP32 kernel
 mkdir -p gpurun_out
-SDEB200_LIB=variants/libsdeb200_man64.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "reference_order or layouts_agree" > gpurun_out/pytest_r2k.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_r2k.log
-tail -n 4 gpurun_out/pytest_r2k.log
-for v in cur man32 man64; do
-if [ $v = cur ]; then L=""; else L="variants/libsdeb200_$v.so"; fi
-for r in 0 2; do for p in f64 f32; do
-if [ $r = 0 ] && [ $p = f32 ]; then continue; fi
-if [ $v = man32 ] && [ $p = f64 ]; then continue; fi
-echo "== $v rng=$r $p"; SDEB200_LIB=$L SDEB200_RNG=$r timeout 300 python tools/prof_sample.py $p 10000000 fullpath 2>&1 | grep " 1 " | awk '{print "   ", $1, $3, $(NF-1), $NF}'
-done; done; done 2>&1 | tee gpurun_out/c3_r2k.log
+export SDEB200_RNG=2
+for m in simref32 simsoa32; do
+  case $m in simref32) K=sdek_bs_f_simrt_mil_f32;; simsoa32) K=sdek_bs_f_simsoa_mil_f32;; esac
+  timeout 300 python tools/prof_kernels.py $m > gpurun_out/src_${m}_plain.log 2>&1 &&
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 1 -c 1 -f -o /tmp/prof_src_$m python tools/prof_kernels.py $m > gpurun_out/src_${m}_ncu.log 2>&1
+  ncu -i /tmp/prof_src_$m.ncu-rep --page source --csv > gpurun_out/r02zz_${m}_source.csv 2>/dev/null
+  ls -la gpurun_out/r02zz_${m}_source.csv
+done
