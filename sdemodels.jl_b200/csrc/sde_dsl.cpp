@@ -846,7 +846,9 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
     //   reversion) are expanded first; then c' = 1 + (sum of parameter-only coefficients of x_i), A = the coefficients of
     //   x_i that vary per step, cB = the sum of the parameter-only terms, B = the remaining terms.  Geometric rows come out
     //   as x*A + x, mean-reverting ones as x*c' + (cB + noise): one FMA each.
-    auto fast_row = [&](int i, const std::vector<std::vector<E>> &terms) {
+    //   The expansion of mean reversion is for Float64 only (`expand`): in FP32, 1 - κΔt rounded to 24 bits carries κΔt to
+    //   only 2^-24 / (κΔt) relative and would shift the reversion level by that much at every step; FP32 keeps x + c (a - x).
+    auto fast_row = [&](int i, const std::vector<std::vector<E>> &terms, bool expand) {
       const E xi = mk_sym(vars[i]);
       auto dynamic = [&](const E &e) { return depends_on(e, dyn2); };
       std::vector<std::vector<E>> ex;
@@ -855,7 +857,7 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
         for (size_t k = 0; k < f.size(); k++)
           if (dynamic(f[k])) { ndyn++; idx = (int)k; }
         bool done = false;
-        if (ndyn == 1 && f[idx]->kind == Expr::CALL && (f[idx]->name == "+" || (f[idx]->name == "-" && f[idx]->args.size() == 2))) {
+        if (expand && ndyn == 1 && f[idx]->kind == Expr::CALL && (f[idx]->name == "+" || (f[idx]->name == "-" && f[idx]->args.size() == 2))) {
           const E &g = f[idx];
           std::vector<E> st;
           int sx = 0;
@@ -914,13 +916,14 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
       if (rest.empty()) return core;
       return mk_call("+", {core, sum_of(rest)});
     };
-    std::vector<E> fast_em(D), fast_polar(D);
+    std::vector<E> fast_em(D), fast_polar(D), fast_em32(D), fast_polar32(D);
     for (int i = 0; i < D; i++) {
       std::vector<std::vector<E>> terms;
       if (!is_val(drift[i], 0)) { auto f = flat(drift[i]); f.push_back(mk_sym("dt")); terms.push_back(f); }
       for (int j = 0; j < M; j++)
         if (!is_val(diffm[i][j], 0)) { auto f = flat(diffm[i][j]); f.push_back(mk_sym("__dw" + std::to_string(j))); terms.push_back(f); }
-      fast_em[i] = fast_row(i, terms);
+      fast_em[i] = fast_row(i, terms, true);
+      fast_em32[i] = fast_row(i, terms, false);
       if (have_polar) {
         // the noise of the row as ONE term G * N_i; x_i is common only if it is a factor of every rest_ij
         const E xi = mk_sym(vars[i]);
@@ -955,7 +958,8 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
           if (common) nf.push_back(xi);
           pt.push_back(nf);
         }
-        fast_polar[i] = fast_row(i, pt);
+        fast_polar[i] = fast_row(i, pt, true);
+        fast_polar32[i] = fast_row(i, pt, false);
       }
     }
     const int NP = (int)params.size();
@@ -998,8 +1002,11 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
     o << "    (void)c; (void)t; (void)dw;\n";
     for (int i = 0; i < D; i++) o << "    const T x" << i << " = x[" << i << "];  // " << vars[i] << "\n";
     o << "#if !SDE_STRICT\n    if (SCHEME == 0) {  // FAST math: folded constants, common state factor (same algebra as below)\n";
-    for (int i = 0; i < D; i++) o << "      x[" << i << "] = " << ef.ex(fast_em[i]) << ";\n";
-    o << "      return;\n    }\n#endif\n";
+    o << "      if (sizeof(T) == 8) {\n";
+    for (int i = 0; i < D; i++) o << "        x[" << i << "] = " << ef.ex(fast_em[i]) << ";\n";
+    o << "      } else {  // FP32: mean reversion stays x + c (a - x)\n";
+    for (int i = 0; i < D; i++) o << "        x[" << i << "] = " << ef.ex(fast_em32[i]) << ";\n";
+    o << "      }\n      return;\n    }\n#endif\n";
     for (int i = 0; i < D; i++) o << "    const T mu" << i << " = " << em.ex(hdrift[i]) << ";\n";
     for (int i = 0; i < D; i++)
       for (int j = 0; j < M; j++)
@@ -1054,7 +1061,11 @@ bool sde_dsl_build(const std::string &name, const std::string &eqs, const std::v
       o << "    (void)c; (void)t; (void)dt;\n";
       for (int i = 0; i < D; i++) o << "    const T x" << i << " = x[" << i << "];  // " << vars[i] << "\n";
       o << "    const T G = SDE_SQRT(" << em.ex(polar_arg) << " * w);\n";
-      for (int i = 0; i < D; i++) o << "    x[" << i << "] = " << ef.ex(fast_polar[i]) << ";\n";
+      o << "    if (sizeof(T) == 8) {\n";
+      for (int i = 0; i < D; i++) o << "      x[" << i << "] = " << ef.ex(fast_polar[i]) << ";\n";
+      o << "    } else {\n";
+      for (int i = 0; i < D; i++) o << "      x[" << i << "] = " << ef.ex(fast_polar32[i]) << ";\n";
+      o << "    }\n";
       o << "  }\n";
     }
     // drift / diffusion at a point, double precision, un-hoisted

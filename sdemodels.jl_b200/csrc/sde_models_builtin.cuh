@@ -25,6 +25,20 @@ SDE_HD float sde_exp(float v) { return expf(v); }
 SDE_HD double sde_log(double v) { return log(v); }
 SDE_HD float sde_log(float v) { return logf(v); }
 
+// x + κΔt (θ - x), FAST math.  Float64: x (1 - κΔt) + κθΔt, one FMA (the rounding of 1 - κΔt, 2^-53, is harmless).  FP32 keeps
+// the difference form: 1 - κΔt rounded to 24 bits would carry κΔt itself to only 2^-24 / (κΔt) relative — 6e-4 for κΔt =
+// 1e-4 — and shift the level the state reverts to by that much, the same way at every step.
+SDE_HD double mean_reversion(double x, double one_minus_kdt, double kthdt, double kdt, double theta) {
+  (void)kdt;
+  (void)theta;
+  return fma(x, one_minus_kdt, kthdt);
+}
+SDE_HD float mean_reversion(float x, float one_minus_kdt, float kthdt, float kdt, float theta) {
+  (void)one_minus_kdt;
+  (void)kthdt;
+  return fmaf(kdt, theta - x, x);
+}
+
 struct BlackScholes {  // dS = r*S*dt + σ*S*dW, params (r, σ)
   static constexpr int D = 1, M = 1, NP = 2;
   template <typename T> SDE_HD static void prepare(const T *p, T dt, T *c) {
@@ -90,6 +104,7 @@ struct OrnsteinUhlenbeck {  // dx = θ*(μ-x)*dt + σ*dW, params (θ, μ, σ)   
 #if !SDE_STRICT
     c[6] = (T)1 - p[0] * dt;   // 1 - θΔt
     c[7] = p[0] * p[1] * dt;   // θμΔt
+    c[8] = p[0] * dt;          // θΔt (FP32: see mean_reversion)
 #endif
   }
   template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
@@ -111,7 +126,7 @@ struct OrnsteinUhlenbeck {  // dx = θ*(μ-x)*dt + σ*dW, params (θ, μ, σ)   
     // left to choose, so every kernel form produces the same bits
     (void)dt;
     if (SCHEME == 3) x[0] = sde_fma(c[5], w, sde_fma(X, c[3], c[4]));
-    else x[0] = sde_fma(c[2], w, sde_fma(X, c[6], c[7]));   // the Milstein / RungeKutta corrections are exactly 0
+    else x[0] = sde_fma(c[2], w, mean_reversion(X, c[6], c[7], c[8], c[1]));   // the Milstein / RungeKutta corrections are exactly 0
 #endif
   }
   SDE_HD static void coefficients(const double *p, double t, const double *x, double *mu, double *sig) {
@@ -134,6 +149,8 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
     c[2] = p[1] * p[2] * dt;               // κ θ Δt
     c[3] = p[3] * p[4];                    // σ ρ
     c[4] = p[3] * sde_sqrt((T)1 - p[4] * p[4]);  // σ sqrt(1 - ρ²)
+    c[5] = p[1] * dt;                      // κ Δt   (FP32: see mean_reversion)
+    c[6] = p[2];                           // θ
 #endif
   }
   template <int SCHEME, typename T> SDE_HD static void step(const T *c, T t, T dt, const T *dw, T *x) {
@@ -151,7 +168,7 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
     const T sv = sqrt_fast(V);  // <= 1 ulp, branch-free; sqrt(0) = 0, sqrt(V < 0) = NaN like the reference's DomainError
     x[0] = sde_fma(S, sde_fma(sv, dw[0], c[0]), S);
     const T n = sde_fma(c[4], dw[1], c[3] * dw[0]);
-    x[1] = sde_fma(sv, n, sde_fma(V, c[1], c[2]));
+    x[1] = sde_fma(sv, n, mean_reversion(V, c[1], c[2], c[5], c[6]));
 #endif
   }
 #if !SDE_STRICT
@@ -169,7 +186,7 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
     const T Ga = sqrt_fast(V * a[0]), Gb = sqrt_fast(V * b[0]);
     x[0] = sde_fma(S, sde_fma(Gb, b[1], sde_fma(Ga, a[1], c[0])), S);
     const T na = sde_fma(c[4], a[2], c[3] * a[1]), nb = sde_fma(c[4], b[2], c[3] * b[1]);
-    x[1] = sde_fma(Gb, nb, sde_fma(Ga, na, sde_fma(V, c[1], c[2])));
+    x[1] = sde_fma(Gb, nb, sde_fma(Ga, na, mean_reversion(V, c[1], c[2], c[5], c[6])));
   }
   template <typename T> SDE_HD static void step_polar(const T *c, T t, T dt, T w, T ca, T sb, T *x) {
     (void)t;
@@ -178,7 +195,7 @@ struct Heston {  // dS = r*S*dt + sqrt(V)*S*dW1 ; dV = κ*(θ-V)*dt + σ*sqrt(V)
     const T G = sqrt_fast(V * w);
     x[0] = sde_fma(S, sde_fma(G, ca, c[0]), S);
     const T n = sde_fma(c[4], sb, c[3] * ca);
-    x[1] = sde_fma(G, n, sde_fma(V, c[1], c[2]));
+    x[1] = sde_fma(G, n, mean_reversion(V, c[1], c[2], c[5], c[6]));
   }
 #endif
   SDE_HD static void coefficients(const double *p, double t, const double *x, double *mu, double *sig) {

@@ -157,3 +157,16 @@ extern "C" void h_heston_polar2(const double *params, double dt_fine, const uint
   NoiseStep<Heston, 0, true, 2>::run2(c, 0.0, 2.0 * dt_fine, na, nb, x_p2);
   NoiseStep<Heston, 0, false, 2>::run(c, 0.0, 2.0 * dt_fine, DW, x_plain);
 }
+// the variance row of the Heston FAST step without noise (dw = 0), FP32 and Float64: mean reversion only
+extern "C" float h_heston_drift_f32(const float *params, float dt, float V) {
+  float c[SDE_MAXC], x[2] = {100.0f, V}, dw[2] = {0.0f, 0.0f};
+  Heston::prepare(params, dt, c);
+  Heston::step<0>(c, 0.0f, dt, dw, x);
+  return x[1];
+}
+extern "C" double h_heston_drift_f64(const double *params, double dt, double V) {
+  double c[SDE_MAXC], x[2] = {100.0, V}, dw[2] = {0.0, 0.0};
+  Heston::prepare(params, dt, c);
+  Heston::step<0>(c, 0.0, dt, dw, x);
+  return x[1];
+}

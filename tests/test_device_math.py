@@ -204,3 +204,25 @@ def test_heston_coarse_step_from_two_polar_triples(H):
     assert worst <= 4.0, worst
     H.h_heston_polar2(params, C.c_double(dtf), (C.c_uint32 * 3)(1, 2, 3), (C.c_uint32 * 3)(4, 5, 6), (C.c_double * 2)(100.0, -0.01), xp, xq)
     assert not np.isfinite(xp[0]) and not np.isfinite(xp[1])
+
+
+def test_fp32_mean_reversion_keeps_its_level(H):
+    """FAST math, FP32: the variance row reverts as V + κΔt (θ - V), not as V (1 - κΔt) + κθΔt — with 1 - κΔt rounded to
+    24 bits the second form carries κΔt to only 2^-24 / (κΔt) relative and moves the level the state reverts to.  The
+    level θ is an exact fixed point of the FP32 drift for any κ, Δt, and a step from 2θ is the once-rounded 2θ - κΔt θ;
+    Float64 uses the one-FMA form, where the same effect stays at rounding level."""
+    H.h_heston_drift_f32.restype = C.c_float
+    H.h_heston_drift_f64.restype = C.c_double
+    rng = np.random.default_rng(15)
+    f32 = np.float32
+    for _ in range(300):
+        kappa, theta = float(f32(rng.uniform(0.1, 12.0))), float(f32(rng.uniform(0.01, 0.5)))
+        dt = float(f32(2.0 ** -rng.integers(6, 17) * rng.uniform(0.5, 1.0)))
+        p32 = (C.c_float * 5)(0.01, kappa, theta, 0.1, 0.4)
+        assert H.h_heston_drift_f32(p32, C.c_float(dt), C.c_float(theta)) == f32(theta)
+        v1 = float(H.h_heston_drift_f32(p32, C.c_float(dt), C.c_float(2 * theta)))
+        kdt = float(f32(f32(kappa) * f32(dt)))
+        exact = 2 * theta - kdt * theta                       # in double, from the float-rounded κΔt
+        assert abs(v1 - exact) <= 2.0 ** -23 * 2 * theta      # one float rounding of the result (the expanded form: up to 2^-24 θ / 1 per unit of κΔt more)
+        p64 = (C.c_double * 5)(0.01, kappa, theta, 0.1, 0.4)
+        assert abs(H.h_heston_drift_f64(p64, C.c_double(dt), C.c_double(theta)) / theta - 1.0) <= 3e-16

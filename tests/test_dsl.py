@@ -296,5 +296,8 @@ def test_fast_forms_of_the_generated_update(S):
     src = L.sdeb200_model_cuda_source(build(S, "CoxIngersollRoss")._handle).decode()
     assert "c[3] = ((T)1 + (((T)(-1) * c[0]) * dt));" in src and "c[4] = ((c[0] * dt) * c[1]);" in src
     assert "x[0] = ((x0 * c[3]) + (c[4] + ((c[2] * SDE_SQRT(x0)) * dw[0])));" in src   # mean reversion: x*(1 - κΔt) + (κθΔt + noise)
+    # ... in Float64 only: FP32 keeps x + κΔt (θ - x), whose level θ does not move with the rounding of 1 - κΔt
+    assert "} else {  // FP32: mean reversion stays x + c (a - x)" in src
+    assert "x[0] = (x0 + ((c[5] * (c[1] - x0)) + ((c[2] * SDE_SQRT(x0)) * dw[0])));" in src
     src = L.sdeb200_model_cuda_source(build(S, "TimeDependent")._handle).decode()
     assert "(c[2] * t)" in src                                       # t stays a per-step factor
