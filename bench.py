@@ -320,7 +320,7 @@ def main():
         if key in sass:
             fl = sass[key]["fp_flops_per_path_step"]
             roofline["executed_flops_per_path_step"] = fl
-            roofline["executed_frac"] = rate1 * fl / 1e12 / peak_tf
+            roofline["executed_frac"] = rate1 * fl / 1e12 / peak_used   # the same denominator as `frac`
         line = {
             "metric": METRIC, "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
